@@ -1,0 +1,225 @@
+/*
+ * rtx_b200.h — C ABI of the B200-native ray-tracing hot path.
+ *
+ * This is the drop-in boundary for the reference's only seam on this path:
+ *
+ *   void rt_scene(std::vector<vec3> u, const std::vector<std::unique_ptr<SceneGeometry>>& scene,
+ *                 const Camera& cam, std::vector<std::vector<RGB>>& frame_buffer)   (main.cpp:124-139)
+ *   followed by the 8-bit quantise loop                                              (main.cpp:338-347)
+ *
+ * The reference has no FFI; every entry point below names the reference code it
+ * replaces. Plain pointers and sizes only — no C++ or torch types cross this line.
+ * All reference arithmetic is IEEE double (vec.h:15), so every POD here is double.
+ *
+ * Conventions (mirroring main.cpp:329): calls are synchronous and blocking; the
+ * caller owns and pre-allocates every output, the callee overwrites every pixel;
+ * the scene is copied by rtx_set_scene (caller keeps ownership). Errors are int
+ * status codes (0 = ok) plus rtx_last_error(); nothing is thrown across the ABI.
+ * Calls on one context must be serialised by the caller (the reference is single
+ * threaded); different contexts (GPUs) may be driven from different host threads.
+ *
+ * There is NO CPU fallback: every compute entry point fails with RTX_ERR_CUDA when
+ * no sm_100-class device is usable.
+ */
+#ifndef RTX_B200_H
+#define RTX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTX_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------- */
+#define RTX_OK              0
+#define RTX_ERR_INVALID     1   /* bad argument (null pointer, negative size, H/W <= 0 ...) */
+#define RTX_ERR_CUDA        2   /* CUDA runtime error or no usable device */
+#define RTX_ERR_NO_SCENE    3   /* rtx_render before rtx_set_scene */
+#define RTX_ERR_NOMEM       4   /* host or device allocation failed */
+
+/* ---- PODs ---------------------------------------------------------------- */
+
+/* vec3 / point3 / RGB (vec.h:12-40): three doubles. */
+typedef struct rtx_vec3 { double x, y, z; } rtx_vec3;
+
+/* Material (scene.h:35-49); same field order as the reference struct.
+ * Reference ctor order is (color, metallic=.5, ambient=.1, diffuse=.9, specular=.4,
+ * specular_exponent=50) (scene.h:48). */
+typedef struct rtx_material {
+    rtx_vec3 color;
+    double ambient;
+    double metallic;
+    double diffuse;
+    double specular;
+    double specular_exponent;
+} rtx_material;
+
+#define RTX_SPHERE 0   /* Sphere(Material, point3 center, double radius)              scene.h:75-84  */
+#define RTX_WALL   1   /* Wall(Material, point3 position, vec3 normal, length, width) scene.h:62-73  */
+
+/* One entry of the reference's std::vector<std::unique_ptr<SceneGeometry>> (main.cpp:156-163).
+ * The array index IS the object id (hit_object_index, main.cpp:80) and the tie-break order
+ * (strict '<' in main.cpp:77 => lowest index wins equal distances). */
+typedef struct rtx_object {
+    int32_t      kind;     /* RTX_SPHERE | RTX_WALL */
+    int32_t      reserved; /* must be 0 */
+    rtx_material mat;
+    rtx_vec3     p;        /* sphere: center            | wall: corner 'position' (scene.h:64) */
+    rtx_vec3     n;        /* sphere: ignored           | wall: normal AS PASSED to the ctor; the library
+                              normalises it exactly as scene.h:71 does (n / sqrt(n.n)) */
+    double       a;        /* sphere: radius            | wall: length */
+    double       b;        /* sphere: ignored           | wall: width  */
+} rtx_object;
+
+/* Inputs of Camera::init (scene.h:94-99, main.cpp:146-153). image_width/aspect_ratio are doubles
+ * in the reference (scene.h:95). */
+typedef struct rtx_camera_desc {
+    rtx_vec3 position, lookat, vup;
+    double   vfov;          /* degrees; converted with 3.14/180 (scene.cpp:84), NOT pi */
+    double   aspect_ratio;
+    double   image_width;
+} rtx_camera_desc;
+
+/* What Camera::init yields and rt_scene consumes (scene.cpp:80-106, main.cpp:132-134):
+ * pixel (row i, col j) has centre image_top_left + delta_x*j + delta_y*i; the primary ray is
+ * origin = position, direction = position - centre (unnormalised). */
+typedef struct rtx_camera {
+    rtx_vec3 position;
+    rtx_vec3 image_top_left;
+    rtx_vec3 delta_x;        /* u[0], scene.cpp:99  */
+    rtx_vec3 delta_y;        /* u[1], scene.cpp:100 */
+    int32_t  width;          /* columns j, image_width  */
+    int32_t  height;         /* rows i,    image_height = int(image_width / aspect_ratio), scene.cpp:82 */
+} rtx_camera;
+
+#define RTX_QUANT_WRAP     0  /* reference: implicit double->Uint8, truncation, wraps mod 256 (main.cpp:345) */
+#define RTX_QUANT_SATURATE 1  /* labelled non-parity option: clamp to [0,255] */
+
+/* Compile-time constants of the reference, exposed as run-time parameters.
+ * rtx_default_params() fills in the reference literals. */
+typedef struct rtx_params {
+    int32_t  max_depth;        /* remaining_iterations, default 10 (main.cpp:89); <= RTX_MAX_DEPTH */
+    int32_t  quantise_mode;    /* RTX_QUANT_* */
+    int32_t  fuse_quantise;    /* 1: trace kernel writes rgba8 itself; 0: radiance buffer + quantise kernel */
+    int32_t  reserved;
+    rtx_vec3 light_pos;        /* LIGHT_POS      (0,0,0)            main.cpp:14 */
+    rtx_vec3 ground_color;     /* GROUND_COLOR   (.025,.05,.075)    main.cpp:15 */
+    rtx_vec3 sky_low;          /* SKYCOLOR_LOW   (.36,.45,.57)      main.cpp:16 */
+    rtx_vec3 sky_high;         /* SKYCOLOR_HIGH  (.14,.21,.49)      main.cpp:17 */
+    double   reflect_offset;   /* .0001                             main.cpp:111 */
+    double   sky_exponent;     /* 1./4. (as float -> 0.25 exactly)  main.cpp:34 */
+    /* Row sharding for one big frame split over several GPUs (one context per GPU).
+     * Rows are grouped in bands of band_rows; band b belongs to rank (b mod n_ranks).
+     * A rank renders only its own rows, packed in increasing row order.
+     * n_ranks = 1 renders the whole frame. */
+    int32_t  band_rows;
+    int32_t  n_ranks;
+    int32_t  rank;
+    int32_t  reserved2;
+} rtx_params;
+
+#define RTX_MAX_DEPTH 254     /* ray_count is a uint8: depth+1 rays per pixel at most */
+
+#define RTX_MEM_HOST   0
+#define RTX_MEM_DEVICE 1
+
+/* Output planes, each optional (NULL = not wanted), caller-allocated, all of them either host or
+ * device pointers (memory). Shapes are [n_frames][rows][width] where rows = height when n_ranks = 1,
+ * else rtx_local_rows(height, band_rows, n_ranks, rank). */
+typedef struct rtx_outputs {
+    uint32_t* rgba8;         /* R<<24 | G<<16 | B<<8 | 0xFF : SDL RGBA8888 surface word (main.cpp:193,345) */
+    float*    radiance_f32;  /* [..][3] frame_buffer value (main.cpp:136) rounded to float */
+    double*   radiance_f64;  /* [..][3] frame_buffer value in double */
+    int32_t*  object_id;     /* primary-ray hit_object_index (main.cpp:80), -1 = miss */
+    uint8_t*  hit_mask;      /* 1 iff the primary ray hit anything */
+    uint8_t*  ray_count;     /* rays traced for the pixel (primary + reflections), 1..max_depth+1 */
+    int32_t   memory;        /* RTX_MEM_HOST | RTX_MEM_DEVICE */
+    int32_t   reserved;
+} rtx_outputs;
+
+/* Device-side timing and diagnostics of the last rtx_render / rtx_quantise on a context.
+ * Stage names follow the reference's log (main.cpp:386-391): "raytracing" = trace, "surface update" = quantise. */
+typedef struct rtx_stats {
+    double   raytracing_ms;      /* trace kernel(s), CUDA events */
+    double   surface_update_ms;  /* quantise kernel (0 when fused) */
+    double   h2d_ms;             /* camera upload */
+    double   d2h_ms;             /* output download (RTX_MEM_HOST only) */
+    double   total_ms;           /* first event to last event */
+    uint64_t total_rays;         /* sum of ray_count over all pixels rendered by this call */
+    uint64_t sphere_tests;       /* total_rays * n_spheres */
+    uint64_t wall_tests;         /* total_rays * n_walls   */
+    uint64_t over_range_pixels;  /* pixels with a channel outside [0, 256/255): quantise wraps there */
+    double   max_luminance;      /* max over pixels of (R+G+B)/3; diagnostic only, never alters pixels */
+    int32_t  launches;           /* kernels launched by the call */
+    int32_t  reserved;
+} rtx_stats;
+
+typedef struct rtx_ctx rtx_ctx;
+
+/* ---- entry points ---------------------------------------------------------- */
+
+/* ABI version of the loaded library (== RTX_ABI_VERSION). */
+int rtx_abi_version(void);
+
+/* Human-readable text for a status code. */
+const char* rtx_status_string(int status);
+
+/* One context per GPU: owns the stream, events, the device copy of the scene and scratch buffers.
+ * Replaces nothing in the reference (it has no device); plays the role of the objects that live
+ * for the duration of main() (main.cpp:146-173). */
+int  rtx_create(rtx_ctx** out, int device);
+void rtx_destroy(rtx_ctx* ctx);
+
+/* Text of the last error on this context ("" if none). Valid until the next call on ctx. */
+const char* rtx_last_error(const rtx_ctx* ctx);
+
+/* Use an externally owned cudaStream_t (passed as void*) for all work of this context, e.g. the
+ * caller's current stream so that its own events bracket the kernels. NULL restores the private stream. */
+int rtx_set_stream(rtx_ctx* ctx, void* cuda_stream);
+
+/* Replaces the scene.push_back(...) sequence (main.cpp:156-163): copies n objects in scene order,
+ * normalises wall normals (scene.h:71), precomputes each wall's in-plane basis (scene.cpp:18-19, which
+ * the reference recomputes per intersection although it is ray independent) and uploads SoA arrays. */
+int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n_objects);
+
+/* Camera::init (scene.cpp:80-106) on the host, in double, quirks included (3.14, int() truncation). */
+int rtx_camera_init(const rtx_camera_desc* desc, rtx_camera* out);
+
+/* Fills params with the reference's literals (see rtx_params). */
+void rtx_default_params(rtx_params* params);
+
+/* Number of rows rank 'rank' renders of a frame of 'height' rows with cyclic bands. */
+int32_t rtx_local_rows(int32_t height, int32_t band_rows, int32_t n_ranks, int32_t rank);
+
+/* Global row index of this rank's packed local row (inverse of the band map); -1 if out of range. */
+int32_t rtx_global_row(int32_t local_row, int32_t height, int32_t band_rows, int32_t n_ranks, int32_t rank);
+
+/* Replaces rt_scene (main.cpp:124-139) + the quantise loop (main.cpp:338-347) for n_frames cameras
+ * that share width/height: ray generation, nearest hit over all objects (main.cpp:67-84), the
+ * reflection chain with the depth cap (main.cpp:89-119), Blinn-Phong (main.cpp:42-62,102-104),
+ * sky (main.cpp:28-37) and the truncating 8-bit pack. stats may be NULL. */
+int rtx_render(rtx_ctx* ctx, const rtx_camera* cameras, int32_t n_frames,
+               const rtx_params* params, const rtx_outputs* outputs, rtx_stats* stats);
+
+/* The quantise loop alone (main.cpp:338-347) on a caller-supplied radiance buffer of n_pixels
+ * RGB triples (exactly one of radiance_f32 / radiance_f64 non-NULL), memory = RTX_MEM_*. */
+int rtx_quantise(rtx_ctx* ctx, const float* radiance_f32, const double* radiance_f64, int64_t n_pixels,
+                 int32_t quantise_mode, uint32_t* rgba8, int32_t memory, rtx_stats* stats);
+
+/* Multi-GPU gather epilogue: scatters a band-major buffer (n_ranks blocks of rows_per_rank rows, block r =
+ * rank r's packed rows, as an all-gather delivers them) into a row-major frame. Device pointers,
+ * elem_bytes in {1,4}. rows_per_rank must be >= every rank's rtx_local_rows(). */
+int rtx_unpermute_bands(rtx_ctx* ctx, const void* band_major, void* row_major, int32_t height, int32_t width,
+                        int32_t elem_bytes, int32_t band_rows, int32_t n_ranks, int32_t rows_per_rank);
+
+/* FP32 FFMA throughput microbenchmark (the roofline denominator has no entry in MEASURED_PEAKS.json):
+ * returns achieved TFLOP/s of a dependent-chain-free FFMA loop over the whole chip. variant 0 = scalar
+ * FFMA, 1 = packed fma.rn.f32x2. */
+int rtx_ffma_peak(rtx_ctx* ctx, int32_t variant, double* tflops, double* sm_clock_mhz_estimate);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTX_B200_H */

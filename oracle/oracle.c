@@ -1,0 +1,398 @@
+/*
+ * oracle.c — CPU restatement of the reference's ray-tracing hot path in plain C.
+ *
+ * TEST INFRASTRUCTURE ONLY. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this; the product library never does (there is no CPU fallback).
+ *
+ * Parity is PINNED: tests/test_oracle.py checks this file bit-for-bit against
+ *   (1) the golden vectors the survey captured from the unmodified reference, and
+ *   (2) oracle/_ref/libref_oracle.so — the reference's own sources compiled unmodified —
+ *       on the default scene, the synthetic 10k scene and random rays,
+ * and against the fixtures in tests/golden/ that (2) generated (tests/golden/make_golden.py).
+ *
+ * Every function cites the reference lines it restates (paths relative to /root/reference).
+ * All arithmetic is IEEE double in the reference's operation order; build with -ffp-contract=off and
+ * without -ffast-math so that no FMA contraction or reassociation changes a rounding
+ * (the reference is built -O3 for baseline x86-64, which has no FMA: CMakeLists.txt:23).
+ * Third-party arithmetic: glibc libm pow / sqrt / tan (main.cpp:35,103; vec.cpp:4; scene.cpp:65,70-71,85),
+ * the same libm the reference links, so results are bit-identical to it on this image.
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "rtx_b200.h"
+
+typedef rtx_vec3 v3;
+
+/* ---- vec3 (vec.h:12-37, vec.cpp:3-57) --------------------------------------------------------- */
+static inline v3 mk(double x, double y, double z) { v3 r = {x, y, z}; return r; }
+static inline double len2(v3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }            /* vec.cpp:7-9   */
+static inline double len(v3 a) { return sqrt(len2(a)); }                                 /* vec.cpp:3-5   */
+static inline double dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }        /* vec.cpp:11-14 */
+static inline v3 cross(v3 u, v3 v)                                                        /* vec.cpp:15-19 */
+{
+    return mk(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);
+}
+static inline v3 add(v3 a, v3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }          /* vec.cpp:26-28 */
+static inline v3 sub(v3 a, v3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }          /* vec.cpp:32-34 */
+static inline v3 neg(v3 a) { return mk(-a.x, -a.y, -a.z); }                               /* vec.cpp:29-31 */
+static inline v3 scale(v3 a, double d) { return mk(a.x * d, a.y * d, a.z * d); }          /* vec.cpp:38-40 */
+static inline v3 divs(v3 a, double t) { return mk(a.x / t, a.y / t, a.z / t); }           /* vec.cpp:41-43 */
+static inline v3 unit(v3 a) { return divs(a, len(a)); }                                   /* vec.cpp:21-24: divides, not a reciprocal */
+static inline v3 lerp(v3 a, v3 b, double d)                                               /* vec.cpp:45-49 */
+{
+    return mk(a.x + d * (b.x - a.x), a.y + d * (b.y - a.y), a.z + d * (b.z - a.z));
+}
+static inline v3 reflect(v3 v, v3 normal)                                                 /* vec.cpp:51-57 */
+{
+    v3 nn = unit(normal);
+    v3 nv = unit(v);
+    double k = 2 * dot(nv, nn);
+    return sub(nv, scale(nn, k));
+}
+
+/* ---- Collision (scene.h:27-33) ------------------------------------------------------------------ */
+typedef struct { double distance; v3 normal; int hit; int index; } collision;
+static inline collision miss(void) { collision c = {-1, {0, 0, 0}, 0, -1}; return c; }     /* scene.cpp:34,59 */
+
+/* ---- scene objects with the constructor-time work done once ------------------------------------ */
+typedef struct {
+    int kind;
+    rtx_material mat;
+    v3 p;        /* center | corner */
+    v3 n;        /* wall normal after Wall's ctor normalised it (scene.h:71) */
+    double a, b; /* radius | length,width */
+} object;
+
+static void prepare(const rtx_object* in, int n, object* out)
+{
+    for (int k = 0; k < n; k++) {
+        out[k].kind = in[k].kind;
+        out[k].mat = in[k].mat;
+        out[k].p = in[k].p;
+        out[k].a = in[k].a;
+        out[k].b = in[k].b;
+        out[k].n = in[k].kind == RTX_WALL ? unit(in[k].n) : mk(0, 0, 0);
+    }
+}
+
+/* Wall::intersect (scene.cpp:4-35). Distance is the PARAMETER t of the (possibly unnormalised) direction. */
+static collision wall_intersect(const object* w, v3 o, v3 d)
+{
+    double denominator = dot(w->n, d);
+    double t = dot(sub(w->p, o), w->n) / denominator;
+    if (t > 0) {
+        v3 point = add(o, scale(d, t));
+        v3 right = unit(cross(w->n, mk(0, 0, 1)));          /* scene.cpp:18 (recomputed per call there) */
+        v3 up = unit(cross(right, w->n));                    /* scene.cpp:19 */
+        v3 rel = sub(point, w->p);
+        double px = dot(rel, right);
+        double py = dot(rel, up);
+        if (px >= 0 && px <= w->a && py >= 0 && py <= w->b) {
+            collision c = {t, w->n, 1, -1};
+            return c;
+        }
+    }
+    return miss();
+}
+
+/* Sphere::intersect (scene.cpp:40-78). Distance is in WORLD units (projection * |d|), the normal is
+ * unnormalised (length r), and "hit" is reported even for negative projections. */
+static collision sphere_intersect(const object* s, v3 o, v3 d)
+{
+    v3 oc = sub(o, s->p);
+    double a = len2(d);
+    double b = 2 * dot(d, oc);
+    double c = len2(oc) - s->a * s->a;
+    double det = b * b - 4 * a * c;
+    double projection = -1;
+    if (det < 0) return miss();
+    v3 point = mk(0, 0, 0);
+    if (det == 0) {
+        point = add(o, scale(d, -b / (2 * a)));
+        projection = (-b - sqrt(det)) / a;               /* divides by a, not 2a (scene.cpp:65) */
+    } else {
+        double p1 = (-b + sqrt(det)) / (2 * a);
+        double p2 = (-b - sqrt(det)) / (2 * a);
+        projection = p1 < p2 ? p1 : p2;
+        point = add(o, scale(d, projection));
+    }
+    collision r = {projection * len(d), sub(point, s->p), 1, -1};
+    return r;
+}
+
+static inline collision intersect(const object* g, v3 o, v3 d)
+{
+    return g->kind == RTX_SPHERE ? sphere_intersect(g, o, d) : wall_intersect(g, o, d);
+}
+
+/* find_closest_hit (main.cpp:67-84): strict '<' keeps the lowest index on equal distances. */
+static collision closest_hit(const object* scene, int n, v3 o, v3 d)
+{
+    collision best = {DBL_MAX, {0, 0, 0}, 0, -1};
+    for (int j = 0; j < n; j++) {
+        collision c = intersect(&scene[j], o, d);
+        if (c.distance > 0 && c.distance < best.distance) {
+            best = c;
+            best.index = j;
+        }
+    }
+    return best;
+}
+
+/* out_color (main.cpp:28-37): the sign test is on the UNNORMALISED z. */
+static v3 sky(v3 v, const rtx_params* p)
+{
+    if (v.z < 0.0) return p->ground_color;
+    v = unit(v);
+    return lerp(p->sky_low, p->sky_high, pow(v.z, p->sky_exponent));
+}
+
+/* diffuse_shading (main.cpp:42-48) */
+static double diffuse_term(v3 pos, v3 normal, v3 light)
+{
+    v3 l = unit(sub(light, pos));
+    double lambert = dot(l, unit(normal));
+    return lambert > 0 ? lambert : 0;
+}
+
+/* specular (main.cpp:53-62); the exponent is applied by the caller (main.cpp:103) */
+static double specular_term(v3 pos, v3 normal, v3 light, v3 view)
+{
+    view = unit(view);
+    normal = unit(normal);
+    v3 l = unit(sub(light, pos));
+    v3 h = unit(add(view, l));
+    double r = dot(h, normal);
+    return r > 0 ? r : 0;
+}
+
+/* recursive_ray_tracing (main.cpp:89-119). *rays counts find_closest_hit calls (may be NULL). */
+static v3 trace(const object* scene, int n, v3 o, v3 d, int remaining, const rtx_params* p, int* rays)
+{
+    collision col = closest_hit(scene, n, o, d);
+    if (rays) (*rays)++;
+    if (col.index < 0) return sky(d, p);
+    v3 pos = add(o, scale(d, col.distance));
+    const rtx_material* m = &scene[col.index].mat;
+    double di = diffuse_term(add(o, scale(d, col.distance)), col.normal, p->light_pos);
+    double si = pow(specular_term(pos, col.normal, p->light_pos, neg(d)), m->specular_exponent);
+    v3 local = scale(m->color, di * m->diffuse + si * m->specular + m->ambient);
+    if (remaining <= 0) return local;
+    v3 start = add(pos, scale(col.normal, p->reflect_offset));   /* normal unnormalised: offset = r*1e-4 on spheres */
+    v3 rd = reflect(d, col.normal);
+    v3 rt = trace(scene, n, start, rd, remaining - 1, p, rays);
+    return lerp(local, rt, m->metallic);
+}
+
+/* main.cpp:345: double -> Uint8 is the implicit C conversion. On x86-64 the compiler emits cvttsd2si
+ * (32-bit) and keeps the low byte: in-range values truncate toward zero and wrap mod 256; NaN and
+ * |v| >= 2^31 produce 0x80000000 whose low byte is 0. Written out so the result does not depend on UB. */
+static inline uint32_t to_u8_wrap(double v)
+{
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return 0;
+    return (uint32_t)(int32_t)v & 0xFFu;
+}
+static inline uint32_t to_u8_sat(double v)
+{
+    if (!(v > 0.0)) return 0;
+    if (v >= 255.0) return 255;
+    return (uint32_t)v;
+}
+static inline uint32_t pack_rgba(v3 c, int mode)                          /* main.cpp:193,345 */
+{
+    double r = c.x * 255, g = c.y * 255, b = c.z * 255;
+    uint32_t R = mode == RTX_QUANT_SATURATE ? to_u8_sat(r) : to_u8_wrap(r);
+    uint32_t G = mode == RTX_QUANT_SATURATE ? to_u8_sat(g) : to_u8_wrap(g);
+    uint32_t B = mode == RTX_QUANT_SATURATE ? to_u8_sat(b) : to_u8_wrap(b);
+    return (R << 24) | (G << 16) | (B << 8) | 0xFFu;
+}
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+/* ================================================================================================ */
+
+void orc_default_params(rtx_params* p)
+{
+    memset(p, 0, sizeof *p);
+    p->max_depth = 10;                            /* main.cpp:89  */
+    p->quantise_mode = RTX_QUANT_WRAP;
+    p->fuse_quantise = 1;
+    p->light_pos = mk(0, 0, 0);                   /* main.cpp:14  */
+    p->ground_color = mk(0.025, 0.05, 0.075);     /* main.cpp:15  */
+    p->sky_low = mk(0.36, 0.45, 0.57);            /* main.cpp:16  */
+    p->sky_high = mk(0.14, 0.21, 0.49);           /* main.cpp:17  */
+    p->reflect_offset = .0001;                    /* main.cpp:111 */
+    p->sky_exponent = (double)(float)(1. / 4.);   /* `const float skyGradient = 1. / 4.` main.cpp:34 */
+    p->band_rows = 4;
+    p->n_ranks = 1;
+    p->rank = 0;
+}
+
+int orc_abi_version(void) { return RTX_ABI_VERSION; }
+
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* Camera::init (scene.cpp:80-106). */
+void orc_camera_init(const rtx_camera_desc* d, rtx_camera* out)
+{
+    double image_width = d->image_width;
+    double image_height = (int)(image_width / d->aspect_ratio);
+    double focal = len(sub(d->position, d->lookat));
+    double theta = d->vfov * 3.14 / 180.0;
+    double h = tan(theta / 2);
+    double fov_height = 2 * h * focal;
+    double fov_width = fov_height * (image_width / image_height);
+    v3 w = unit(sub(d->position, d->lookat));
+    v3 u = unit(cross(d->vup, w));
+    v3 v = cross(w, u);
+    v3 fov_x = scale(u, fov_width);
+    v3 fov_y = scale(v, -fov_height);
+    v3 dx = divs(fov_x, image_width);
+    v3 dy = divs(fov_y, image_height);
+    v3 top_left = sub(sub(sub(d->position, scale(w, focal)), divs(fov_x, 2)), divs(fov_y, 2));
+    out->position = d->position;
+    out->image_top_left = add(top_left, scale(add(dx, dy), 0.5));
+    out->delta_x = dx;
+    out->delta_y = dy;
+    out->width = (int32_t)image_width;
+    out->height = (int32_t)image_height;
+}
+
+/* The loop body of rt_scene (main.cpp:129-136) over the given global rows, packed [n_rows][width];
+ * every output plane is optional. Returns seconds spent in the loop, -1 on bad arguments. */
+double orc_render_rows_params(const rtx_object* objs, int32_t n_objs, const rtx_camera* cam, const rtx_params* p,
+                              const int32_t* rows, int32_t n_rows, int32_t n_threads,
+                              double* radiance, uint32_t* rgba8, int32_t* object_id, uint8_t* hit_mask,
+                              uint8_t* ray_count, uint64_t* total_rays)
+{
+    if ((!objs && n_objs > 0) || !cam || !rows || n_rows < 0 || !p) return -1;
+    object* scene = (object*)malloc(sizeof(object) * (size_t)(n_objs > 0 ? n_objs : 1));
+    if (!scene) return -1;
+    prepare(objs, n_objs, scene);
+    const int W = cam->width;
+    uint64_t rays_sum = 0;
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+#endif
+    double t0 = now_s();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads) reduction(+ : rays_sum)
+    for (int k = 0; k < n_rows; k++) {
+        const int i = rows[k];
+        for (int j = 0; j < W; j++) {
+            v3 center = add(add(cam->image_top_left, scale(cam->delta_x, j)), scale(cam->delta_y, i)); /* main.cpp:132 */
+            v3 d = sub(cam->position, center);                                                          /* main.cpp:133 */
+            int rays = 0;
+            v3 c = trace(scene, n_objs, cam->position, d, p->max_depth, p, &rays);                      /* main.cpp:136 */
+            size_t px = (size_t)k * W + j;
+            if (radiance) {
+                radiance[3 * px + 0] = c.x;
+                radiance[3 * px + 1] = c.y;
+                radiance[3 * px + 2] = c.z;
+            }
+            if (rgba8) rgba8[px] = pack_rgba(c, p->quantise_mode);
+            if (object_id || hit_mask) {
+                collision first = closest_hit(scene, n_objs, cam->position, d);
+                if (object_id) object_id[px] = first.index;
+                if (hit_mask) hit_mask[px] = first.index >= 0;
+            }
+            if (ray_count) ray_count[px] = (uint8_t)rays;
+            rays_sum += (uint64_t)rays;
+        }
+    }
+    double t1 = now_s();
+    free(scene);
+    if (total_rays) *total_rays = rays_sum;
+    return t1 - t0;
+}
+
+/* Same door as ref_render_rows in oracle/ref_harness.cpp: reference literals for every parameter. */
+double orc_render_rows(const rtx_object* objs, int32_t n_objs, const rtx_camera* cam, int32_t max_depth,
+                       const int32_t* rows, int32_t n_rows, int32_t n_threads,
+                       double* radiance, uint32_t* rgba8, int32_t* object_id, uint8_t* hit_mask, uint8_t* ray_count,
+                       uint64_t* total_rays)
+{
+    rtx_params p;
+    orc_default_params(&p);
+    p.max_depth = max_depth;
+    return orc_render_rows_params(objs, n_objs, cam, &p, rows, n_rows, n_threads, radiance, rgba8, object_id, hit_mask,
+                                  ray_count, total_rays);
+}
+
+/* main.cpp:343-345 over n RGB triples. */
+void orc_quantise(const double* rgb, int64_t n, uint32_t* out)
+{
+    for (int64_t k = 0; k < n; k++) out[k] = pack_rgba(mk(rgb[3 * k], rgb[3 * k + 1], rgb[3 * k + 2]), RTX_QUANT_WRAP);
+}
+void orc_quantise_mode(const double* rgb, int64_t n, int32_t mode, uint32_t* out)
+{
+    for (int64_t k = 0; k < n; k++) out[k] = pack_rgba(mk(rgb[3 * k], rgb[3 * k + 1], rgb[3 * k + 2]), mode);
+}
+/* The float-radiance variant of the product's standalone quantise: float -> double is exact, then main.cpp:345. */
+void orc_quantise_f32(const float* rgb, int64_t n, int32_t mode, uint32_t* out)
+{
+    for (int64_t k = 0; k < n; k++)
+        out[k] = pack_rgba(mk((double)rgb[3 * k], (double)rgb[3 * k + 1], (double)rgb[3 * k + 2]), mode);
+}
+
+/* ---- function-level doors (same signatures as the ref_* ones) ------------------------------------ */
+void orc_intersect(const rtx_object* obj, const v3* origin, const v3* dir, double* distance, v3* normal, int32_t* hit)
+{
+    object g;
+    prepare(obj, 1, &g);
+    collision c = intersect(&g, *origin, *dir);
+    *distance = c.distance;
+    *normal = c.normal;
+    *hit = c.hit;
+}
+
+void orc_find_closest_hit(const rtx_object* objs, int32_t n, const v3* origin, const v3* dir, double* distance, v3* normal,
+                          int32_t* index)
+{
+    object* scene = (object*)malloc(sizeof(object) * (size_t)(n > 0 ? n : 1));
+    prepare(objs, n, scene);
+    collision c = closest_hit(scene, n, *origin, *dir);
+    *distance = c.distance;
+    *normal = c.normal;
+    *index = c.index;
+    free(scene);
+}
+
+void orc_trace_ray(const rtx_object* objs, int32_t n, const v3* origin, const v3* dir, int32_t depth, v3* rgb)
+{
+    rtx_params p;
+    orc_default_params(&p);
+    object* scene = (object*)malloc(sizeof(object) * (size_t)(n > 0 ? n : 1));
+    prepare(objs, n, scene);
+    *rgb = trace(scene, n, *origin, *dir, depth, &p, NULL);
+    free(scene);
+}
+
+void orc_out_color(const v3* v, v3* rgb)
+{
+    rtx_params p;
+    orc_default_params(&p);
+    *rgb = sky(*v, &p);
+}
+void orc_reflect(const v3* v, const v3* n, v3* out) { *out = reflect(*v, *n); }
+double orc_diffuse(const v3* pos, const v3* n, const v3* light) { return diffuse_term(*pos, *n, *light); }
+double orc_specular(const v3* pos, const v3* n, const v3* light, const v3* view) { return specular_term(*pos, *n, *light, *view); }
