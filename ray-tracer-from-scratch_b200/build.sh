@@ -1,0 +1,15 @@
+#!/usr/bin/env bash
+# Builds librtx_b200.so (the C-ABI library, sm_100a only) in-tree, next to this script.
+#   -lineinfo                 source mapping for ncu
+#   -Xcompiler -ffp-contract=off   host doubles (wall basis, Camera::init) round like the reference's x86-64 build
+# Device double arithmetic on the parity path uses explicit __d*_rn intrinsics, so -fmad stays at its default
+# for the FP32 screen's FFMAs.
+set -euo pipefail
+here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+    -Xcompiler -fPIC,-ffp-contract=off,-Wall ${RTX_NVCC_EXTRA:-} \
+    -I"$here/../include" -I"$here/csrc" -shared \
+    "$here/csrc/api.cu" "$here/csrc/trace.cu" "$here/csrc/aux_kernels.cu" \
+    -o "$here/librtx_b200.so"
+echo "built $here/librtx_b200.so"

@@ -1,0 +1,567 @@
+// api.cu — the extern "C" layer of include/rtx_b200.h: context, scene upload, render, quantise, gather epilogue.
+// Host code only (kernels are in trace.cu / aux_kernels.cu). Built with -ffp-contract=off: the few doubles
+// computed here (wall normal + basis, Camera::init) must round exactly like the reference's x86-64 build.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rtx_device.cuh"
+
+using namespace rtx;
+
+struct rtx_ctx {
+    int device = 0;
+    int n_sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    std::string error;
+
+    // scene
+    bool have_scene = false;
+    SceneDev scene = {};
+    void* d_scene_blob = nullptr;
+    double scene_bound = 0.0;          // max over objects of |coordinate| + extent
+
+    // per-call scratch (grown on demand, reused across calls)
+    rtx_camera* d_cameras = nullptr;
+    rtx_camera* h_cameras = nullptr;   // pinned
+    int cameras_cap = 0;
+    unsigned long long* d_counters = nullptr;
+    unsigned long long* h_counters = nullptr;   // pinned
+    void* d_out[6] = {};
+    size_t d_out_cap[6] = {};
+    double* d_rad_scratch = nullptr;   // radiance buffer for the unfused quantise path
+    size_t d_rad_scratch_cap = 0;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int fail(rtx_ctx* ctx, int code, const std::string& msg)
+{
+    if (ctx) ctx->error = msg;
+    return code;
+}
+
+int cuda_fail(rtx_ctx* ctx, cudaError_t e, const char* what)
+{
+    return fail(ctx, RTX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+
+#define RTX_CUDA(ctx, call)                                     \
+    do {                                                        \
+        cudaError_t e__ = (call);                               \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+// host doubles in the reference's operation order (vec.cpp)
+struct h3 { double x, y, z; };
+inline h3 H(const rtx_vec3& v) { return h3{v.x, v.y, v.z}; }
+inline double hlen(h3 a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+inline h3 hdiv(h3 a, double s) { return h3{a.x / s, a.y / s, a.z / s}; }
+inline h3 hunit(h3 a) { return hdiv(a, hlen(a)); }
+inline h3 hcross(h3 u, h3 v) { return h3{u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x}; }
+inline h3 hsub(h3 a, h3 b) { return h3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline h3 hadd(h3 a, h3 b) { return h3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline h3 hmul(h3 a, double s) { return h3{a.x * s, a.y * s, a.z * s}; }
+inline d3 D(h3 a) { return d3{a.x, a.y, a.z}; }
+inline double amax3(h3 a) { return std::fmax(std::fabs(a.x), std::fmax(std::fabs(a.y), std::fabs(a.z))); }
+
+int grow(rtx_ctx* ctx, void** p, size_t* cap, size_t need)
+{
+    if (need <= *cap) return RTX_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) return fail(ctx, RTX_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    *cap = need;
+    return RTX_OK;
+}
+
+constexpr int kPad = 8;   // hot-loop unroll factor of trace.cu
+
+}  // namespace
+
+extern "C" {
+
+int rtx_abi_version(void) { return RTX_ABI_VERSION; }
+
+const char* rtx_status_string(int status)
+{
+    switch (status) {
+        case RTX_OK: return "ok";
+        case RTX_ERR_INVALID: return "invalid argument";
+        case RTX_ERR_CUDA: return "CUDA error or no usable device";
+        case RTX_ERR_NO_SCENE: return "no scene set";
+        case RTX_ERR_NOMEM: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+int rtx_create(rtx_ctx** out, int device)
+{
+    if (!out) return RTX_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0");
+        return RTX_ERR_CUDA;   // no CPU fallback, by design
+    }
+    if (device < 0 || device >= count) return RTX_ERR_INVALID;
+    rtx_ctx* ctx = new (std::nothrow) rtx_ctx;
+    if (!ctx) return RTX_ERR_NOMEM;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete ctx;
+        return RTX_ERR_CUDA;
+    }
+    if (prop.major < 10) {
+        g_create_error = "device is not sm_100-class (kernels are built for sm_100a only)";
+        delete ctx;
+        return RTX_ERR_CUDA;
+    }
+    ctx->n_sms = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&ctx->h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
+    if (!ok) {
+        g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
+        rtx_destroy(ctx);
+        return RTX_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return RTX_OK;
+}
+
+void rtx_destroy(rtx_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->d_scene_blob) cudaFree(ctx->d_scene_blob);
+    if (ctx->d_cameras) cudaFree(ctx->d_cameras);
+    if (ctx->h_cameras) cudaFreeHost(ctx->h_cameras);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    for (auto& p : ctx->d_out)
+        if (p) cudaFree(p);
+    if (ctx->d_rad_scratch) cudaFree(ctx->d_rad_scratch);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* rtx_last_error(const rtx_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int rtx_set_stream(rtx_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return RTX_OK;
+}
+
+int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    if (n < 0 || (n > 0 && !objects)) return fail(ctx, RTX_ERR_INVALID, "rtx_set_scene: null objects or negative count");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<float4> sph32;
+    std::vector<SphereExact> sph64;
+    std::vector<int32_t> sph_id, kind(n), slot(n);
+    std::vector<WallDev> walls;
+    std::vector<MaterialDev> mats(n);
+    double bound = 0.0;
+    for (int k = 0; k < n; k++) {
+        const rtx_object& o = objects[k];
+        if (o.kind != RTX_SPHERE && o.kind != RTX_WALL) return fail(ctx, RTX_ERR_INVALID, "rtx_set_scene: unknown object kind");
+        MaterialDev& m = mats[k];
+        m.color = d3{o.mat.color.x, o.mat.color.y, o.mat.color.z};
+        m.ambient = o.mat.ambient;
+        m.metallic = o.mat.metallic;
+        m.diffuse = o.mat.diffuse;
+        m.specular = o.mat.specular;
+        m.exponent = o.mat.specular_exponent;
+        kind[k] = o.kind;
+        if (o.kind == RTX_SPHERE) {
+            slot[k] = static_cast<int32_t>(sph64.size());
+            sph64.push_back(SphereExact{o.p.x, o.p.y, o.p.z, o.a});
+            // nearest-float copies for the screen; a negative or non-finite radius gets r = +inf there so that
+            // the screen never rejects it and the exact test decides
+            float r32 = static_cast<float>(std::fabs(o.a));
+            if (!(o.a >= 0.0) || !std::isfinite(o.a)) r32 = INFINITY;
+            sph32.push_back(make_float4(static_cast<float>(o.p.x), static_cast<float>(o.p.y), static_cast<float>(o.p.z), r32));
+            sph_id.push_back(k);
+            bound = std::fmax(bound, amax3(H(o.p)) + std::fabs(o.a));
+        } else {
+            slot[k] = static_cast<int32_t>(walls.size());
+            WallDev w;
+            const h3 nrm = hunit(H(o.n));                               // Wall ctor, scene.h:71
+            const h3 right = hunit(hcross(nrm, h3{0, 0, 1}));           // scene.cpp:18
+            const h3 up = hunit(hcross(right, nrm));                    // scene.cpp:19
+            w.p = D(H(o.p));
+            w.n = D(nrm);
+            w.right = D(right);
+            w.up = D(up);
+            w.length = o.a;
+            w.width = o.b;
+            w.id = k;
+            w.pad = 0;
+            walls.push_back(w);
+            bound = std::fmax(bound, amax3(H(o.p)) + std::fabs(o.a) + std::fabs(o.b));
+        }
+    }
+    const int ns = static_cast<int>(sph64.size()), nw = static_cast<int>(walls.size());
+    const int ns_pad = (ns + kPad - 1) / kPad * kPad;
+    sph32.resize(ns_pad, make_float4(0.f, 0.f, 0.f, -1.f));
+
+    // one device blob, 256-byte aligned sections
+    auto align = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
+    size_t off = 0;
+    const size_t o_s32 = off; off = align(off + sizeof(float4) * std::max(ns_pad, 1));
+    const size_t o_s64 = off; off = align(off + sizeof(SphereExact) * std::max(ns, 1));
+    const size_t o_sid = off; off = align(off + sizeof(int32_t) * std::max(ns, 1));
+    const size_t o_wal = off; off = align(off + sizeof(WallDev) * std::max(nw, 1));
+    const size_t o_mat = off; off = align(off + sizeof(MaterialDev) * std::max(n, 1));
+    const size_t o_knd = off; off = align(off + sizeof(int32_t) * std::max(n, 1));
+    const size_t o_slt = off; off = align(off + sizeof(int32_t) * std::max(n, 1));
+    std::vector<unsigned char> blob(off, 0);
+    if (ns_pad) std::memcpy(&blob[o_s32], sph32.data(), sizeof(float4) * ns_pad);
+    if (ns) std::memcpy(&blob[o_s64], sph64.data(), sizeof(SphereExact) * ns);
+    if (ns) std::memcpy(&blob[o_sid], sph_id.data(), sizeof(int32_t) * ns);
+    if (nw) std::memcpy(&blob[o_wal], walls.data(), sizeof(WallDev) * nw);
+    if (n) std::memcpy(&blob[o_mat], mats.data(), sizeof(MaterialDev) * n);
+    if (n) std::memcpy(&blob[o_knd], kind.data(), sizeof(int32_t) * n);
+    if (n) std::memcpy(&blob[o_slt], slot.data(), sizeof(int32_t) * n);
+
+    RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_scene_blob) cudaFree(ctx->d_scene_blob);
+    ctx->d_scene_blob = nullptr;
+    ctx->have_scene = false;
+    cudaError_t e = cudaMalloc(&ctx->d_scene_blob, off);
+    if (e != cudaSuccess) return fail(ctx, RTX_ERR_NOMEM, std::string("cudaMalloc(scene): ") + cudaGetErrorString(e));
+    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_scene_blob, blob.data(), off, cudaMemcpyHostToDevice, ctx->stream));
+    RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned char* base = static_cast<unsigned char*>(ctx->d_scene_blob);
+    SceneDev& s = ctx->scene;
+    s.n_objects = n;
+    s.n_spheres = ns;
+    s.n_walls = nw;
+    s.n_spheres_padded = ns_pad;
+    s.sph32 = reinterpret_cast<const float4*>(base + o_s32);
+    s.sph64 = reinterpret_cast<const SphereExact*>(base + o_s64);
+    s.sph_id = reinterpret_cast<const int32_t*>(base + o_sid);
+    s.walls = reinterpret_cast<const WallDev*>(base + o_wal);
+    s.mats = reinterpret_cast<const MaterialDev*>(base + o_mat);
+    s.kind = reinterpret_cast<const int32_t*>(base + o_knd);
+    s.slot = reinterpret_cast<const int32_t*>(base + o_slt);
+    ctx->scene_bound = bound;
+    ctx->have_scene = true;
+    ctx->error.clear();
+    return RTX_OK;
+}
+
+int rtx_camera_init(const rtx_camera_desc* d, rtx_camera* out)
+{
+    if (!d || !out) return RTX_ERR_INVALID;
+    // Camera::init, scene.cpp:80-106
+    const double image_width = d->image_width;
+    const double image_height = static_cast<int>(image_width / d->aspect_ratio);
+    const h3 position = H(d->position), lookat = H(d->lookat), vup = H(d->vup);
+    const double focal_length = hlen(hsub(position, lookat));
+    const double theta = d->vfov * 3.14 / 180.0;
+    const double h = std::tan(theta / 2);
+    const double fov_height = 2 * h * focal_length;
+    const double fov_width = fov_height * (image_width / image_height);
+    const h3 w = hunit(hsub(position, lookat));
+    const h3 u = hunit(hcross(vup, w));
+    const h3 v = hcross(w, u);
+    const h3 fov_x = hmul(u, fov_width);
+    const h3 fov_y = hmul(v, -fov_height);
+    const h3 dx = hdiv(fov_x, image_width);
+    const h3 dy = hdiv(fov_y, image_height);
+    const h3 top_left = hsub(hsub(hsub(position, hmul(w, focal_length)), hdiv(fov_x, 2)), hdiv(fov_y, 2));
+    const h3 itl = hadd(top_left, hmul(hadd(dx, dy), 0.5));
+    out->position = d->position;
+    out->image_top_left = rtx_vec3{itl.x, itl.y, itl.z};
+    out->delta_x = rtx_vec3{dx.x, dx.y, dx.z};
+    out->delta_y = rtx_vec3{dy.x, dy.y, dy.z};
+    out->width = static_cast<int32_t>(image_width);
+    out->height = static_cast<int32_t>(image_height);
+    return RTX_OK;
+}
+
+void rtx_default_params(rtx_params* p)
+{
+    if (!p) return;
+    std::memset(p, 0, sizeof *p);
+    p->max_depth = 10;
+    p->quantise_mode = RTX_QUANT_WRAP;
+    p->fuse_quantise = 1;
+    p->light_pos = rtx_vec3{0, 0, 0};
+    p->ground_color = rtx_vec3{0.025, 0.05, 0.075};
+    p->sky_low = rtx_vec3{0.36, 0.45, 0.57};
+    p->sky_high = rtx_vec3{0.14, 0.21, 0.49};
+    p->reflect_offset = .0001;
+    p->sky_exponent = static_cast<double>(static_cast<float>(1. / 4.));
+    p->band_rows = 4;
+    p->n_ranks = 1;
+    p->rank = 0;
+}
+
+int32_t rtx_local_rows(int32_t height, int32_t band_rows, int32_t n_ranks, int32_t rank)
+{
+    if (height <= 0 || band_rows <= 0 || n_ranks <= 0 || rank < 0 || rank >= n_ranks) return 0;
+    if (n_ranks == 1) return height;
+    const int32_t n_bands = (height + band_rows - 1) / band_rows;
+    int32_t rows = 0;
+    for (int32_t b = rank; b < n_bands; b += n_ranks) rows += std::min(band_rows, height - b * band_rows);
+    return rows;
+}
+
+int32_t rtx_global_row(int32_t local_row, int32_t height, int32_t band_rows, int32_t n_ranks, int32_t rank)
+{
+    if (local_row < 0 || local_row >= rtx_local_rows(height, band_rows, n_ranks, rank)) return -1;
+    if (n_ranks == 1) return local_row;
+    const int32_t lb = local_row / band_rows;
+    return (lb * n_ranks + rank) * band_rows + (local_row - lb * band_rows);
+}
+
+int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx_params* params, const rtx_outputs* outs,
+               rtx_stats* stats)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    if (!ctx->have_scene) return fail(ctx, RTX_ERR_NO_SCENE, "rtx_render: call rtx_set_scene first");
+    if (!cams || n_frames <= 0 || !params || !outs) return fail(ctx, RTX_ERR_INVALID, "rtx_render: null argument or n_frames <= 0");
+    const rtx_params& p = *params;
+    if (p.max_depth < 0 || p.max_depth > RTX_MAX_DEPTH) return fail(ctx, RTX_ERR_INVALID, "rtx_render: max_depth out of [0, 254]");
+    if (p.n_ranks < 1 || p.rank < 0 || p.rank >= p.n_ranks || (p.n_ranks > 1 && p.band_rows < 1))
+        return fail(ctx, RTX_ERR_INVALID, "rtx_render: bad band sharding (band_rows, n_ranks, rank)");
+    if (p.quantise_mode != RTX_QUANT_WRAP && p.quantise_mode != RTX_QUANT_SATURATE)
+        return fail(ctx, RTX_ERR_INVALID, "rtx_render: unknown quantise_mode");
+    if (outs->memory != RTX_MEM_HOST && outs->memory != RTX_MEM_DEVICE)
+        return fail(ctx, RTX_ERR_INVALID, "rtx_render: outputs.memory must be RTX_MEM_HOST or RTX_MEM_DEVICE");
+    const int W = cams[0].width, Hh = cams[0].height;
+    if (W <= 0 || Hh <= 0) return fail(ctx, RTX_ERR_INVALID, "rtx_render: camera width/height must be positive");
+    double cam_bound = 0.0;
+    for (int f = 0; f < n_frames; f++) {
+        if (cams[f].width != W || cams[f].height != Hh)
+            return fail(ctx, RTX_ERR_INVALID, "rtx_render: all cameras of one call must share width/height");
+        cam_bound = std::fmax(cam_bound, amax3(H(cams[f].position)));
+    }
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int band_rows = p.n_ranks > 1 ? p.band_rows : 1;
+    const int local_rows = rtx_local_rows(Hh, band_rows, p.n_ranks, p.rank);
+    const size_t n_px = static_cast<size_t>(n_frames) * local_rows * W;
+
+    // cameras -> pinned staging -> device
+    if (n_frames > ctx->cameras_cap) {
+        if (ctx->d_cameras) cudaFree(ctx->d_cameras);
+        if (ctx->h_cameras) cudaFreeHost(ctx->h_cameras);
+        ctx->d_cameras = nullptr;
+        ctx->h_cameras = nullptr;
+        ctx->cameras_cap = 0;
+        const int cap = std::max(n_frames, 16);
+        if (cudaMalloc(&ctx->d_cameras, sizeof(rtx_camera) * cap) != cudaSuccess ||
+            cudaHostAlloc(&ctx->h_cameras, sizeof(rtx_camera) * cap, cudaHostAllocDefault) != cudaSuccess)
+            return fail(ctx, RTX_ERR_NOMEM, "rtx_render: camera buffers");
+        ctx->cameras_cap = cap;
+    }
+    std::memcpy(ctx->h_cameras, cams, sizeof(rtx_camera) * n_frames);
+
+    // output planes: the caller's device pointers, or device staging for host pointers
+    void* user[6] = {outs->rgba8, outs->radiance_f32, outs->radiance_f64, outs->object_id, outs->hit_mask, outs->ray_count};
+    const size_t elem[6] = {4, 12, 24, 4, 1, 1};
+    void* dev[6] = {};
+    const bool host_out = outs->memory == RTX_MEM_HOST;
+    for (int k = 0; k < 6; k++) {
+        if (!user[k]) continue;
+        if (host_out) {
+            int rc = grow(ctx, &ctx->d_out[k], &ctx->d_out_cap[k], std::max<size_t>(n_px * elem[k], 16));
+            if (rc != RTX_OK) return rc;
+            dev[k] = ctx->d_out[k];
+        } else {
+            dev[k] = user[k];
+        }
+    }
+    const bool unfused = !p.fuse_quantise && user[0];
+    double* rad_for_quant = nullptr;
+    if (unfused) {
+        if (dev[2]) {
+            rad_for_quant = static_cast<double*>(dev[2]);
+        } else {
+            void* pp = ctx->d_rad_scratch;
+            int rc = grow(ctx, &pp, &ctx->d_rad_scratch_cap, std::max<size_t>(n_px * 24, 16));
+            ctx->d_rad_scratch = static_cast<double*>(pp);
+            if (rc != RTX_OK) return rc;
+            rad_for_quant = ctx->d_rad_scratch;
+        }
+    }
+
+    TraceArgs a = {};
+    a.scene = ctx->scene;
+    a.cameras = ctx->d_cameras;
+    a.n_frames = n_frames;
+    a.width = W;
+    a.height = Hh;
+    a.local_rows = local_rows;
+    a.band_rows = band_rows;
+    a.n_ranks = p.n_ranks;
+    a.rank = p.rank;
+    a.max_depth = p.max_depth;
+    a.quantise_mode = p.quantise_mode;
+    a.light = D(H(p.light_pos));
+    a.ground = D(H(p.ground_color));
+    a.sky_low = D(H(p.sky_low));
+    a.sky_high = D(H(p.sky_high));
+    a.reflect_offset = p.reflect_offset;
+    a.sky_exponent = p.sky_exponent;
+    // FP32 screen error bound (derivation in DESIGN.md §3.2): with B = scene/camera extent and ray origins
+    // within 2B, the line-distance error is below 1.1e-6*B; 4e-6*B leaves a 4x margin. Origins beyond 2B
+    // (primary-ray overshoot) fall back to exact tests lane by lane.
+    const double B = std::fmax(std::fmax(ctx->scene_bound, cam_bound), 1e-3);
+    a.filter_eps = static_cast<float>(4e-6 * B);
+    a.origin_bound = static_cast<float>(2.0 * B);
+    a.rgba8 = unfused ? nullptr : static_cast<uint32_t*>(dev[0]);
+    a.rad32 = static_cast<float*>(dev[1]);
+    a.rad64 = unfused ? rad_for_quant : static_cast<double*>(dev[2]);
+    a.object_id = static_cast<int32_t*>(dev[3]);
+    a.hit_mask = static_cast<uint8_t*>(dev[4]);
+    a.ray_count = static_cast<uint8_t*>(dev[5]);
+    a.counters = ctx->d_counters;
+
+    int launches = 0;
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_cameras, ctx->h_cameras, sizeof(rtx_camera) * n_frames, cudaMemcpyHostToDevice, st));
+    RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    RTX_CUDA(ctx, launch_trace(a, ctx->n_sms, st, &launches));
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    if (unfused) {
+        RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 2, 0, 2 * sizeof(unsigned long long), st));
+        RTX_CUDA(ctx, launch_quantise_f64(rad_for_quant, static_cast<int64_t>(n_px), p.quantise_mode,
+                                          static_cast<uint32_t*>(dev[0]), ctx->d_counters, ctx->n_sms, st));
+        launches++;
+    }
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    if (host_out) {
+        for (int k = 0; k < 6; k++)
+            if (user[k]) RTX_CUDA(ctx, cudaMemcpyAsync(user[k], dev[k], n_px * elem[k], cudaMemcpyDeviceToHost, st));
+    }
+    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+    RTX_CUDA(ctx, cudaStreamSynchronize(st));
+    RTX_CUDA(ctx, cudaGetLastError());
+
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); stats->h2d_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); stats->raytracing_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); stats->surface_update_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); stats->d2h_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); stats->total_ms = ms;
+        stats->total_rays = ctx->h_counters[1];
+        stats->sphere_tests = stats->total_rays * static_cast<uint64_t>(ctx->scene.n_spheres);
+        stats->wall_tests = stats->total_rays * static_cast<uint64_t>(ctx->scene.n_walls);
+        stats->over_range_pixels = ctx->h_counters[2];
+        long long bits = static_cast<long long>(ctx->h_counters[3]);
+        std::memcpy(&stats->max_luminance, &bits, sizeof bits);
+        stats->launches = launches;
+    }
+    ctx->error.clear();
+    return RTX_OK;
+}
+
+int rtx_quantise(rtx_ctx* ctx, const float* rad32, const double* rad64, int64_t n_pixels, int32_t mode, uint32_t* rgba8,
+                 int32_t memory, rtx_stats* stats)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    if ((rad32 == nullptr) == (rad64 == nullptr)) return fail(ctx, RTX_ERR_INVALID, "rtx_quantise: pass exactly one radiance buffer");
+    if (n_pixels < 0 || !rgba8) return fail(ctx, RTX_ERR_INVALID, "rtx_quantise: bad size or null output");
+    if (mode != RTX_QUANT_WRAP && mode != RTX_QUANT_SATURATE) return fail(ctx, RTX_ERR_INVALID, "rtx_quantise: unknown mode");
+    if (memory != RTX_MEM_HOST && memory != RTX_MEM_DEVICE) return fail(ctx, RTX_ERR_INVALID, "rtx_quantise: bad memory kind");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t in_bytes = static_cast<size_t>(n_pixels) * (rad32 ? 12 : 24);
+    const void* d_in = rad32 ? static_cast<const void*>(rad32) : static_cast<const void*>(rad64);
+    uint32_t* d_o = rgba8;
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    if (memory == RTX_MEM_HOST) {
+        void* pp = ctx->d_rad_scratch;
+        int rc = grow(ctx, &pp, &ctx->d_rad_scratch_cap, std::max<size_t>(in_bytes, 16));
+        ctx->d_rad_scratch = static_cast<double*>(pp);
+        if (rc != RTX_OK) return rc;
+        rc = grow(ctx, &ctx->d_out[0], &ctx->d_out_cap[0], std::max<size_t>(static_cast<size_t>(n_pixels) * 4, 16));
+        if (rc != RTX_OK) return rc;
+        RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rad_scratch, d_in, in_bytes, cudaMemcpyHostToDevice, st));
+        d_in = ctx->d_rad_scratch;
+        d_o = static_cast<uint32_t*>(ctx->d_out[0]);
+    }
+    RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    if (rad32)
+        RTX_CUDA(ctx, launch_quantise_f32(static_cast<const float*>(d_in), n_pixels, mode, d_o, ctx->d_counters, ctx->n_sms, st));
+    else
+        RTX_CUDA(ctx, launch_quantise_f64(static_cast<const double*>(d_in), n_pixels, mode, d_o, ctx->d_counters, ctx->n_sms, st));
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    if (memory == RTX_MEM_HOST)
+        RTX_CUDA(ctx, cudaMemcpyAsync(rgba8, d_o, static_cast<size_t>(n_pixels) * 4, cudaMemcpyDeviceToHost, st));
+    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    RTX_CUDA(ctx, cudaStreamSynchronize(st));
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); stats->h2d_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); stats->surface_update_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); stats->d2h_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); stats->total_ms = ms;
+        stats->over_range_pixels = ctx->h_counters[2];
+        long long bits = static_cast<long long>(ctx->h_counters[3]);
+        std::memcpy(&stats->max_luminance, &bits, sizeof bits);
+        stats->launches = 1;
+    }
+    ctx->error.clear();
+    return RTX_OK;
+}
+
+int rtx_unpermute_bands(rtx_ctx* ctx, const void* band_major, void* row_major, int32_t height, int32_t width, int32_t elem_bytes,
+                        int32_t band_rows, int32_t n_ranks, int32_t rows_per_rank)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    if (!band_major || !row_major || height <= 0 || width <= 0 || band_rows <= 0 || n_ranks <= 0 || (elem_bytes != 1 && elem_bytes != 4))
+        return fail(ctx, RTX_ERR_INVALID, "rtx_unpermute_bands: bad argument");
+    for (int r = 0; r < n_ranks; r++)
+        if (rtx_local_rows(height, band_rows, n_ranks, r) > rows_per_rank)
+            return fail(ctx, RTX_ERR_INVALID, "rtx_unpermute_bands: rows_per_rank smaller than a rank's row count");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    RTX_CUDA(ctx, launch_unpermute(band_major, row_major, height, width, elem_bytes, band_rows, n_ranks, rows_per_rank, ctx->stream));
+    RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->error.clear();
+    return RTX_OK;
+}
+
+int rtx_ffma_peak(rtx_ctx* ctx, int32_t variant, double* tflops, double* mhz)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    if (variant != 0 && variant != 1) return fail(ctx, RTX_ERR_INVALID, "rtx_ffma_peak: variant must be 0 or 1");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    RTX_CUDA(ctx, run_ffma_peak(variant, ctx->n_sms, ctx->stream, tflops, mhz));
+    ctx->error.clear();
+    return RTX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,272 @@
+// aux_kernels.cu — the HBM-side kernels around the trace kernel:
+//
+//   quantise_*      the reference's 8-bit pack loop (main.cpp:338-347) as a vectorised streaming kernel
+//                   (4 pixels per thread: 128-bit loads, one 128-bit uchar4x4 store) with warp-shuffle
+//                   reductions for the two frame statistics (over-range pixel count, max luminance);
+//   unpermute_*     scatter of all-gathered cyclic row bands into a row-major frame (multi-GPU epilogue);
+//   ffma_peak_*     FP32 FMA throughput microbenchmark — the roofline denominator of the trace kernel,
+//                   which MEASURED_PEAKS.json does not carry.
+#include "rtx_device.cuh"
+
+namespace rtx {
+
+constexpr unsigned kFullMask = 0xFFFFFFFFu;
+
+struct FrameStats {
+    unsigned long long over;
+    double maxlum;
+};
+
+__device__ __forceinline__ void stats_add(FrameStats& s, double r, double g, double b)
+{
+    if (over_range(r, g, b)) s.over++;
+    const double lum = (r + g + b) * (1.0 / 3.0);
+    if (lum > s.maxlum) s.maxlum = lum;
+}
+
+__device__ __forceinline__ void stats_commit(FrameStats s, unsigned long long* counters)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s.over += __shfl_down_sync(kFullMask, s.over, off);
+        s.maxlum = fmax(s.maxlum, __shfl_down_sync(kFullMask, s.maxlum, off));
+    }
+    if ((threadIdx.x & 31) == 0 && counters) {
+        if (s.over) atomicAdd(&counters[2], s.over);
+        if (s.maxlum > 0.0) atomicMax(&counters[3], static_cast<unsigned long long>(__double_as_longlong(s.maxlum)));
+    }
+}
+
+// float radiance: 4 pixels = 12 floats = three float4 loads -> one uint4 store.
+__global__ void __launch_bounds__(256) quantise_f32_kernel(const float* __restrict__ rad, long long n_pixels, int mode,
+                                                           uint32_t* __restrict__ out, unsigned long long* counters)
+{
+    FrameStats st{0ull, 0.0};
+    const long long n_quads = n_pixels >> 2;
+    const float4* __restrict__ in4 = reinterpret_cast<const float4*>(rad);
+    uint4* __restrict__ out4 = reinterpret_cast<uint4*>(out);
+    for (long long qd = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; qd < n_quads;
+         qd += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 a = __ldcs(&in4[3 * qd + 0]);
+        const float4 b = __ldcs(&in4[3 * qd + 1]);
+        const float4 c = __ldcs(&in4[3 * qd + 2]);
+        uint4 o;
+        o.x = pack_rgba(a.x, a.y, a.z, mode);
+        o.y = pack_rgba(a.w, b.x, b.y, mode);
+        o.z = pack_rgba(b.z, b.w, c.x, mode);
+        o.w = pack_rgba(c.y, c.z, c.w, mode);
+        stats_add(st, a.x, a.y, a.z);
+        stats_add(st, a.w, b.x, b.y);
+        stats_add(st, b.z, b.w, c.x);
+        stats_add(st, c.y, c.z, c.w);
+        __stcs(&out4[qd], o);
+    }
+    // ragged tail (n_pixels not a multiple of 4)
+    if (blockIdx.x == 0 && threadIdx.x < (n_pixels & 3)) {
+        const long long p = (n_quads << 2) + threadIdx.x;
+        const double r = rad[3 * p], g = rad[3 * p + 1], b = rad[3 * p + 2];
+        out[p] = pack_rgba(r, g, b, mode);
+        stats_add(st, r, g, b);
+    }
+    stats_commit(st, counters);
+}
+
+// double radiance: 4 pixels = 12 doubles = six double2 loads -> one uint4 store.
+__global__ void __launch_bounds__(256) quantise_f64_kernel(const double* __restrict__ rad, long long n_pixels, int mode,
+                                                           uint32_t* __restrict__ out, unsigned long long* counters)
+{
+    FrameStats st{0ull, 0.0};
+    const long long n_quads = n_pixels >> 2;
+    const double2* __restrict__ in2 = reinterpret_cast<const double2*>(rad);
+    uint4* __restrict__ out4 = reinterpret_cast<uint4*>(out);
+    for (long long qd = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; qd < n_quads;
+         qd += static_cast<long long>(gridDim.x) * blockDim.x) {
+        double2 v[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) v[k] = __ldcs(&in2[6 * qd + k]);
+        uint4 o;
+        o.x = pack_rgba(v[0].x, v[0].y, v[1].x, mode);
+        o.y = pack_rgba(v[1].y, v[2].x, v[2].y, mode);
+        o.z = pack_rgba(v[3].x, v[3].y, v[4].x, mode);
+        o.w = pack_rgba(v[4].y, v[5].x, v[5].y, mode);
+        stats_add(st, v[0].x, v[0].y, v[1].x);
+        stats_add(st, v[1].y, v[2].x, v[2].y);
+        stats_add(st, v[3].x, v[3].y, v[4].x);
+        stats_add(st, v[4].y, v[5].x, v[5].y);
+        __stcs(&out4[qd], o);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n_pixels & 3)) {
+        const long long p = (n_quads << 2) + threadIdx.x;
+        const double r = rad[3 * p], g = rad[3 * p + 1], b = rad[3 * p + 2];
+        out[p] = pack_rgba(r, g, b, mode);
+        stats_add(st, r, g, b);
+    }
+    stats_commit(st, counters);
+}
+
+static int stream_grid(long long work_items, int threads, int n_sms)
+{
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = static_cast<long long>(n_sms) * 8;   // 8 x 256 threads = full occupancy, whole waves
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<int>(blocks);
+}
+
+cudaError_t launch_quantise_f64(const double* rad, int64_t n_pixels, int mode, uint32_t* rgba8,
+                                unsigned long long* counters, int n_sms, cudaStream_t stream)
+{
+    if (n_pixels <= 0) return cudaSuccess;
+    quantise_f64_kernel<<<stream_grid((n_pixels + 3) / 4, 256, n_sms), 256, 0, stream>>>(rad, n_pixels, mode, rgba8, counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_quantise_f32(const float* rad, int64_t n_pixels, int mode, uint32_t* rgba8,
+                                unsigned long long* counters, int n_sms, cudaStream_t stream)
+{
+    if (n_pixels <= 0) return cudaSuccess;
+    quantise_f32_kernel<<<stream_grid((n_pixels + 3) / 4, 256, n_sms), 256, 0, stream>>>(rad, n_pixels, mode, rgba8, counters);
+    return cudaGetLastError();
+}
+
+// ---- multi-GPU epilogue ----------------------------------------------------------------------------------
+// dst row i lives in band b = i / band_rows, owned by rank b % n_ranks, at packed local row
+// (b / n_ranks) * band_rows + i % band_rows of that rank's block.
+template <typename T>
+__global__ void __launch_bounds__(256) unpermute_kernel(const T* __restrict__ src, T* __restrict__ dst, int height,
+                                                        int row_elems, int band_rows, int n_ranks, int rows_per_rank)
+{
+    const long long total = static_cast<long long>(height) * row_elems;
+    for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int i = static_cast<int>(e / row_elems);
+        const int x = static_cast<int>(e - static_cast<long long>(i) * row_elems);
+        const int band = i / band_rows;
+        const int r = band % n_ranks;
+        const int lrow = (band / n_ranks) * band_rows + (i - band * band_rows);
+        dst[e] = src[(static_cast<long long>(r) * rows_per_rank + lrow) * row_elems + x];
+    }
+}
+
+cudaError_t launch_unpermute(const void* band_major, void* row_major, int height, int width, int elem_bytes,
+                             int band_rows, int n_ranks, int rows_per_rank, cudaStream_t stream)
+{
+    const long long row_bytes = static_cast<long long>(width) * elem_bytes;
+    const bool vec16 = (row_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(band_major) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(row_major) % 16 == 0);
+    if (vec16) {
+        const int row_elems = static_cast<int>(row_bytes / 16);
+        const long long total = static_cast<long long>(height) * row_elems;
+        unpermute_kernel<uint4><<<stream_grid(total, 256, 148), 256, 0, stream>>>(
+            static_cast<const uint4*>(band_major), static_cast<uint4*>(row_major), height, row_elems, band_rows, n_ranks,
+            rows_per_rank);
+    } else if (elem_bytes == 4) {
+        const long long total = static_cast<long long>(height) * width;
+        unpermute_kernel<uint32_t><<<stream_grid(total, 256, 148), 256, 0, stream>>>(
+            static_cast<const uint32_t*>(band_major), static_cast<uint32_t*>(row_major), height, width, band_rows, n_ranks,
+            rows_per_rank);
+    } else {
+        const long long total = static_cast<long long>(height) * width;
+        unpermute_kernel<uint8_t><<<stream_grid(total, 256, 148), 256, 0, stream>>>(
+            static_cast<const uint8_t*>(band_major), static_cast<uint8_t*>(row_major), height, width, band_rows, n_ranks,
+            rows_per_rank);
+    }
+    return cudaGetLastError();
+}
+
+// ---- FP32 peak microbenchmark --------------------------------------------------------------------------------
+constexpr int kPeakChains = 16;
+constexpr int kPeakIters = 4096;
+
+__global__ void __launch_bounds__(512) ffma_peak_scalar(float* sink, float a, float b, long long* clocks)
+{
+    float acc[kPeakChains];
+#pragma unroll
+    for (int k = 0; k < kPeakChains; k++) acc[k] = threadIdx.x * 1e-3f + k;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kPeakIters; it++) {
+#pragma unroll
+        for (int k = 0; k < kPeakChains; k++) acc[k] = fmaf(acc[k], a, b);
+    }
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kPeakChains; k++) s += acc[k];
+    if (s == 123.456f) sink[0] = s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) clocks[0] = t1 - t0;
+}
+
+__global__ void __launch_bounds__(512) ffma_peak_packed(float* sink, float a, float b, long long* clocks)
+{
+    unsigned long long acc[kPeakChains / 2];
+    unsigned long long av, bv;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+#pragma unroll
+    for (int k = 0; k < kPeakChains / 2; k++) {
+        const float lo = threadIdx.x * 1e-3f + k, hi = lo + 0.5f;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(acc[k]) : "f"(lo), "f"(hi));
+    }
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kPeakIters; it++) {
+#pragma unroll
+        for (int k = 0; k < kPeakChains / 2; k++)
+            asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[k]) : "l"(av), "l"(bv));
+    }
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kPeakChains / 2; k++) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[k]));
+        s += lo + hi;
+    }
+    if (s == 123.456f) sink[0] = s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) clocks[0] = t1 - t0;
+}
+
+cudaError_t run_ffma_peak(int variant, int n_sms, cudaStream_t stream, double* tflops, double* mhz)
+{
+    float* sink = nullptr;
+    long long* clocks = nullptr;
+    cudaError_t err = cudaMalloc(&sink, sizeof(float));
+    if (err != cudaSuccess) return err;
+    err = cudaMalloc(&clocks, sizeof(long long));
+    if (err != cudaSuccess) { cudaFree(sink); return err; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = n_sms * 4 * 8, threads = 512;   // 8 waves of 4 CTAs per SM
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0, stream);
+        if (variant == 1)
+            ffma_peak_packed<<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
+        else
+            ffma_peak_scalar<<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
+        cudaEventRecord(e1, stream);
+        err = cudaEventSynchronize(e1);
+        if (err != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    if (err == cudaSuccess) err = cudaGetLastError();
+    if (err == cudaSuccess) {
+        const double flops = 2.0 * kPeakChains * kPeakIters * static_cast<double>(blocks) * threads;
+        if (tflops) *tflops = flops / (best_ms * 1e-3) / 1e12;
+        long long h_clocks = 0;
+        cudaMemcpy(&h_clocks, clocks, sizeof h_clocks, cudaMemcpyDeviceToHost);
+        // one CTA's loop in SM cycles vs. the whole launch in time: 32 CTAs per SM run in 8 waves
+        if (mhz) *mhz = static_cast<double>(h_clocks) * 8.0 / (best_ms * 1e-3) / 1e6;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    cudaFree(clocks);
+    return err;
+}
+
+}  // namespace rtx

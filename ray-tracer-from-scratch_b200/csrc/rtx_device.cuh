@@ -1,0 +1,151 @@
+// rtx_device.cuh — device-side data layout and the exact-double vocabulary of the trace kernel.
+//
+// The reference computes everything in IEEE double without FMA contraction (x86-64 baseline build,
+// CMakeLists.txt:23). Every helper in namespace ex:: therefore uses the explicitly rounded intrinsics
+// (__dadd_rn, __dmul_rn, __ddiv_rn, __dsqrt_rn), which nvcc never fuses into DFMA, and keeps the
+// reference's operation order (cited per function). That is what makes object ids and distances
+// bit-identical to the reference, not merely "close".
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "rtx_b200.h"
+
+namespace rtx {
+
+struct d3 {
+    double x, y, z;
+};
+
+namespace ex {
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+
+__device__ __forceinline__ d3 mk(double x, double y, double z) { return d3{x, y, z}; }
+__device__ __forceinline__ d3 mk(const rtx_vec3& v) { return d3{v.x, v.y, v.z}; }
+// vec3::dot, vec.cpp:11-14: (x*x' + y*y') + z*z'
+__device__ __forceinline__ double dot(d3 a, d3 b) { return add(add(mul(a.x, b.x), mul(a.y, b.y)), mul(a.z, b.z)); }
+// vec3::length_squared / length, vec.cpp:3-9
+__device__ __forceinline__ double len2(d3 a) { return add(add(mul(a.x, a.x), mul(a.y, a.y)), mul(a.z, a.z)); }
+__device__ __forceinline__ double len(d3 a) { return sqrt(len2(a)); }
+__device__ __forceinline__ d3 add(d3 a, d3 b) { return d3{add(a.x, b.x), add(a.y, b.y), add(a.z, b.z)}; }   // vec.cpp:26-28
+__device__ __forceinline__ d3 sub(d3 a, d3 b) { return d3{sub(a.x, b.x), sub(a.y, b.y), sub(a.z, b.z)}; }   // vec.cpp:32-34
+__device__ __forceinline__ d3 neg(d3 a) { return d3{-a.x, -a.y, -a.z}; }                                    // vec.cpp:29-31
+__device__ __forceinline__ d3 scale(d3 a, double s) { return d3{mul(a.x, s), mul(a.y, s), mul(a.z, s)}; }   // vec.cpp:38-40
+__device__ __forceinline__ d3 divs(d3 a, double s) { return d3{div(a.x, s), div(a.y, s), div(a.z, s)}; }    // vec.cpp:41-43
+// vec3::normalize, vec.cpp:21-24: three divides by length(), not a multiply by the reciprocal
+__device__ __forceinline__ d3 unit(d3 a) { return divs(a, len(a)); }
+// vec3::linear_interp, vec.cpp:45-49: a + d*(b - a)
+__device__ __forceinline__ d3 lerp(d3 a, d3 b, double t)
+{
+    return d3{add(a.x, mul(t, sub(b.x, a.x))), add(a.y, mul(t, sub(b.y, a.y))), add(a.z, mul(t, sub(b.z, a.z)))};
+}
+}  // namespace ex
+
+// ---- device copy of the scene (built by rtx_set_scene) --------------------------------------------
+//
+// Spheres and walls are split into two SoA-ish arrays (the "type-switched, warp-uniform hit loop"
+// replacing the virtual SceneGeometry::intersect, scene.h:51-60); `id` maps back to the index in the
+// reference's scene vector, which is both the object id and the tie-break order (main.cpp:77-80).
+
+struct SphereExact {   // 32 B, read only for filter survivors
+    double cx, cy, cz, r;
+};
+
+struct WallDev {       // everything Wall::intersect needs, with the ray-independent basis precomputed
+    d3 p;              // corner (scene.h:64)
+    d3 n;              // normal after the ctor's normalize (scene.h:71)
+    d3 right;          // normalize(cross(n, (0,0,1)))        scene.cpp:18
+    d3 up;             // normalize(cross(right, n))          scene.cpp:19
+    double length, width;
+    int32_t id;
+    int32_t pad;
+};
+
+struct MaterialDev {   // Material (scene.h:35-49), indexed by scene id
+    d3 color;
+    double ambient, metallic, diffuse, specular, exponent;
+};
+
+struct SceneDev {
+    int32_t n_objects, n_spheres, n_walls;
+    int32_t n_spheres_padded;          // multiple of the hot loop's unroll factor
+    const float4* sph32;               // [n_spheres_padded] (cx, cy, cz, r) rounded to nearest float; pad r = -1
+    const SphereExact* sph64;          // [n_spheres]
+    const int32_t* sph_id;             // [n_spheres]
+    const WallDev* walls;              // [n_walls]
+    const MaterialDev* mats;           // [n_objects]
+    const int32_t* kind;               // [n_objects] RTX_SPHERE | RTX_WALL
+    const int32_t* slot;               // [n_objects] index into sph64 / walls
+};
+
+// Per-launch arguments of the trace kernel.
+struct TraceArgs {
+    SceneDev scene;
+    const rtx_camera* cameras;         // [n_frames] device copy
+    int32_t n_frames, width, height;   // global frame size
+    int32_t local_rows;                // rows this rank renders per frame
+    int32_t band_rows, n_ranks, rank;
+    int32_t max_depth, quantise_mode;
+    d3 light, ground, sky_low, sky_high;
+    double reflect_offset, sky_exponent;
+    float filter_eps;                  // E: bound on the FP32 filter's distance error (see trace.cu)
+    float origin_bound;                // rays whose origin exceeds this fall back to exact tests
+    // outputs (device pointers, any may be null)
+    uint32_t* rgba8;
+    float* rad32;
+    double* rad64;
+    int32_t* object_id;
+    uint8_t* hit_mask;
+    uint8_t* ray_count;
+    // counters: [0] next pixel, [1] total rays, [2] over-range pixels, [3] max luminance (double bits)
+    unsigned long long* counters;
+};
+
+// Reference quantise, main.cpp:345: implicit double -> Uint8. g++ emits cvttsd2si (32-bit) and keeps the
+// low byte: truncation toward zero, wrap mod 256; NaN or |v| >= 2^31 give 0x80000000 -> byte 0.
+// CUDA's own conversion saturates instead, so the out-of-range cases are spelled out.
+__device__ __forceinline__ uint32_t to_u8_wrap(double v)
+{
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return 0u;
+    return static_cast<uint32_t>(__double2int_rz(v)) & 0xFFu;
+}
+__device__ __forceinline__ uint32_t to_u8_sat(double v)
+{
+    if (!(v > 0.0)) return 0u;
+    if (v >= 255.0) return 255u;
+    return static_cast<uint32_t>(__double2int_rz(v));
+}
+// SDL_MapRGB for the RGBA8888 masks of main.cpp:193.
+__device__ __forceinline__ uint32_t pack_rgba(double r, double g, double b, int mode)
+{
+    const double R = ex::mul(r, 255.0), G = ex::mul(g, 255.0), B = ex::mul(b, 255.0);
+    uint32_t ur, ug, ub;
+    if (mode == RTX_QUANT_SATURATE) {
+        ur = to_u8_sat(R); ug = to_u8_sat(G); ub = to_u8_sat(B);
+    } else {
+        ur = to_u8_wrap(R); ug = to_u8_wrap(G); ub = to_u8_wrap(B);
+    }
+    return (ur << 24) | (ug << 16) | (ub << 8) | 0xFFu;
+}
+// A channel is "over range" when the reference's wrap would alter it: v*255 outside [0,256).
+__device__ __forceinline__ bool over_range(double r, double g, double b)
+{
+    const double R = ex::mul(r, 255.0), G = ex::mul(g, 255.0), B = ex::mul(b, 255.0);
+    return !(R >= 0.0 && R < 256.0 && G >= 0.0 && G < 256.0 && B >= 0.0 && B < 256.0);
+}
+
+// Launch wrappers implemented in the .cu files, called by api.cu.
+cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, int* launches);
+cudaError_t launch_quantise_f64(const double* rad, int64_t n_pixels, int mode, uint32_t* rgba8,
+                                unsigned long long* counters, int n_sms, cudaStream_t stream);
+cudaError_t launch_quantise_f32(const float* rad, int64_t n_pixels, int mode, uint32_t* rgba8,
+                                unsigned long long* counters, int n_sms, cudaStream_t stream);
+cudaError_t launch_unpermute(const void* band_major, void* row_major, int height, int width, int elem_bytes,
+                             int band_rows, int n_ranks, int rows_per_rank, cudaStream_t stream);
+cudaError_t run_ffma_peak(int variant, int n_sms, cudaStream_t stream, double* tflops, double* mhz);
+
+}  // namespace rtx

@@ -1,0 +1,268 @@
+"""ctypes binding of librtx_b200.so (include/rtx_b200.h) plus the `rt_scene`-shaped convenience call.
+
+This module is host plumbing only: every pixel is computed by the CUDA kernels behind the C ABI.
+There is no CPU fallback — if the library is missing or no B200 is visible, calls raise.
+
+    r = Renderer(device=0)
+    r.set_scene(scene.default_scene())
+    out = r.render([scene.default_camera().pod()], want=("rgba8", "object_id"))     # numpy planes [F][rows][W]
+
+`rt_scene(u, scene, cam, frame_buffer)` mirrors the reference's entry point (main.cpp:124-125).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi, scene as scene_mod
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librtx_b200.so")
+
+_lib = None
+
+
+class RtxError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("rtx status %d (%s): %s" % (status, _status_name(status), message))
+        self.status = status
+
+
+def _status_name(status):
+    return {0: "ok", 1: "invalid", 2: "cuda", 3: "no_scene", 4: "nomem"}.get(status, "?")
+
+
+def load_library(path=LIB_PATH):
+    """Loads the C-ABI library and declares every entry point of include/rtx_b200.h."""
+    global _lib
+    if _lib is not None and path == LIB_PATH:
+        return _lib
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            "%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the hot path)" % path)
+    lib = C.CDLL(path)
+    ctx = C.c_void_p
+    lib.rtx_abi_version.restype = C.c_int
+    lib.rtx_abi_version.argtypes = []
+    lib.rtx_status_string.restype = C.c_char_p
+    lib.rtx_status_string.argtypes = [C.c_int]
+    lib.rtx_create.restype = C.c_int
+    lib.rtx_create.argtypes = [C.POINTER(ctx), C.c_int]
+    lib.rtx_destroy.restype = None
+    lib.rtx_destroy.argtypes = [ctx]
+    lib.rtx_last_error.restype = C.c_char_p
+    lib.rtx_last_error.argtypes = [ctx]
+    lib.rtx_set_stream.restype = C.c_int
+    lib.rtx_set_stream.argtypes = [ctx, C.c_void_p]
+    lib.rtx_set_scene.restype = C.c_int
+    lib.rtx_set_scene.argtypes = [ctx, C.POINTER(abi.ObjectPOD), C.c_int32]
+    lib.rtx_camera_init.restype = C.c_int
+    lib.rtx_camera_init.argtypes = [C.POINTER(abi.CameraDesc), C.POINTER(abi.CameraPOD)]
+    lib.rtx_default_params.restype = None
+    lib.rtx_default_params.argtypes = [C.POINTER(abi.Params)]
+    lib.rtx_local_rows.restype = C.c_int32
+    lib.rtx_local_rows.argtypes = [C.c_int32] * 4
+    lib.rtx_global_row.restype = C.c_int32
+    lib.rtx_global_row.argtypes = [C.c_int32] * 5
+    lib.rtx_render.restype = C.c_int
+    lib.rtx_render.argtypes = [ctx, C.POINTER(abi.CameraPOD), C.c_int32, C.POINTER(abi.Params),
+                               C.POINTER(abi.Outputs), C.POINTER(abi.Stats)]
+    lib.rtx_quantise.restype = C.c_int
+    lib.rtx_quantise.argtypes = [ctx, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
+                                 C.POINTER(abi.Stats)]
+    lib.rtx_unpermute_bands.restype = C.c_int
+    lib.rtx_unpermute_bands.argtypes = [ctx, C.c_void_p, C.c_void_p] + [C.c_int32] * 6
+    lib.rtx_ffma_peak.restype = C.c_int
+    lib.rtx_ffma_peak.argtypes = [ctx, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    if lib.rtx_abi_version() != abi.ABI_VERSION:
+        raise RuntimeError("librtx_b200.so ABI %d != binding ABI %d" % (lib.rtx_abi_version(), abi.ABI_VERSION))
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def default_params(**overrides):
+    """rtx_params with the reference's literals (main.cpp:14-17,34,89,111), then keyword overrides."""
+    p = abi.Params()
+    load_library().rtx_default_params(C.byref(p))
+    for k, v in overrides.items():
+        if k in ("light_pos", "ground_color", "sky_low", "sky_high"):
+            v = abi.Vec3(*v)
+        if not hasattr(p, k):
+            raise AttributeError("rtx_params has no field %r" % k)
+        setattr(p, k, v)
+    return p
+
+
+def camera_init(cam):
+    """Camera::init through the library (host code of the C ABI). cam: scene.Camera."""
+    out = abi.CameraPOD()
+    d = cam.desc()
+    rc = load_library().rtx_camera_init(C.byref(d), C.byref(out))
+    if rc != abi.RTX_OK:
+        raise RtxError(rc, "rtx_camera_init")
+    return out
+
+
+def local_rows(height, band_rows, n_ranks, rank):
+    return load_library().rtx_local_rows(height, band_rows, n_ranks, rank)
+
+
+def global_rows(height, band_rows, n_ranks, rank):
+    """Global row index of every packed local row of `rank` (numpy int32)."""
+    lib = load_library()
+    n = lib.rtx_local_rows(height, band_rows, n_ranks, rank)
+    return np.array([lib.rtx_global_row(k, height, band_rows, n_ranks, rank) for k in range(n)], dtype=np.int32)
+
+
+_PLANES = {  # name -> (Outputs field, numpy dtype, trailing shape)
+    "rgba8": ("rgba8", np.uint32, ()),
+    "radiance_f32": ("radiance_f32", np.float32, (3,)),
+    "radiance_f64": ("radiance_f64", np.float64, (3,)),
+    "object_id": ("object_id", np.int32, ()),
+    "hit_mask": ("hit_mask", np.uint8, ()),
+    "ray_count": ("ray_count", np.uint8, ()),
+}
+
+
+class Renderer:
+    """One rtx_ctx (one GPU)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self._ctx = C.c_void_p()
+        rc = self.lib.rtx_create(C.byref(self._ctx), int(device))
+        if rc != abi.RTX_OK:
+            msg = self.lib.rtx_last_error(None)
+            raise RtxError(rc, (msg or b"").decode() or "rtx_create failed")
+        self.device = device
+        self.n_objects = 0
+        self.last_stats = None
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self.lib.rtx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != abi.RTX_OK:
+            raise RtxError(rc, (self.lib.rtx_last_error(self._ctx) or b"").decode())
+
+    def set_stream(self, cuda_stream_handle):
+        """cuda_stream_handle: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+        self._check(self.lib.rtx_set_stream(self._ctx, C.c_void_p(cuda_stream_handle or 0)))
+
+    def set_scene(self, scene):
+        """scene: list of scene.Sphere / scene.Wall in scene order, or a ctypes array of rtx_object."""
+        if isinstance(scene, C.Array):
+            objs, n = scene, len(scene)
+        else:
+            objs, n = scene_mod.flatten(scene), len(scene)
+        self._check(self.lib.rtx_set_scene(self._ctx, objs, n))
+        self.n_objects = n
+
+    def render_raw(self, cams, params, outputs):
+        """Direct rtx_render with caller-built ctypes structures (device or host pointers). Returns Stats."""
+        arr = (abi.CameraPOD * len(cams))(*cams)
+        st = abi.Stats()
+        self._check(self.lib.rtx_render(self._ctx, arr, len(cams), C.byref(params), C.byref(outputs), C.byref(st)))
+        self.last_stats = st
+        return st
+
+    def render(self, cams, params=None, want=("rgba8",), out=None):
+        """Renders len(cams) frames into host numpy planes shaped [F][rows][W](+[3]).
+        `out` may carry preallocated (e.g. pinned) arrays by plane name. Returns (planes dict, Stats)."""
+        if isinstance(cams, abi.CameraPOD):
+            cams = [cams]
+        params = params if params is not None else default_params()
+        W, H = cams[0].width, cams[0].height
+        rows = H if params.n_ranks <= 1 else self.lib.rtx_local_rows(H, params.band_rows, params.n_ranks, params.rank)
+        o = abi.Outputs()
+        o.memory = abi.RTX_MEM_HOST
+        planes = {}
+        for name in want:
+            field, dtype, tail = _PLANES[name]
+            shape = (len(cams), rows, W) + tail
+            a = out[name] if out is not None and name in out else np.empty(shape, dtype)
+            if a.dtype != dtype or a.size != int(np.prod(shape)) or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("output plane %s must be C-contiguous %s of shape %s" % (name, dtype, shape))
+            planes[name] = a.reshape(shape)
+            setattr(o, field, a.ctypes.data)
+        st = self.render_raw(cams, params, o)
+        return planes, st
+
+    def quantise(self, radiance, mode=abi.RTX_QUANT_WRAP):
+        """Standalone quantise pass (main.cpp:338-347) on a host float32/float64 array of RGB triples."""
+        rad = np.ascontiguousarray(radiance)
+        if rad.dtype not in (np.float32, np.float64):
+            raise ValueError("radiance must be float32 or float64")
+        n = rad.size // 3
+        out = np.empty(n, np.uint32)
+        st = abi.Stats()
+        p32 = rad.ctypes.data if rad.dtype == np.float32 else None
+        p64 = rad.ctypes.data if rad.dtype == np.float64 else None
+        self._check(self.lib.rtx_quantise(self._ctx, p32, p64, n, int(mode), out.ctypes.data, abi.RTX_MEM_HOST,
+                                          C.byref(st)))
+        self.last_stats = st
+        return out.reshape(rad.shape[:-1]) if rad.ndim > 1 else out
+
+    def quantise_device(self, rad_ptr, is_f32, n_pixels, out_ptr, mode=abi.RTX_QUANT_WRAP):
+        st = abi.Stats()
+        self._check(self.lib.rtx_quantise(self._ctx, rad_ptr if is_f32 else None, None if is_f32 else rad_ptr,
+                                          int(n_pixels), int(mode), out_ptr, abi.RTX_MEM_DEVICE, C.byref(st)))
+        self.last_stats = st
+        return st
+
+    def unpermute_bands(self, band_major_ptr, row_major_ptr, height, width, elem_bytes, band_rows, n_ranks,
+                        rows_per_rank):
+        self._check(self.lib.rtx_unpermute_bands(self._ctx, band_major_ptr, row_major_ptr, height, width, elem_bytes,
+                                                 band_rows, n_ranks, rows_per_rank))
+
+    def ffma_peak(self, variant=0):
+        t, m = C.c_double(), C.c_double()
+        self._check(self.lib.rtx_ffma_peak(self._ctx, variant, C.byref(t), C.byref(m)))
+        return t.value, m.value
+
+
+_default_renderer = None
+
+
+def rt_scene(u, scene, cam, frame_buffer, max_depth=10):
+    """Drop-in shape of the reference's `rt_scene(u, scene, cam, frame_buffer)` (main.cpp:124-139):
+    u = [pixel_delta_x, pixel_delta_y] as returned by cam.init(); scene = list of Sphere/Wall; cam = scene.Camera;
+    frame_buffer = float64 array [image_height][image_width][3], overwritten in place (row i, column j)."""
+    global _default_renderer
+    if _default_renderer is None:
+        _default_renderer = Renderer(0)
+    pod = cam.pod()
+    pod.delta_x, pod.delta_y = abi.Vec3(*u[0]), abi.Vec3(*u[1])
+    fb = np.asarray(frame_buffer)
+    if fb.dtype != np.float64 or fb.shape != (pod.height, pod.width, 3) or not fb.flags["C_CONTIGUOUS"]:
+        raise ValueError("frame_buffer must be a C-contiguous float64 array [image_height][image_width][3]")
+    _default_renderer.set_scene(scene)
+    _default_renderer.render([pod], default_params(max_depth=max_depth), want=("radiance_f64",),
+                             out={"radiance_f64": fb})
+    return fb
+
+
+def write_ppm(path, rgba8):
+    """Headless output (replaces the SDL present, main.cpp:351-358): binary PPM from RGBA8888 words."""
+    a = np.asarray(rgba8, dtype=np.uint32)
+    h, w = a.shape
+    rgb = np.stack([(a >> 24) & 0xFF, (a >> 16) & 0xFF, (a >> 8) & 0xFF], axis=-1).astype(np.uint8)
+    with open(path, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (w, h))
+        f.write(rgb.tobytes())

@@ -1,0 +1,267 @@
+"""GPU suite: the CUDA path, called through the C ABI, against the oracle and the committed golden fixtures.
+
+Bars (BASELINE.json north_star): object-id / hit-mask bit-exact (we additionally require ray counts and RGBA8 to be
+identical — the kernel takes every hit decision in the reference's own double arithmetic); radiance relative error
+<= 1e-4 with denominator max(|ref|, 1e-3) — asserted here at the much tighter 1e-12, the only divergence being
+libm-vs-CUDA pow (<= 2 ulp) and the front-to-back accumulation order of the reflection lerp.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import fh3, load_golden_frame, load_json
+
+pytestmark = pytest.mark.gpu
+
+WANT = ("rgba8", "radiance_f64", "radiance_f32", "object_id", "hit_mask", "ray_count")
+RAD_TOL = 1e-12          # asserted; the contract's tolerance is 1e-4
+RAD_TOL_CONTRACT = 1e-4
+
+
+def rel_err(got, exp):
+    return np.abs(got - exp) / np.maximum(np.abs(exp), 1e-3)
+
+
+def check_frame(got, exp, st=None):
+    assert np.array_equal(got["object_id"], exp["object_id"])
+    assert np.array_equal(got["hit_mask"], exp["hit_mask"])
+    assert np.array_equal(got["ray_count"], exp["ray_count"])
+    e64 = rel_err(got["radiance_f64"], exp["radiance"])
+    assert np.nanmax(e64) < RAD_TOL, np.nanmax(e64)
+    e32 = rel_err(got["radiance_f32"].astype(np.float64), exp["radiance"])
+    assert np.nanmax(e32) < RAD_TOL_CONTRACT
+    lsb = np.abs(unpack(got["rgba8"]).astype(int) - unpack(exp["rgba8"]).astype(int))
+    assert lsb.max() <= 1                                  # the contract
+    assert np.array_equal(got["rgba8"], exp["rgba8"])      # what we actually deliver
+    if st is not None:
+        assert st.total_rays == int(exp["ray_count"].astype(np.int64).sum())
+
+
+def unpack(rgba):
+    a = np.asarray(rgba, dtype=np.uint32)
+    return np.stack([(a >> 24) & 255, (a >> 16) & 255, (a >> 8) & 255], axis=-1)
+
+
+def render(gpu, renderer_mod, scene, pod, depth, **kw):
+    gpu.set_scene(scene)
+    planes, st = gpu.render([pod], renderer_mod.default_params(max_depth=depth, **kw), want=WANT)
+    return {k: v[0] for k, v in planes.items()}, st
+
+
+@pytest.fixture(scope="module")
+def syn(S):
+    return S.synthetic_scene()
+
+
+def test_c1_default_frame_matches_reference_hashes(gpu, renderer_mod, S, ob):
+    """640x640 default frame: the reference's own golden hashes (ids, ray counts, RGBA8 surface of main())."""
+    g = load_json("c1_default_640.json")
+    got, st = render(gpu, renderer_mod, S.default_scene(), S.default_camera().pod(), 10)
+    assert hashlib.sha256(got["object_id"].tobytes()).hexdigest() == g["object_id_sha256"]
+    assert hashlib.sha256(got["ray_count"].tobytes()).hexdigest() == g["ray_count_sha256"]
+    assert hashlib.sha256(got["rgba8"].tobytes()).hexdigest() == g["rgba8_sha256"] == g["main_surface_sha256"]
+    assert hashlib.sha256(ob.rgb8_bytes(got["rgba8"]).tobytes()).hexdigest() == g["rgb8_sha256"]
+    assert st.total_rays == g["total_rays"] == 486688
+    for px in g["pixels"]:
+        assert rel_err(got["radiance_f64"][px["i"], px["j"]], np.array(fh3(px["rgb"]))).max() < RAD_TOL
+
+
+@pytest.mark.parametrize("name", ["default_160x90_d8.npz", "synthetic_96x54_d10.npz", "synthetic_384x216_bands_d10.npz",
+                                  "flythrough_96x54_k000.npz", "flythrough_96x54_k048.npz",
+                                  "flythrough_96x54_k128.npz", "flythrough_96x54_k224.npz"])
+def test_golden_frames(gpu, renderer_mod, S, syn, name):
+    g = load_golden_frame(name)
+    scene = syn if name.startswith("synthetic") else S.default_scene()
+    if name.startswith("flythrough"):
+        cam = S.flythrough_cameras(256, g["width"], 16.0 / 9.0)[int(name[-7:-4])]
+    else:
+        cam = S.default_camera(g["width"], 16.0 / 9.0)
+    got, _ = render(gpu, renderer_mod, scene, cam.pod(), g["depth"])
+    got = {k: v[g["rows"]] for k, v in got.items()}
+    check_frame(got, g)
+
+
+@pytest.mark.parametrize("width,aspect,depth", [(320, 16.0 / 9.0, 8), (97, 1.3, 2), (33, 1.0, 0), (1, 1.0, 10), (640, 1.0, 10)])
+def test_default_scene_vs_oracle(gpu, renderer_mod, port, S, width, aspect, depth):
+    scene, pod = S.default_scene(), S.default_camera(width, aspect).pod()
+    got, st = render(gpu, renderer_mod, scene, pod, depth)
+    check_frame(got, port.render(scene, pod, depth), st)
+
+
+def test_synthetic_10k_vs_oracle(gpu, renderer_mod, port, S, syn):
+    """Config C3's scene at a size the oracle finishes in seconds (depth 10, long chains, over-range radiance)."""
+    pod = S.default_camera(128, 16.0 / 9.0).pod()
+    got, st = render(gpu, renderer_mod, syn, pod, 10)
+    exp = port.render(syn, pod, 10)
+    check_frame(got, exp, st)
+    assert exp["ray_count"].max() == 11                              # chains reach the cap
+    assert np.nanmax(exp["radiance"]) > 1.0 and st.over_range_pixels > 0   # the wrap of main.cpp:345 is exercised
+    over = (exp["radiance"] * 255 >= 256).any(axis=-1) | (exp["radiance"] < 0).any(axis=-1)
+    assert st.over_range_pixels == int(over.sum())
+    assert abs(st.max_luminance - exp["radiance"].mean(axis=-1).max()) < 1e-12
+
+
+def test_synthetic_other_viewpoints(gpu, renderer_mod, port, S, syn):
+    """Cameras inside the sphere cloud: origins inside spheres, back faces, grazing hits."""
+    for pos, look in [((30.0, 0.0, 8.0), (29.0, 0.3, 8.1)), ((62.0, 30.0, 20.0), (63.0, 31.0, 20.5)), ((10.0, -20.0, -5.0), (10.0, -21.0, -5.0))]:
+        cam = S.Camera()
+        cam.aspect_ratio, cam.image_width, cam.vfov = 16.0 / 9.0, 64, 90
+        cam.position, cam.lookat, cam.vup = pos, look, (0, 0, -1)
+        pod = cam.pod()
+        got, st = render(gpu, renderer_mod, syn, pod, 10)
+        check_frame(got, port.render(syn, pod, 10), st)
+
+
+def test_mixed_scene_order_and_ties(gpu, renderer_mod, port, S):
+    """Walls and spheres interleaved in scene order; duplicated objects give exact distance ties, where the
+    lowest scene index must win (strict '<' in main.cpp:77)."""
+    M = S.Material
+    scene = [
+        S.Wall(M((.2, .3, .9), .3), (3.0, 2, 0), (0, -1, 0), 1, 1),
+        S.Sphere(M((.9, .2, .1), .6), (2.0, 0.3, 0.2), .4),
+        S.Sphere(M((.1, .9, .1), .2), (2.0, 0.3, 0.2), .4),            # exact duplicate of id 1
+        S.Wall(M((.9, .9, .1), .5), (3.0, -3, 0), (0, 1, 0), 2, 2),
+        S.Wall(M((.1, .9, .9), .5), (3.0, -3, 0), (0, 1, 0), 2, 2),    # exact duplicate of id 3
+        S.Sphere(M((.5, .5, .5), .7), (4.0, -1.0, 1.0), 1.0),
+        S.Sphere(),                                                    # DEFAULT_MAT, unit sphere around the camera: never hit from inside
+        S.Wall(M((1, 1, 1)), (1, 0, 0), (0, 0, 1), 1, 1),               # normal || z: NaN basis, never hit (scene.cpp:18)
+    ]
+    pod = S.default_camera(96, 1.0).pod()
+    got, st = render(gpu, renderer_mod, scene, pod, 6)
+    exp = port.render(scene, pod, 6)
+    check_frame(got, exp, st)
+    ids = set(np.unique(exp["object_id"]))
+    assert 1 in ids and 2 not in ids and 3 in ids and 4 not in ids and 6 not in ids and 7 not in ids
+
+
+def test_empty_scene_and_walls_only_and_spheres_only(gpu, renderer_mod, port, S):
+    pod = S.default_camera(48, 1.0).pod()
+    for scene in ([], S.default_scene()[1:], S.default_scene()[:1], S.synthetic_scene(7, 0, seed=3), S.synthetic_scene(0, 5, seed=4)):
+        got, st = render(gpu, renderer_mod, scene, pod, 4)
+        check_frame(got, port.render(scene, pod, 4), st)
+
+
+def test_params_are_honoured(gpu, renderer_mod, port, S):
+    scene, pod = S.default_scene(), S.default_camera(80, 1.0).pod()
+    kw = dict(light_pos=(0.5, -1.0, 2.0), ground_color=(.3, .2, .1), sky_low=(.9, .8, .7), sky_high=(.1, .2, .3),
+              reflect_offset=.001, sky_exponent=0.5)
+    p = port.default_params()
+    p.max_depth = 5
+    for k, v in kw.items():
+        setattr(p, k, type(getattr(p, k))(*v) if isinstance(v, tuple) else v)
+    got, st = render(gpu, renderer_mod, scene, pod, 5, **kw)
+    check_frame(got, port.render(scene, pod, params=p), st)
+
+
+def test_multi_frame_batch_equals_single_frames(gpu, renderer_mod, port, S):
+    """Config C5's shape: several cameras in one launch."""
+    scene = S.default_scene()
+    cams = S.flythrough_cameras(256, 64, 16.0 / 9.0)
+    pick = [0, 48, 100, 128, 224]
+    gpu.set_scene(scene)
+    planes, st = gpu.render([cams[k].pod() for k in pick], renderer_mod.default_params(), want=WANT)
+    total = 0
+    for f, k in enumerate(pick):
+        exp = port.render(scene, cams[k].pod(), 10)
+        check_frame({n: v[f] for n, v in planes.items()}, exp)
+        total += exp["total_rays"]
+    assert st.total_rays == total
+
+
+@pytest.mark.parametrize("height_w,band,ranks", [((54, 96), 4, 2), ((54, 96), 4, 8), ((50, 64), 3, 4), ((7, 16), 16, 4)])
+def test_row_band_sharding_reassembles_the_frame(gpu, renderer_mod, port, S, syn, height_w, band, ranks):
+    """Config C4's shape: every rank renders its cyclic bands; the union is the full frame."""
+    H, W = height_w
+    cam = S.default_camera(W, W / H)
+    pod = cam.pod()
+    assert pod.height == H
+    scene = syn[:400] + syn[10000:10016]
+    exp = port.render(scene, pod, 10)
+    gpu.set_scene(scene)
+    seen = np.zeros(H, bool)
+    total = 0
+    for r in range(ranks):
+        rows = renderer_mod.global_rows(H, band, ranks, r)
+        if len(rows) == 0:
+            continue
+        planes, st = gpu.render([pod], renderer_mod.default_params(band_rows=band, n_ranks=ranks, rank=r), want=WANT)
+        assert planes["rgba8"].shape == (1, len(rows), W)
+        check_frame({n: v[0] for n, v in planes.items()}, {k: exp[k][rows] for k in ("radiance", "rgba8", "object_id", "hit_mask", "ray_count")})
+        seen[rows] = True
+        total += st.total_rays
+    assert seen.all() and total == exp["total_rays"]
+
+
+def test_unfused_quantise_equals_fused(gpu, renderer_mod, S, syn):
+    pod = S.default_camera(96, 16.0 / 9.0).pod()
+    gpu.set_scene(syn)
+    a, sa = gpu.render([pod], renderer_mod.default_params(fuse_quantise=1), want=("rgba8", "radiance_f64"))
+    b, sb = gpu.render([pod], renderer_mod.default_params(fuse_quantise=0), want=("rgba8",))
+    assert np.array_equal(a["rgba8"], b["rgba8"])
+    assert sb.launches == 2 and sa.launches == 1 and sb.surface_update_ms > 0
+    assert sa.over_range_pixels == sb.over_range_pixels and sa.max_luminance == sb.max_luminance
+
+
+def test_standalone_quantise_kernel(gpu, port):
+    """main.cpp:338-347 as its own kernel: golden vectors from the reference, wrap semantics, ragged sizes."""
+    q = load_json("kat.json")["quantise"]
+    rgb = np.array([float.fromhex(x) for x in q["rgb"]]).reshape(-1, 3)
+    assert list(gpu.quantise(rgb)) == q["rgba8"]
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3, 4, 5, 1023, 4096, 100003):
+        x = rng.uniform(-0.5, 1.6, size=(n, 3))
+        assert np.array_equal(gpu.quantise(x), port.quantise(x))
+        x32 = x.astype(np.float32)
+        assert np.array_equal(gpu.quantise(x32), port.quantise_mode(x32, 0))
+        assert np.array_equal(gpu.quantise(x, 1), port.quantise_mode(x, 1))
+        over = ((x * 255 >= 256) | (x * 255 < 0)).any(axis=-1).sum()
+        gpu.quantise(x)
+        assert gpu.last_stats.over_range_pixels == over
+    assert gpu.quantise(np.zeros((0, 3))).size == 0
+
+
+def test_rt_scene_shaped_call(renderer_mod, port, S):
+    """The drop-in call with the reference's signature shape (main.cpp:124-125, call site main.cpp:329)."""
+    cam = S.default_camera(120, 1.0)
+    u = cam.init()
+    scene = S.default_scene()
+    frame_buffer = np.zeros((int(cam.image_height), int(cam.image_width), 3))
+    renderer_mod.rt_scene(u, scene, cam, frame_buffer)
+    exp = port.render(scene, cam.pod(), 10)
+    assert rel_err(frame_buffer, exp["radiance"]).max() < RAD_TOL
+
+
+def test_error_paths(gpu, renderer_mod, pkg, S):
+    a = pkg.abi
+    fresh = renderer_mod.Renderer(0)
+    with pytest.raises(renderer_mod.RtxError) as e:
+        fresh.render([S.default_camera(8, 1.0).pod()])
+    assert e.value.status == a.RTX_ERR_NO_SCENE
+    fresh.set_scene(S.default_scene())
+    with pytest.raises(renderer_mod.RtxError) as e:
+        fresh.render([S.default_camera(8, 1.0).pod()], renderer_mod.default_params(max_depth=300))
+    assert e.value.status == a.RTX_ERR_INVALID
+    with pytest.raises(renderer_mod.RtxError):
+        fresh.render([S.default_camera(8, 1.0).pod(), S.default_camera(9, 1.0).pod()])
+    with pytest.raises(renderer_mod.RtxError):
+        fresh.render([S.default_camera(8, 1.0).pod()], renderer_mod.default_params(n_ranks=2, rank=2))
+    bad = S.Sphere()
+    bad.kind = 7
+    with pytest.raises(renderer_mod.RtxError):
+        fresh.set_scene([bad])
+    fresh.close()
+
+
+def test_ray_far_outside_scene_bound_falls_back_to_exact(gpu, renderer_mod, port, S):
+    """Primary-ray overshoot can start a bounce beyond the FP32 screen's assumed origin
+    bound: those lanes must fall back to exact tests. A wide FOV with tiny spheres far away provokes it."""
+    M = S.Material
+    scene = [S.Sphere(M((.9, .9, .9), .9), (40.0, 39.0, 39.0), 1.0), S.Sphere(M((.2, .9, .2), .9), (41.0, 35.0, 41.0), 1.5),
+             S.Sphere(M((.9, .2, .2), .9), (38.0, 42.0, 36.0), 2.0), S.Wall(M((.3, .3, .9), .5), (60, -30, -30), (-1, 0, 0), 60, 60)]
+    cam = S.Camera()
+    cam.aspect_ratio, cam.image_width, cam.vfov = 1.0, 200, 100
+    cam.position, cam.lookat, cam.vup = (0, 0, 0), (-1, -1, -1), (0, 0, -1)
+    pod = cam.pod()
+    got, st = render(gpu, renderer_mod, scene, pod, 8)
+    check_frame(got, port.render(scene, pod, 8), st)

@@ -1,0 +1,130 @@
+"""CPU suite, part 2: the host side of the C ABI and the Python mirror of the reference interface.
+
+No compute call is made here (there is no GPU): the library must load, export every symbol of
+include/rtx_b200.h, answer its host-only entry points, and REFUSE to create a context (no CPU fallback).
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, fh, fh3, load_json
+
+
+@pytest.fixture(scope="module")
+def lib(renderer_mod):
+    if not os.path.exists(renderer_mod.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return renderer_mod.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib, pkg):
+    header = open(os.path.join(ROOT, "include", "rtx_b200.h")).read()
+    declared = set(re.findall(r"\b(rtx_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(pkg.abi.EXPORTS), declared ^ set(pkg.abi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.rtx_abi_version() == pkg.abi.ABI_VERSION
+
+
+def test_struct_sizes_match_header(pkg):
+    a = pkg.abi
+    assert C.sizeof(a.Vec3) == 24 and C.sizeof(a.MaterialPOD) == 64
+    assert C.sizeof(a.ObjectPOD) == 8 + 64 + 24 + 24 + 16
+    assert C.sizeof(a.CameraPOD) == 4 * 24 + 8 and C.sizeof(a.CameraDesc) == 3 * 24 + 24
+    assert C.sizeof(a.Params) == 16 + 4 * 24 + 16 + 16
+    assert C.sizeof(a.Outputs) == 6 * 8 + 8
+    assert C.sizeof(a.Stats) == 5 * 8 + 4 * 8 + 8 + 8
+
+
+def test_no_cpu_fallback(lib, pkg):
+    """Without a GPU the product path must fail loudly instead of computing anything on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    ctx = C.c_void_p()
+    rc = lib.rtx_create(C.byref(ctx), 0)
+    assert rc == pkg.abi.RTX_ERR_CUDA and not ctx.value
+    assert b"CUDA" in lib.rtx_last_error(None) or b"device" in lib.rtx_last_error(None)
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the package or include/ may reference it."""
+    pkg_dir = os.path.join(ROOT, "ray-tracer-from-scratch_b200")
+    for base, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".sh")):
+                text = open(os.path.join(base, f)).read()
+                assert "liboracle" not in text and "libref_oracle" not in text and "oracle." not in text.replace("oracle.c", ""), f
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
+
+
+def test_default_params_are_the_reference_literals(renderer_mod, port):
+    p, q = renderer_mod.default_params(), port.default_params()
+    for name, _ in p._fields_:
+        a, b = getattr(p, name), getattr(q, name)
+        if hasattr(a, "tuple"):
+            assert a.tuple() == b.tuple(), name
+        else:
+            assert a == b, name
+    assert p.max_depth == 10 and p.reflect_offset == .0001 and p.sky_exponent == 0.25
+    assert p.light_pos.tuple() == (0, 0, 0) and p.ground_color.tuple() == (0.025, 0.05, 0.075)
+
+
+def test_camera_init_three_ways(renderer_mod, port, S):
+    """Camera::init (scene.cpp:80-106): library host code == Python mirror == C oracle == golden (reference)."""
+    for c in load_json("kat.json")["camera"]:
+        cam = S.Camera()
+        cam.position, cam.lookat, cam.vup = fh3(c["position"]), fh3(c["lookat"]), fh3(c["vup"])
+        cam.vfov, cam.aspect_ratio, cam.image_width = fh(c["vfov"]), fh(c["aspect_ratio"]), fh(c["image_width"])
+        cam.init()
+        for pod in (cam.pod(), renderer_mod.camera_init(cam), port.camera_init(cam)):
+            assert pod.image_top_left.tuple() == fh3(c["image_top_left"])
+            assert pod.delta_x.tuple() == fh3(c["delta_x"]) and pod.delta_y.tuple() == fh3(c["delta_y"])
+            assert (pod.width, pod.height) == (c["width"], c["height"])
+
+
+def test_default_camera_quirks(S):
+    """ASPECT_RATIO = 4/3 is integer 1 -> 640x640 (main.cpp:25); pi is 3.14 (scene.cpp:84)."""
+    cam = S.default_camera()
+    assert (int(cam.image_width), int(cam.image_height)) == (640, 640)
+    assert cam.image_top_left == (-1.0, 0.99764273387050351, -0.99764273387050351)
+    assert cam.u[0][1] == -0.0031225124690782585 and cam.u[1][2] == 0.0031225124690782585
+    assert S.default_camera(1920, 16.0 / 9.0).image_height == 1080 and S.default_camera(7680, 16.0 / 9.0).image_height == 4320
+
+
+def test_material_constructor_order_and_default_mat(S):
+    m = S.Material((0, 1, 0), 0.5)
+    assert (m.metallic, m.ambient, m.diffuse, m.specular, m.specular_exponent) == (.5, .1, .9, .4, 50)
+    d = S.default_mat()     # DEFAULT_MAT quirk, scene.h:3
+    assert (d.metallic, d.ambient, d.diffuse, d.specular, d.specular_exponent) == (.9, .9, .3, 30, 50)
+    pod = S.Sphere().pod()
+    assert pod.mat.metallic == .9 and pod.mat.specular == 30 and pod.a == 1.0
+
+
+@pytest.mark.parametrize("height,band,ranks", [(4320, 4, 8), (4320, 4, 2), (2160, 4, 8), (54, 4, 3), (7, 16, 4), (1, 1, 1), (10, 3, 4)])
+def test_band_map_partitions_rows(lib, renderer_mod, height, band, ranks):
+    seen = []
+    for r in range(ranks):
+        rows = renderer_mod.global_rows(height, band, ranks, r)
+        assert len(rows) == lib.rtx_local_rows(height, band, ranks, r)
+        assert list(rows) == sorted(rows) and all((g // band) % ranks == r for g in rows)
+        seen += list(rows)
+        assert lib.rtx_global_row(len(rows), height, band, ranks, r) == -1
+    assert sorted(seen) == list(range(height))
+    assert lib.rtx_local_rows(height, band, ranks, ranks) == 0 and lib.rtx_local_rows(0, band, ranks, 0) == 0
+
+
+def test_flythrough_cameras_keep_focal_length_one(S):
+    """focal length must stay 1 because |d| leaks into sphere hit points (row I)."""
+    cams = S.flythrough_cameras(256, 96, 16.0 / 9.0)
+    assert len(cams) == 256
+    for c in cams[::16]:
+        assert abs(c.focal_length - 1.0) < 1e-12 and int(c.image_height) == 54
+
+
+def test_status_strings(lib):
+    assert lib.rtx_status_string(0) == b"ok" and b"invalid" in lib.rtx_status_string(1)
