@@ -84,7 +84,7 @@ int grow(rtx_ctx* ctx, void** p, size_t* cap, size_t need)
     return RTX_OK;
 }
 
-constexpr int kPad = 8;   // hot-loop unroll factor of trace.cu
+constexpr int kPad = 8;   // entries per hot-loop iteration of trace.cu (kPairsPerIter * 2)
 
 }  // namespace
 
@@ -177,7 +177,7 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
     if (!ctx) return RTX_ERR_INVALID;
     if (n < 0 || (n > 0 && !objects)) return fail(ctx, RTX_ERR_INVALID, "rtx_set_scene: null objects or negative count");
     RTX_CUDA(ctx, cudaSetDevice(ctx->device));
-    std::vector<float4> sph32;
+    std::vector<float4> sph32, wall32;
     std::vector<SphereExact> sph64;
     std::vector<int32_t> sph_id, kind(n), slot(n);
     std::vector<WallDev> walls;
@@ -197,10 +197,10 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
         if (o.kind == RTX_SPHERE) {
             slot[k] = static_cast<int32_t>(sph64.size());
             sph64.push_back(SphereExact{o.p.x, o.p.y, o.p.z, o.a});
-            // nearest-float copies for the screen; a negative or non-finite radius gets r = +inf there so that
-            // the screen never rejects it and the exact test decides
-            float r32 = static_cast<float>(std::fabs(o.a));
-            if (!(o.a >= 0.0) || !std::isfinite(o.a)) r32 = INFINITY;
+            // float copies for the screen; a non-finite radius gets r = +inf there so that the screen never
+            // rejects it and the exact test decides
+            float r32 = std::nextafter(static_cast<float>(std::fabs(o.a)), INFINITY);   // radius enters squared: sign is irrelevant
+            if (!std::isfinite(o.a)) r32 = INFINITY;
             sph32.push_back(make_float4(static_cast<float>(o.p.x), static_cast<float>(o.p.y), static_cast<float>(o.p.z), r32));
             sph_id.push_back(k);
             bound = std::fmax(bound, amax3(H(o.p)) + std::fabs(o.a));
@@ -219,11 +219,20 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
             w.id = k;
             w.pad = 0;
             walls.push_back(w);
+            // Bounding sphere of the rectangle for the FP32 screen: every point Wall::intersect can accept
+            // (0 <= x <= length, 0 <= y <= width in the (right, up) frame, scene.cpp:25-29) lies inside it.
+            const h3 centre = hadd(hadd(H(o.p), hmul(right, o.a / 2)), hmul(up, o.b / 2));
+            float r32 = static_cast<float>(0.5 * std::sqrt(o.a * o.a + o.b * o.b) * (1.0 + 1e-6));
+            r32 = std::nextafter(r32, INFINITY);
+            if (!std::isfinite(o.a) || !std::isfinite(o.b)) r32 = INFINITY;
+            wall32.push_back(make_float4(static_cast<float>(centre.x), static_cast<float>(centre.y), static_cast<float>(centre.z), r32));
             bound = std::fmax(bound, amax3(H(o.p)) + std::fabs(o.a) + std::fabs(o.b));
         }
     }
     const int ns = static_cast<int>(sph64.size()), nw = static_cast<int>(walls.size());
-    const int ns_pad = (ns + kPad - 1) / kPad * kPad;
+    const int ne = ns + nw;
+    const int ns_pad = (ne + kPad - 1) / kPad * kPad;        // padded entry count
+    sph32.insert(sph32.end(), wall32.begin(), wall32.end());
     sph32.resize(ns_pad, make_float4(0.f, 0.f, 0.f, -1.f));
 
     // one device blob, 256-byte aligned sections
@@ -258,8 +267,9 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
     s.n_objects = n;
     s.n_spheres = ns;
     s.n_walls = nw;
-    s.n_spheres_padded = ns_pad;
-    s.sph32 = reinterpret_cast<const float4*>(base + o_s32);
+    s.n_entries = ne;
+    s.n_entries_padded = ns_pad;
+    s.ent32 = reinterpret_cast<const float4*>(base + o_s32);
     s.sph64 = reinterpret_cast<const SphereExact*>(base + o_s64);
     s.sph_id = reinterpret_cast<const int32_t*>(base + o_sid);
     s.walls = reinterpret_cast<const WallDev*>(base + o_wal);

@@ -47,9 +47,10 @@ __device__ __forceinline__ d3 lerp(d3 a, d3 b, double t)
 
 // ---- device copy of the scene (built by rtx_set_scene) --------------------------------------------
 //
-// Spheres and walls are split into two SoA-ish arrays (the "type-switched, warp-uniform hit loop"
-// replacing the virtual SceneGeometry::intersect, scene.h:51-60); `id` maps back to the index in the
-// reference's scene vector, which is both the object id and the tie-break order (main.cpp:77-80).
+// The virtual SceneGeometry::intersect (scene.h:51-60) is replaced by one flat array of screen entries
+// (warp-uniform scan, no dispatch) plus type-switched exact data for the few survivors; `id` maps back to
+// the index in the reference's scene vector, which is both the object id and the tie-break order
+// (main.cpp:77-80).
 
 struct SphereExact {   // 32 B, read only for filter survivors
     double cx, cy, cz, r;
@@ -72,8 +73,11 @@ struct MaterialDev {   // Material (scene.h:35-49), indexed by scene id
 
 struct SceneDev {
     int32_t n_objects, n_spheres, n_walls;
-    int32_t n_spheres_padded;          // multiple of the hot loop's unroll factor
-    const float4* sph32;               // [n_spheres_padded] (cx, cy, cz, r) rounded to nearest float; pad r = -1
+    int32_t n_entries;                 // n_spheres + n_walls: what the FP32 screen scans
+    int32_t n_entries_padded;          // multiple of the hot loop's entries per iteration
+    // Screen entries (cx, cy, cz, r) rounded to float: spheres first (entry e = sphere slot e), then one
+    // BOUNDING sphere per wall (entry n_spheres + w = wall slot w); padding has r = -1.
+    const float4* ent32;               // [n_entries_padded]
     const SphereExact* sph64;          // [n_spheres]
     const int32_t* sph_id;             // [n_spheres]
     const WallDev* walls;              // [n_walls]

@@ -4,34 +4,35 @@
 // Replaces rt_scene -> recursive_ray_tracing -> find_closest_hit -> SceneGeometry::intersect
 // (main.cpp:67-139, scene.cpp:4-78) and, when fused, the quantise loop (main.cpp:338-347).
 //
-// Design (see DESIGN.md for the derivations):
+// Design (derivations and measurements in DESIGN.md):
 //
-//  * Persistent lanes. One CTA per SM; each lane owns one pixel's reflection chain at a time and fetches
-//    the next pixel (warp-aggregated atomic) the moment its chain ends, so the O(N) object loop always
-//    runs with 32 live lanes although chains are 1..depth+1 rays long. recursive_ray_tracing's
-//    back-to-front lerp (main.cpp:117) becomes a front-to-back accumulation: colour = sum_k W_k(1-m_k)L_k + W_end*T.
+//  * Persistent lanes, two chains per lane. One CTA per SM; every lane owns two pixels' reflection chains and
+//    fetches a new pixel (warp-aggregated atomic) the moment a chain ends, so the O(N) object scan always runs
+//    with live lanes although chains are 1..depth+1 rays long. recursive_ray_tracing's back-to-front lerp
+//    (main.cpp:117) becomes a front-to-back accumulation: colour = sum_k W_k (1-m_k) L_k + W_end * T.
 //
-//  * Exact decisions, FP32 search. The reference is IEEE double. A ray/sphere pair is first screened by a
-//    CONSERVATIVE FP32 test, 10 instructions per pair: the squared distance from the sphere centre to the ray's
-//    line, |c x d^ - o x d^|^2, against (r + E)^2, where E bounds the FP32 error (filter_eps). The cross-product
-//    form has no |oc|^2 - b^2 cancellation; its error grows with |c|, not |c|^2. Survivors (about 2 per ray in
-//    the 10k-sphere scene) pass a second FP32 screen (behind the origin? farther than the best so far?) and are
-//    then evaluated with the reference's own double arithmetic, operation for operation, and compared with the
-//    reference's rule (distance > 0, strictly smaller, lowest scene index on ties). The FP32 stage can only
-//    discard pairs the double test would also discard, so ids/distances equal the reference's bit for bit.
+//  * Exact decisions, FP32 search. The reference is IEEE double. Every (ray, object) pair is first screened by a
+//    CONSERVATIVE FP32 test: squared distance from the object's centre to the ray's line, |c x d^ - o x d^|^2,
+//    against (r + E)^2, E bounding the FP32 error (filter_eps). The cross-product form has no |oc|^2 - b^2
+//    cancellation: its error grows with |c|, not |c|^2. Walls take part through their bounding sphere.
+//    The screen is 9 packed FFMA2 (fma.rn.f32x2, two spheres per instruction) + 2 funnel shifts per two pairs;
+//    each broadcast LDS.128 of sphere data feeds four pairs (2 spheres x 2 chains).
+//    Survivors (a few per ray) are queued per chain and, after the scan, evaluated with the reference's own
+//    double arithmetic, operation for operation, many lanes at a time, and compared with the reference's rule
+//    (distance > 0, strictly smaller, lowest scene index on ties). The FP32 stage can only discard pairs the
+//    double test would also discard, so ids/distances equal the reference's bit for bit.
 //
-//  * Spheres live in shared memory as float4 (cx, cy, cz, (r+E)^2): every lane reads the same sphere, one
-//    broadcast LDS.128 per pair. 10 000 spheres = 160 KB, resident for the whole launch. Larger scenes stream
-//    tiles through the same buffer (CTA-synchronous loop).
-//
-//  * Walls are few; each is evaluated in double exactly as Wall::intersect, with the ray-independent basis
-//    (scene.cpp:18-19) precomputed at rtx_set_scene.
+//  * Objects live in shared memory, pair-interleaved for FFMA2: (cx_a,cx_b,cy_a,cy_b)(cz_a,cz_b,-w_a,-w_b) with
+//    w = (r+E)^2. 10 064 entries = 161 KB, resident for the whole launch. Larger scenes stream tiles through the
+//    same buffer (CTA-synchronous loop).
 #include "rtx_device.cuh"
 
 namespace rtx {
 
 constexpr int kThreads = 512;         // 16 warps per SM, 4 per scheduler
-constexpr int kUnroll = 8;            // spheres per hot-loop iteration
+constexpr int kChains = 2;            // pixels in flight per lane
+constexpr int kPairsPerIter = 4;      // sphere pairs (8 entries) per hot-loop iteration
+constexpr int kQueue = 24;            // screen survivors buffered per chain before an early flush
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kMaxSmemBytes = 227 * 1024;
 
@@ -40,7 +41,7 @@ constexpr int kMaxSmemBytes = 227 * 1024;
 // Sphere::intersect, scene.cpp:40-78. `a` = d.d and `dlen` = |d| are ray constants hoisted by the caller
 // (the reference recomputes them per call with the same result). Returns the reference's `distance`
 // (projection * |d|, world units; negative when the sphere is behind) or -1 for det < 0.
-__device__ __noinline__ double sphere_exact(d3 o, d3 d, double a, double dlen, SphereExact s, d3* normal)
+__device__ __forceinline__ double sphere_exact(d3 o, d3 d, double a, double dlen, SphereExact s, d3* normal)
 {
     using namespace ex;
     const d3 c = mk(s.cx, s.cy, s.cz);
@@ -80,356 +81,433 @@ __device__ __forceinline__ double wall_exact(d3 o, d3 d, const WallDev& w)
     return -1.0;
 }
 
-// ---- per-ray FP32 screening constants -------------------------------------------------------------------
-struct RayF {
-    float dx, dy, dz;   // d^ = d/|d| rounded to float
-    float kx, ky, kz;   // o x d^ (computed in double with the ROUNDED d^, then rounded)
-    float d_o;          // d^ . o
-    float best_hi;      // float upper bound of the best distance so far
-};
-
-__device__ __forceinline__ RayF make_rayf(d3 o, d3 d, double dlen, float origin_bound)
-{
-    RayF f;
-    const double inv = 1.0 / dlen;
-    f.dx = static_cast<float>(d.x * inv);
-    f.dy = static_cast<float>(d.y * inv);
-    f.dz = static_cast<float>(d.z * inv);
-    const double ux = f.dx, uy = f.dy, uz = f.dz;
-    f.kx = static_cast<float>(o.y * uz - o.z * uy);
-    f.ky = static_cast<float>(o.z * ux - o.x * uz);
-    f.kz = static_cast<float>(o.x * uy - o.y * ux);
-    f.d_o = static_cast<float>(ux * o.x + uy * o.y + uz * o.z);
-    f.best_hi = __int_as_float(0x7f800000);
-    // The error bound E assumes |o| <= origin_bound. A ray that starts farther out (possible through the
-    // reference's primary-ray overshoot, main.cpp:99 with |d| > 1) poisons its constants with NaN: every
-    // FP32 screen then answers "maybe" and the lane falls back to exact tests of all spheres.
-    const double om = fmax(fabs(o.x), fmax(fabs(o.y), fabs(o.z)));
-    if (!(om <= static_cast<double>(origin_bound)) || !(dlen > 0.0) || !(dlen < 1e300)) {
-        f.kx = f.ky = f.kz = f.d_o = __int_as_float(0x7fc00000);
-    }
-    return f;
-}
-
-struct Best {
-    double dist;
-    int id;    // scene index, -1 = none
-};
-
-// main.cpp:77 generalised to any evaluation order: accept iff distance > 0 and (distance, id) is
-// lexicographically smaller than the best so far — identical to the in-order strict '<' scan.
-__device__ __forceinline__ bool better(double dist, int id, const Best& b)
-{
-    return dist > 0 && (dist < b.dist || (dist == b.dist && id < b.id));
-}
-
-// Second FP32 screen + exact evaluation of one filter survivor.
-__device__ __forceinline__ void consider(int j, float4 s, RayF& f, d3 o, d3 d, double a, double dlen,
-                                         const SceneDev& sc, Best& best)
-{
-    if (j >= sc.n_spheres) return;
-    // b32 ~ d^.(c - o); the reference distance D satisfies b* - r <= D <= b*, |b32 - b*| <= E, and
-    // rb >= r + E, so D >= b32 - rb. b* < 0 means both roots are negative: never accepted.
-    const float b32 = fmaf(f.dx, s.x, fmaf(f.dy, s.y, fmaf(f.dz, s.z, -f.d_o)));
-    const float rb = sqrtf(s.w) * 1.000001f;
-    if (b32 < -rb) return;
-    if (b32 - rb > f.best_hi) return;
-    const SphereExact e = sc.sph64[j];
-    const double dist = sphere_exact(o, d, a, dlen, e, nullptr);
-    const int id = sc.sph_id[j];
-    if (better(dist, id, best)) {
-        best.dist = dist;
-        best.id = id;
-        f.best_hi = __double2float_ru(dist);
-    }
-}
-
-// The O(N) loop over one shared-memory tile of spheres: the FP32 screen, kUnroll pairs per iteration.
-__device__ __forceinline__ void scan_tile(const float4* __restrict__ tile, int count, int base, RayF& f, d3 o, d3 d,
-                                          double a, double dlen, const SceneDev& sc, Best& best)
-{
-    const float dx = f.dx, dy = f.dy, dz = f.dz;
-    const float nkx = -f.kx, nky = -f.ky, nkz = -f.kz;
-#pragma unroll 1
-    for (int j = 0; j < count; j += kUnroll) {
-        float4 s[kUnroll];
-        float q[kUnroll];
-        bool any = false;
-#pragma unroll
-        for (int u = 0; u < kUnroll; u++) s[u] = tile[j + u];
-#pragma unroll
-        for (int u = 0; u < kUnroll; u++) {
-            // m = c x d^ - o x d^ ; q = |m|^2 = squared distance from the centre to the ray's line
-            const float mx = fmaf(s[u].y, dz, fmaf(-s[u].z, dy, nkx));
-            const float my = fmaf(s[u].z, dx, fmaf(-s[u].x, dz, nky));
-            const float mz = fmaf(s[u].x, dy, fmaf(-s[u].y, dx, nkz));
-            q[u] = fmaf(mx, mx, fmaf(my, my, mz * mz));
-            any |= !(q[u] > s[u].w);      // NaN-safe: unordered counts as "maybe"
-        }
-        if (any) {
-#pragma unroll
-            for (int u = 0; u < kUnroll; u++)
-                if (!(q[u] > s[u].w)) consider(base + j + u, s[u], f, o, d, a, dlen, sc, best);
-        }
-    }
-}
-
-// Cooperative tile fill: (cx, cy, cz, r) -> (cx, cy, cz, (r + E)^2); padding entries (r < 0) can never pass.
-__device__ __forceinline__ void fill_tile(float4* tile, const float4* __restrict__ src, int count, float eps)
-{
-    for (int i = threadIdx.x; i < count; i += kThreads) {
-        float4 v = __ldg(&src[i]);
-        if (v.w >= 0.f) {
-            const float re = v.w + eps;
-            v.w = re * re;
-        } else {
-            v = make_float4(0.f, 0.f, 0.f, -1.f);
-        }
-        tile[i] = v;
-    }
-}
-
-struct Lane {
+// ---- per-chain state (local memory; the hot loop never touches it) ---------------------------------------------
+struct Chain {
     d3 o, d;            // current ray (double, as the reference)
+    double a_dd, dlen;  // d.d and |d|
     d3 acc;             // accumulated colour
     double weight;      // product of the metallic factors so far
+    double best_dist;   // find_closest_hit state (main.cpp:70)
     unsigned long long pixel;
+    float fdx, fdy, fdz, fd_o;   // second-screen constants: d^ and d^.o in float
+    float inv_dlen_lo;           // float lower bound of 1/|d| (wall distances are parametric)
+    float best_hi;               // float upper bound of best_dist
+    int best_id;
     int remaining;      // remaining_iterations (main.cpp:89)
     int first_id;       // primary hit id
     int rays;
-    bool active;
+    int active;
+    int qn;
+    int queue[kQueue];  // entry indices that passed the FP32 screen
 };
 
+// Packed screen constants of one chain: every value duplicated in both halves of a 64-bit register pair.
+struct Packed {
+    float2 dx, dy, dz, ndx, ndy, ndz, nkx, nky, nkz;
+};
+
+__device__ __forceinline__ float2 dup(float v) { return make_float2(v, v); }
+
+// main.cpp:77 generalised to any evaluation order: accept iff distance > 0 and (distance, id) is
+// lexicographically smaller than the best so far — identical to the in-order strict '<' scan.
+__device__ __forceinline__ bool better(double dist, int id, double best_dist, int best_id)
+{
+    return dist > 0 && (dist < best_dist || (dist == best_dist && id < best_id));
+}
+
+// Ray constants for both screens. `origin_bound`: the error bound E assumes |o| <= origin_bound; a ray that
+// starts farther out (possible through the reference's primary-ray overshoot, main.cpp:99 with |d| > 1) gets
+// constants under which EVERY entry passes the screens, i.e. the chain falls back to exact tests of everything.
+__device__ __forceinline__ Packed setup_chain(Chain& c, float origin_bound)
+{
+    Packed k;
+    if (!c.active) {
+        // idle chain (only while the frame drains): m = -k is huge, nothing passes
+        k.dx = k.dy = k.dz = k.ndx = k.ndy = k.ndz = dup(0.f);
+        k.nkx = k.nky = k.nkz = dup(1e15f);
+        c.qn = 0;
+        return k;
+    }
+    c.a_dd = ex::len2(c.d);
+    c.dlen = ex::sqrt(c.a_dd);
+    c.best_dist = 1.7976931348623157e308;   // DBL_MAX, main.cpp:70
+    c.best_id = -1;
+    c.best_hi = __int_as_float(0x7f800000);
+    c.qn = 0;
+    const double inv = 1.0 / c.dlen;
+    const float fx = static_cast<float>(c.d.x * inv), fy = static_cast<float>(c.d.y * inv), fz = static_cast<float>(c.d.z * inv);
+    const double ux = fx, uy = fy, uz = fz;          // the ROUNDED direction: k must match what the FMAs see
+    const float kx = static_cast<float>(c.o.y * uz - c.o.z * uy);
+    const float ky = static_cast<float>(c.o.z * ux - c.o.x * uz);
+    const float kz = static_cast<float>(c.o.x * uy - c.o.y * ux);
+    c.fdx = fx;
+    c.fdy = fy;
+    c.fdz = fz;
+    c.fd_o = static_cast<float>(ux * c.o.x + uy * c.o.y + uz * c.o.z);
+    c.inv_dlen_lo = __double2float_rd(inv) * 0.999999f;
+    const double om = fmax(fabs(c.o.x), fmax(fabs(c.o.y), fabs(c.o.z)));
+    const bool ok = (om <= static_cast<double>(origin_bound)) && (c.dlen > 0.0) && (c.dlen < 1e300);
+    if (ok) {
+        k.dx = dup(fx); k.dy = dup(fy); k.dz = dup(fz);
+        k.ndx = dup(-fx); k.ndy = dup(-fy); k.ndz = dup(-fz);
+        k.nkx = dup(-kx); k.nky = dup(-ky); k.nkz = dup(-kz);
+    } else {
+        // m = 0 for every entry -> q - w = -w < 0 -> everything passes; NaN makes the second screen pass too
+        k.dx = k.dy = k.dz = k.ndx = k.ndy = k.ndz = k.nkx = k.nky = k.nkz = dup(0.f);
+        c.fdx = c.fdy = c.fdz = c.fd_o = __int_as_float(0x7fc00000);
+    }
+    return k;
+}
+
+// Second FP32 screen + exact evaluation of the queued survivors of one chain. Lanes run this together; each
+// iterates over its own queue, so most exact evaluations execute with many lanes active.
+__device__ __noinline__ void drain_queue(Chain& c, const SceneDev sc, const float eps)
+{
+    const int n = c.qn;
+    for (int q = 0; q < n; q++) {
+        const int e = c.queue[q];
+        if (e >= sc.n_entries) continue;                       // padding (only reachable by fallback chains)
+        const float4 s = __ldg(&sc.ent32[e]);                  // (cx, cy, cz, r) of the sphere / bounding sphere
+        // b32 ~ d^.(c - o). With b* the exact value: |b32 - b*| <= E and the hit lies in [b* - r, b* + r].
+        const float b32 = fmaf(c.fdx, s.x, fmaf(c.fdy, s.y, fmaf(c.fdz, s.z, -c.fd_o)));
+        const float rb = (s.w + eps) * 1.000001f;
+        if (b32 < -rb) continue;                               // entirely behind the origin: never accepted
+        if (e < sc.n_spheres) {
+            if (b32 - rb > c.best_hi) continue;                // sphere distance is in world units (scene.cpp:77)
+            const double dist = sphere_exact(c.o, c.d, c.a_dd, c.dlen, sc.sph64[e], nullptr);
+            const int id = sc.sph_id[e];
+            if (better(dist, id, c.best_dist, c.best_id)) {
+                c.best_dist = dist;
+                c.best_id = id;
+                c.best_hi = __double2float_ru(dist);
+            }
+        } else {
+            if ((b32 - rb) * c.inv_dlen_lo > c.best_hi) continue;   // wall distance is t of the unnormalised d
+            const WallDev& w = sc.walls[e - sc.n_spheres];
+            const double t = wall_exact(c.o, c.d, w);
+            if (better(t, w.id, c.best_dist, c.best_id)) {
+                c.best_dist = t;
+                c.best_id = w.id;
+                c.best_hi = __double2float_ru(t);
+            }
+        }
+    }
+    c.qn = 0;
+}
+
+__device__ __forceinline__ void enqueue(Chain& c, int entry, const SceneDev& sc, float eps)
+{
+    if (c.qn == kQueue) drain_queue(c, sc, eps);   // rare: early flush
+    c.queue[c.qn++] = entry;
+}
+
+// 128-bit shared load from a 32-bit shared-window address (keeps address arithmetic out of the loop).
+__device__ __forceinline__ float4 lds128(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// One packed screen step: two entries (a, b) against one chain. Returns q - w for both.
+__device__ __forceinline__ float2 screen(const float2 cx, const float2 cy, const float2 cz, const float2 nw, const Packed& k)
+{
+    // m = c x d^ - o x d^   (squared length = squared distance from the centre to the ray's line)
+    const float2 mx = __ffma2_rn(cy, k.dz, __ffma2_rn(cz, k.ndy, k.nkx));
+    const float2 my = __ffma2_rn(cz, k.dx, __ffma2_rn(cx, k.ndz, k.nky));
+    const float2 mz = __ffma2_rn(cx, k.dy, __ffma2_rn(cy, k.ndx, k.nkz));
+    return __ffma2_rn(mx, mx, __ffma2_rn(my, my, __ffma2_rn(mz, mz, nw)));
+}
+
+// The O(N) scan over one shared-memory tile: n_pairs entry pairs starting at entry index `base`.
+__device__ __forceinline__ void scan_tile(unsigned tile_addr, int n_pairs, int base, const Packed& k0, const Packed& k1,
+                                          Chain& c0, Chain& c1, const SceneDev& sc, float eps)
+{
+    const unsigned end = tile_addr + static_cast<unsigned>(n_pairs) * 32u;
+    int entry = base;
+#pragma unroll 1
+    for (unsigned addr = tile_addr; addr < end; addr += kPairsPerIter * 32u, entry += 2 * kPairsPerIter) {
+        float4 p0[kPairsPerIter], p1[kPairsPerIter];
+#pragma unroll
+        for (int u = 0; u < kPairsPerIter; u++) {
+            p0[u] = lds128(addr + u * 32u);
+            p1[u] = lds128(addr + u * 32u + 16u);
+        }
+        unsigned h0 = 0u, h1 = 0u;     // sign history: one bit per pair test, newest in bit 0
+#pragma unroll
+        for (int u = 0; u < kPairsPerIter; u++) {
+            const float2 cx = make_float2(p0[u].x, p0[u].y), cy = make_float2(p0[u].z, p0[u].w);
+            const float2 cz = make_float2(p1[u].x, p1[u].y), nw = make_float2(p1[u].z, p1[u].w);
+            const float2 qa = screen(cx, cy, cz, nw, k0);
+            const float2 qb = screen(cx, cy, cz, nw, k1);
+            h0 = __funnelshift_l(__float_as_uint(qa.x), h0, 1);
+            h0 = __funnelshift_l(__float_as_uint(qa.y), h0, 1);
+            h1 = __funnelshift_l(__float_as_uint(qb.x), h1, 1);
+            h1 = __funnelshift_l(__float_as_uint(qb.y), h1, 1);
+        }
+        if (h0 | h1) {                 // some q - w < 0: a survivor (about 2e-4 of all pairs)
+            while (h0) {
+                const int bit = 31 - __clz(h0);
+                h0 &= ~(1u << bit);
+                enqueue(c0, entry + (2 * kPairsPerIter - 1 - bit), sc, eps);
+            }
+            while (h1) {
+                const int bit = 31 - __clz(h1);
+                h1 &= ~(1u << bit);
+                enqueue(c1, entry + (2 * kPairsPerIter - 1 - bit), sc, eps);
+            }
+        }
+    }
+}
+
+// Cooperative tile fill: entries (cx, cy, cz, r) -> pair-interleaved (cx_a,cx_b,cy_a,cy_b)(cz_a,cz_b,-w_a,-w_b),
+// w = (r + E)^2. Padding entries (r < 0) get -w = +1 and can never pass.
+__device__ __forceinline__ void fill_tile(float4* tile, const float4* __restrict__ src, int n_pairs, float eps)
+{
+    for (int i = threadIdx.x; i < n_pairs; i += kThreads) {
+        const float4 a = __ldg(&src[2 * i]), b = __ldg(&src[2 * i + 1]);
+        const float ra = a.w + eps, rb = b.w + eps;
+        const float nwa = a.w >= 0.f ? -(ra * ra) : 1.f;
+        const float nwb = b.w >= 0.f ? -(rb * rb) : 1.f;
+        tile[2 * i] = make_float4(a.x, b.x, a.y, b.y);
+        tile[2 * i + 1] = make_float4(a.z, b.z, nwa, nwb);
+    }
+}
+
+struct FrameTotals {
+    unsigned long long rays, over;
+    double maxlum;
+};
+
+// Shade one finished segment of a chain (recursive_ray_tracing, main.cpp:89-119) and either set up the
+// reflected ray or write the pixel.
+__device__ __noinline__ void shade_chain(Chain& c, const TraceArgs& a, FrameTotals& tot)
+{
+    using namespace ex;
+    const SceneDev& sc = a.scene;
+    c.rays++;
+    if (c.rays == 1) c.first_id = c.best_id;
+    bool done;
+    if (c.best_id < 0) {
+        // out_color, main.cpp:28-37 (sign test on the unnormalised z)
+        d3 col;
+        if (c.d.z < 0.0) {
+            col = a.ground;
+        } else {
+            const double vz = div(c.d.z, c.dlen);
+            // pow(v.z, 0.25): two correctly rounded square roots are within 1 ulp of it
+            const double s = (a.sky_exponent == 0.25) ? sqrt(sqrt(vz)) : pow(vz, a.sky_exponent);
+            col = lerp(a.sky_low, a.sky_high, s);
+        }
+        c.acc.x += c.weight * col.x;
+        c.acc.y += c.weight * col.y;
+        c.acc.z += c.weight * col.z;
+        done = true;
+    } else {
+        d3 normal;
+        const int slot = sc.slot[c.best_id];
+        if (sc.kind[c.best_id] == RTX_SPHERE) {
+            sphere_exact(c.o, c.d, c.a_dd, c.dlen, sc.sph64[slot], &normal);
+        } else {
+            normal = sc.walls[slot].n;
+        }
+        const MaterialDev m = sc.mats[c.best_id];
+        const d3 pos = add(c.o, scale(c.d, c.best_dist));                  // main.cpp:99
+        const d3 ldir = unit(sub(a.light, pos));                           // main.cpp:44,57
+        const d3 nn = unit(normal);                                        // main.cpp:46,56
+        const d3 dhat = divs(c.d, c.dlen);                                 // normalize(d); normalize(-d) = -dhat
+        const double lambert = dot(ldir, nn);                              // main.cpp:46
+        const double di = lambert > 0 ? lambert : 0;
+        const d3 half = unit(add(neg(dhat), ldir));                        // main.cpp:59
+        const double sp = dot(half, nn);                                   // main.cpp:60
+        const double si = pow(sp > 0 ? sp : 0, m.exponent);                // main.cpp:103
+        const double k = add(add(mul(di, m.diffuse), mul(si, m.specular)), m.ambient);
+        const d3 local = scale(m.color, k);                                // main.cpp:104
+        if (c.remaining <= 0) {                                            // main.cpp:105-108
+            c.acc.x += c.weight * local.x;
+            c.acc.y += c.weight * local.y;
+            c.acc.z += c.weight * local.z;
+            done = true;
+        } else {
+            // lerp(local, reflected, metallic) unrolled front to back (main.cpp:117)
+            const double wl = c.weight * (1.0 - m.metallic);
+            c.acc.x += wl * local.x;
+            c.acc.y += wl * local.y;
+            c.acc.z += wl * local.z;
+            c.weight *= m.metallic;
+            const d3 start = add(pos, scale(normal, a.reflect_offset));    // main.cpp:111 (normal unnormalised)
+            const double kk = mul(2.0, dot(dhat, nn));                     // vec.cpp:55
+            c.d = sub(dhat, scale(nn, kk));                                // vec.cpp:56
+            c.o = start;
+            c.remaining--;
+            done = false;
+        }
+    }
+    if (done) {
+        const unsigned long long p = c.pixel;
+        if (a.rgba8) a.rgba8[p] = pack_rgba(c.acc.x, c.acc.y, c.acc.z, a.quantise_mode);
+        if (a.rad64) {
+            a.rad64[3 * p + 0] = c.acc.x;
+            a.rad64[3 * p + 1] = c.acc.y;
+            a.rad64[3 * p + 2] = c.acc.z;
+        }
+        if (a.rad32) {
+            a.rad32[3 * p + 0] = static_cast<float>(c.acc.x);
+            a.rad32[3 * p + 1] = static_cast<float>(c.acc.y);
+            a.rad32[3 * p + 2] = static_cast<float>(c.acc.z);
+        }
+        if (a.object_id) a.object_id[p] = c.first_id;
+        if (a.hit_mask) a.hit_mask[p] = c.first_id >= 0 ? 1 : 0;
+        if (a.ray_count) a.ray_count[p] = static_cast<uint8_t>(c.rays);
+        tot.rays += static_cast<unsigned long long>(c.rays);
+        if (over_range(c.acc.x, c.acc.y, c.acc.z)) tot.over++;
+        const double lum = (c.acc.x + c.acc.y + c.acc.z) * (1.0 / 3.0);
+        if (lum > tot.maxlum) tot.maxlum = lum;
+        c.active = 0;
+    }
+}
+
+// Primary ray of packed pixel index p (main.cpp:129-134).
+__device__ __noinline__ void start_pixel(Chain& c, unsigned long long p, const TraceArgs& a)
+{
+    using namespace ex;
+    const unsigned long long frame_pixels = static_cast<unsigned long long>(a.local_rows) * a.width;
+    const int frame = static_cast<int>(p / frame_pixels);
+    const unsigned rem = static_cast<unsigned>(p - frame * frame_pixels);
+    const int lrow = rem / a.width;
+    const int col = rem - lrow * a.width;
+    int grow = lrow;
+    if (a.n_ranks > 1) {
+        const int lb = lrow / a.band_rows;
+        grow = (lb * a.n_ranks + a.rank) * a.band_rows + (lrow - lb * a.band_rows);
+    }
+    const rtx_camera& cam = a.cameras[frame];
+    const d3 centre = add(add(mk(cam.image_top_left), scale(mk(cam.delta_x), static_cast<double>(col))),
+                          scale(mk(cam.delta_y), static_cast<double>(grow)));   // main.cpp:132
+    c.o = mk(cam.position);
+    c.d = sub(mk(cam.position), centre);                                           // main.cpp:133
+    c.acc = d3{0.0, 0.0, 0.0};
+    c.weight = 1.0;
+    c.pixel = p;
+    c.remaining = a.max_depth;
+    c.first_id = -1;
+    c.rays = 0;
+    c.active = 1;
+}
+
 template <bool STREAM>
-__global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, const int tile_capacity)
+__global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, const int tile_pairs)
 {
     extern __shared__ float4 s_tile[];
     const SceneDev& sc = a.scene;
     const unsigned lane_id = threadIdx.x & 31u;
     const unsigned long long total_pixels =
         static_cast<unsigned long long>(a.n_frames) * static_cast<unsigned long long>(a.local_rows) * a.width;
-    const unsigned long long frame_pixels = static_cast<unsigned long long>(a.local_rows) * a.width;
-    const int n_tiles = STREAM ? (sc.n_spheres_padded + tile_capacity - 1) / tile_capacity : 1;
+    const int total_pairs = sc.n_entries_padded >> 1;
+    const int n_tiles = STREAM ? (total_pairs + tile_pairs - 1) / tile_pairs : 1;
+    const unsigned tile_addr = static_cast<unsigned>(__cvta_generic_to_shared(s_tile));
 
     if (!STREAM) {
-        fill_tile(s_tile, sc.sph32, sc.n_spheres_padded, a.filter_eps);
+        fill_tile(s_tile, sc.ent32, total_pairs, a.filter_eps);
         __syncthreads();
     }
 
-    Lane L;
-    L.active = false;
-    L.rays = 0;
-    L.pixel = 0;
-    unsigned long long my_rays = 0, my_over = 0;
-    double my_maxlum = 0.0;
+    Chain ch[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; i++) {
+        ch[i].active = 0;
+        ch[i].qn = 0;
+        ch[i].rays = 0;
+    }
+    FrameTotals tot{0ull, 0ull, 0.0};
 
     for (;;) {
         __syncwarp();
-        // ---- refill idle lanes with fresh pixels (main.cpp:129-134) ------------------------------------
-        const unsigned idle = __ballot_sync(kFull, !L.active);
-        if (idle) {
+        // ---- refill idle chains with fresh pixels ------------------------------------------------------------------
+        const unsigned idle0 = __ballot_sync(kFull, !ch[0].active);
+        const unsigned idle1 = __ballot_sync(kFull, !ch[1].active);
+        if (idle0 | idle1) {
+            const int n0 = __popc(idle0), n1 = __popc(idle1);
             unsigned long long base = 0;
-            const int leader = __ffs(idle) - 1;
-            if (static_cast<int>(lane_id) == leader) base = atomicAdd(&a.counters[0], static_cast<unsigned long long>(__popc(idle)));
-            base = __shfl_sync(kFull, base, leader);
-            if (!L.active) {
-                const unsigned long long p = base + __popc(idle & ((1u << lane_id) - 1u));
-                if (p < total_pixels) {
-                    const int frame = static_cast<int>(p / frame_pixels);
-                    const unsigned rem = static_cast<unsigned>(p - frame * frame_pixels);
-                    const int lrow = rem / a.width;
-                    const int col = rem - lrow * a.width;
-                    int grow = lrow;
-                    if (a.n_ranks > 1) {
-                        const int lb = lrow / a.band_rows;
-                        grow = (lb * a.n_ranks + a.rank) * a.band_rows + (lrow - lb * a.band_rows);
-                    }
-                    const rtx_camera& cam = a.cameras[frame];
-                    using namespace ex;
-                    const d3 centre = add(add(mk(cam.image_top_left), scale(mk(cam.delta_x), static_cast<double>(col))),
-                                          scale(mk(cam.delta_y), static_cast<double>(grow)));   // main.cpp:132
-                    L.o = mk(cam.position);
-                    L.d = sub(mk(cam.position), centre);                                           // main.cpp:133
-                    L.acc = d3{0.0, 0.0, 0.0};
-                    L.weight = 1.0;
-                    L.pixel = p;
-                    L.remaining = a.max_depth;
-                    L.first_id = -1;
-                    L.rays = 0;
-                    L.active = true;
-                }
+            if (lane_id == 0) base = atomicAdd(&a.counters[0], static_cast<unsigned long long>(n0 + n1));
+            base = __shfl_sync(kFull, base, 0);
+            const unsigned below = (1u << lane_id) - 1u;
+            if (!ch[0].active) {
+                const unsigned long long p = base + __popc(idle0 & below);
+                if (p < total_pixels) start_pixel(ch[0], p, a);
+            }
+            if (!ch[1].active) {
+                const unsigned long long p = base + n0 + __popc(idle1 & below);
+                if (p < total_pixels) start_pixel(ch[1], p, a);
             }
         }
+        const int any_active = ch[0].active | ch[1].active;
         if (STREAM) {
-            if (!__syncthreads_or(L.active ? 1 : 0)) break;
+            if (!__syncthreads_or(any_active)) break;
         } else {
-            if (__ballot_sync(kFull, L.active) == 0u) break;
+            if (__ballot_sync(kFull, any_active) == 0u) break;
         }
 
-        // ---- nearest hit (find_closest_hit, main.cpp:67-84) ------------------------------------------------
-        Best best;
-        best.dist = 1.7976931348623157e308;   // DBL_MAX, main.cpp:70
-        best.id = -1;
-        double a_dd = 1.0, dlen = 1.0;
-        RayF f;
-        if (L.active) {
-            a_dd = ex::len2(L.d);
-            dlen = ex::sqrt(a_dd);
-            for (int w = 0; w < sc.n_walls; w++) {
-                const WallDev& wd = sc.walls[w];
-                const double t = wall_exact(L.o, L.d, wd);
-                if (better(t, wd.id, best)) {
-                    best.dist = t;
-                    best.id = wd.id;
-                }
-            }
-            f = make_rayf(L.o, L.d, dlen, a.origin_bound);
-            f.best_hi = __double2float_ru(best.dist);
-        } else {
-            // idle lane (only while the frame drains): constants that no sphere can pass
-            f.dx = f.dy = f.dz = 0.f;
-            f.kx = f.ky = f.kz = 1e15f;
-            f.d_o = 0.f;
-            f.best_hi = -__int_as_float(0x7f800000);
-        }
-
+        // ---- nearest hit (find_closest_hit, main.cpp:67-84): FP32 screen of every entry, exact test of survivors ----
+        const Packed k0 = setup_chain(ch[0], a.origin_bound);
+        const Packed k1 = setup_chain(ch[1], a.origin_bound);
         if (STREAM) {
             for (int t = 0; t < n_tiles; t++) {
-                const int begin = t * tile_capacity;
-                const int count = min(tile_capacity, sc.n_spheres_padded - begin);
+                const int first_pair = t * tile_pairs;
+                const int count = min(tile_pairs, total_pairs - first_pair);
                 __syncthreads();
-                fill_tile(s_tile, sc.sph32 + begin, count, a.filter_eps);
+                fill_tile(s_tile, sc.ent32 + 2 * first_pair, count, a.filter_eps);
                 __syncthreads();
-                scan_tile(s_tile, count, begin, f, L.o, L.d, a_dd, dlen, sc, best);
+                scan_tile(tile_addr, count, 2 * first_pair, k0, k1, ch[0], ch[1], sc, a.filter_eps);
             }
         } else {
-            scan_tile(s_tile, sc.n_spheres_padded, 0, f, L.o, L.d, a_dd, dlen, sc, best);
+            scan_tile(tile_addr, total_pairs, 0, k0, k1, ch[0], ch[1], sc, a.filter_eps);
         }
+        drain_queue(ch[0], sc, a.filter_eps);
+        drain_queue(ch[1], sc, a.filter_eps);
 
-        if (!L.active) continue;
-
-        // ---- shade this segment (recursive_ray_tracing, main.cpp:89-119) -----------------------------------
-        using namespace ex;
-        L.rays++;
-        if (L.rays == 1) L.first_id = best.id;
-        bool done;
-        if (best.id < 0) {
-            // out_color, main.cpp:28-37 (sign test on the unnormalised z)
-            d3 c;
-            if (L.d.z < 0.0) {
-                c = a.ground;
-            } else {
-                const double vz = div(L.d.z, dlen);
-                // pow(v.z, 0.25): two correctly rounded square roots are within 1 ulp of it
-                const double s = (a.sky_exponent == 0.25) ? sqrt(sqrt(vz)) : pow(vz, a.sky_exponent);
-                c = lerp(a.sky_low, a.sky_high, s);
-            }
-            L.acc.x += L.weight * c.x;
-            L.acc.y += L.weight * c.y;
-            L.acc.z += L.weight * c.z;
-            done = true;
-        } else {
-            d3 normal;
-            const int slot = sc.slot[best.id];
-            if (sc.kind[best.id] == RTX_SPHERE) {
-                sphere_exact(L.o, L.d, a_dd, dlen, sc.sph64[slot], &normal);
-            } else {
-                normal = sc.walls[slot].n;
-            }
-            const MaterialDev m = sc.mats[best.id];
-            const d3 pos = add(L.o, scale(L.d, best.dist));                    // main.cpp:99
-            const d3 ldir = unit(sub(a.light, pos));                           // main.cpp:44,57
-            const d3 nn = unit(normal);                                        // main.cpp:46,56
-            const d3 dhat = divs(L.d, dlen);                                   // normalize(d); normalize(-d) = -dhat
-            const double lambert = dot(ldir, nn);                              // main.cpp:46
-            const double di = lambert > 0 ? lambert : 0;
-            const d3 half = unit(add(neg(dhat), ldir));                        // main.cpp:59
-            const double sp = dot(half, nn);                                   // main.cpp:60
-            const double si = pow(sp > 0 ? sp : 0, m.exponent);                // main.cpp:103
-            const double k = add(add(mul(di, m.diffuse), mul(si, m.specular)), m.ambient);
-            const d3 local = scale(m.color, k);                                // main.cpp:104
-            if (L.remaining <= 0) {                                            // main.cpp:105-108
-                L.acc.x += L.weight * local.x;
-                L.acc.y += L.weight * local.y;
-                L.acc.z += L.weight * local.z;
-                done = true;
-            } else {
-                // lerp(local, reflected, metallic) unrolled front to back (main.cpp:117)
-                const double wl = L.weight * (1.0 - m.metallic);
-                L.acc.x += wl * local.x;
-                L.acc.y += wl * local.y;
-                L.acc.z += wl * local.z;
-                L.weight *= m.metallic;
-                const d3 start = add(pos, scale(normal, a.reflect_offset));    // main.cpp:111 (normal unnormalised)
-                const double kk = mul(2.0, dot(dhat, nn));                     // vec.cpp:55
-                L.d = sub(dhat, scale(nn, kk));                                // vec.cpp:56
-                L.o = start;
-                L.remaining--;
-                done = false;
-            }
-        }
-
-        if (done) {
-            const unsigned long long p = L.pixel;
-            if (a.rgba8) a.rgba8[p] = pack_rgba(L.acc.x, L.acc.y, L.acc.z, a.quantise_mode);
-            if (a.rad64) {
-                a.rad64[3 * p + 0] = L.acc.x;
-                a.rad64[3 * p + 1] = L.acc.y;
-                a.rad64[3 * p + 2] = L.acc.z;
-            }
-            if (a.rad32) {
-                a.rad32[3 * p + 0] = static_cast<float>(L.acc.x);
-                a.rad32[3 * p + 1] = static_cast<float>(L.acc.y);
-                a.rad32[3 * p + 2] = static_cast<float>(L.acc.z);
-            }
-            if (a.object_id) a.object_id[p] = L.first_id;
-            if (a.hit_mask) a.hit_mask[p] = L.first_id >= 0 ? 1 : 0;
-            if (a.ray_count) a.ray_count[p] = static_cast<uint8_t>(L.rays);
-            my_rays += static_cast<unsigned long long>(L.rays);
-            if (over_range(L.acc.x, L.acc.y, L.acc.z)) my_over++;
-            const double lum = (L.acc.x + L.acc.y + L.acc.z) * (1.0 / 3.0);
-            if (lum > my_maxlum) my_maxlum = lum;
-            L.active = false;
-        }
+        // ---- shading, bounce or pixel write --------------------------------------------------------------------------------
+        if (ch[0].active) shade_chain(ch[0], a, tot);
+        if (ch[1].active) shade_chain(ch[1], a, tot);
     }
 
     // ---- diagnostics: warp-shuffle reduction, one atomic per warp (never alters a pixel) ----------------------
     __syncwarp();
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-        my_rays += __shfl_down_sync(kFull, my_rays, off);
-        my_over += __shfl_down_sync(kFull, my_over, off);
-        my_maxlum = fmax(my_maxlum, __shfl_down_sync(kFull, my_maxlum, off));
+        tot.rays += __shfl_down_sync(kFull, tot.rays, off);
+        tot.over += __shfl_down_sync(kFull, tot.over, off);
+        tot.maxlum = fmax(tot.maxlum, __shfl_down_sync(kFull, tot.maxlum, off));
     }
     if (lane_id == 0) {
-        if (my_rays) atomicAdd(&a.counters[1], my_rays);
-        if (my_over) atomicAdd(&a.counters[2], my_over);
+        if (tot.rays) atomicAdd(&a.counters[1], tot.rays);
+        if (tot.over) atomicAdd(&a.counters[2], tot.over);
         // non-negative doubles order like their bit patterns
-        if (my_maxlum > 0.0) atomicMax(&a.counters[3], static_cast<unsigned long long>(__double_as_longlong(my_maxlum)));
+        if (tot.maxlum > 0.0) atomicMax(&a.counters[3], static_cast<unsigned long long>(__double_as_longlong(tot.maxlum)));
     }
 }
 
 cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, int* launches)
 {
-    const size_t need = static_cast<size_t>(args.scene.n_spheres_padded) * sizeof(float4);
+    constexpr int iter_bytes = kPairsPerIter * 32;
+    const size_t need = static_cast<size_t>(args.scene.n_entries_padded) * sizeof(float4);
     const bool stream_tiles = need > static_cast<size_t>(kMaxSmemBytes);
-    const size_t smem = stream_tiles ? static_cast<size_t>(kMaxSmemBytes) / (kUnroll * sizeof(float4)) * (kUnroll * sizeof(float4))
-                                     : (need ? need : sizeof(float4));
-    const int tile_capacity = static_cast<int>(smem / sizeof(float4));
+    const size_t smem = stream_tiles ? static_cast<size_t>(kMaxSmemBytes) / iter_bytes * iter_bytes : (need ? need : iter_bytes);
+    const int tile_pairs = static_cast<int>(smem / 32);
     const unsigned long long total =
         static_cast<unsigned long long>(args.n_frames) * static_cast<unsigned long long>(args.local_rows) * args.width;
     if (total == 0) return cudaSuccess;
-    unsigned long long blocks = (total + kThreads - 1) / kThreads;
+    unsigned long long blocks = (total + kThreads * kChains - 1) / (kThreads * kChains);
     if (blocks > static_cast<unsigned long long>(n_sms)) blocks = n_sms;
     cudaError_t err;
     if (stream_tiles) {
         err = cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (err != cudaSuccess) return err;
-        trace_kernel<true><<<static_cast<unsigned>(blocks), kThreads, smem, stream>>>(args, tile_capacity);
+        trace_kernel<true><<<static_cast<unsigned>(blocks), kThreads, smem, stream>>>(args, tile_pairs);
     } else {
         err = cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (err != cudaSuccess) return err;
-        trace_kernel<false><<<static_cast<unsigned>(blocks), kThreads, smem, stream>>>(args, tile_capacity);
+        trace_kernel<false><<<static_cast<unsigned>(blocks), kThreads, smem, stream>>>(args, tile_pairs);
     }
     if (launches) (*launches)++;
     return cudaGetLastError();
