@@ -13,3 +13,8 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
     "$here/csrc/api.cu" "$here/csrc/trace.cu" "$here/csrc/aux_kernels.cu" \
     -o "$here/librtx_b200.so"
 echo "built $here/librtx_b200.so"
+# C++ host facade example: the reference's main loop, headless (writes PPM). Links the C ABI only.
+g++ -std=c++17 -O2 -ffp-contract=off -Wall -I"$here/../include" -I"$here/host" \
+    "$here/examples/headless_main.cpp" -o "$here/rtx_headless" \
+    -L"$here" -lrtx_b200 -Wl,-rpath,'$ORIGIN'
+echo "built $here/rtx_headless"

@@ -567,7 +567,7 @@ int rtx_unpermute_bands(rtx_ctx* ctx, const void* band_major, void* row_major, i
 int rtx_ffma_peak(rtx_ctx* ctx, int32_t variant, double* tflops, double* mhz)
 {
     if (!ctx) return RTX_ERR_INVALID;
-    if (variant != 0 && variant != 1) return fail(ctx, RTX_ERR_INVALID, "rtx_ffma_peak: variant must be 0 or 1");
+    if (variant < 0 || variant > 4) return fail(ctx, RTX_ERR_INVALID, "rtx_ffma_peak: variant must be 0..4");
     RTX_CUDA(ctx, cudaSetDevice(ctx->device));
     RTX_CUDA(ctx, run_ffma_peak(variant, ctx->n_sms, ctx->stream, tflops, mhz));
     ctx->error.clear();

@@ -227,6 +227,45 @@ __global__ void __launch_bounds__(512) ffma_peak_packed(float* sink, float a, fl
     if (blockIdx.x == 0 && threadIdx.x == 0) clocks[0] = t1 - t0;
 }
 
+// Register-file pressure variants of the packed FMA: what limits the trace kernel's screen is not the FMA pipe
+// but how many distinct registers an FFMA2 reads (three 64-bit operands = 6 registers over 2 issue cycles).
+//   variant 2: d_k = fma2(a_k, b_k, d_k)   three distinct pairs per instruction, nothing shared
+//   variant 3: d_k = fma2(a_k, B,   d_k)   one pair shared by consecutive instructions (operand reuse cache)
+//   variant 4: d_k = fma2(a_k, a_k, d_k)   two distinct pairs
+template <int MODE>
+__global__ void __launch_bounds__(512) ffma_peak_operands(float* sink, float a, float b, long long* clocks)
+{
+    constexpr int N = 8;
+    unsigned long long acc[N], x[N], y[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        const float lo = threadIdx.x * 1e-3f + k, hi = lo + 0.5f;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(acc[k]) : "f"(lo), "f"(hi));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x[k]) : "f"(a + k * 1e-9f), "f"(a - k * 1e-9f));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(y[k]) : "f"(b + k * 1e-9f), "f"(b - k * 1e-9f));
+    }
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kPeakIters; it++) {
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            if (MODE == 2) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[k]) : "l"(x[k]), "l"(y[k]));
+            if (MODE == 3) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[k]) : "l"(x[k]), "l"(y[0]));
+            if (MODE == 4) asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc[k]) : "l"(x[k]));
+        }
+    }
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[k]));
+        s += lo + hi;
+    }
+    if (s == 123.456f) sink[0] = s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) clocks[0] = t1 - t0;
+}
+
 cudaError_t run_ffma_peak(int variant, int n_sms, cudaStream_t stream, double* tflops, double* mhz)
 {
     float* sink = nullptr;
@@ -244,6 +283,12 @@ cudaError_t run_ffma_peak(int variant, int n_sms, cudaStream_t stream, double* t
         cudaEventRecord(e0, stream);
         if (variant == 1)
             ffma_peak_packed<<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
+        else if (variant == 2)
+            ffma_peak_operands<2><<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
+        else if (variant == 3)
+            ffma_peak_operands<3><<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
+        else if (variant == 4)
+            ffma_peak_operands<4><<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
         else
             ffma_peak_scalar<<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
         cudaEventRecord(e1, stream);

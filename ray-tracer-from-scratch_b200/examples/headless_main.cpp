@@ -1,0 +1,115 @@
+// headless_main.cpp — the reference's main loop (main.cpp:144-397) without SDL, on the GPU path.
+//
+// Same camera and scene set-up (main.cpp:146-163), same per-frame sequence — key events move the camera
+// (main.cpp:262-306; init() is NOT re-run after a move, exactly like the reference), then
+//     rt_scene(u, scene, cam, frame_buffer)            main.cpp:329
+//     quantise loop into the RGBA8888 surface          main.cpp:338-347
+// — and the same timing log at exit (main.cpp:384-392) with the reference's stage names, plus the device-side
+// CUDA-event times. The window/renderer/texture calls are replaced by a binary PPM (or raw RGBA8888) file.
+//
+//   rtx_headless [--width 640] [--aspect 1] [--depth 10] [--frames 3] [--keys wwad] [--out frame.ppm] [--raw frame.rgba]
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <numeric>
+#include <string>
+
+#include "rtx_scene.hpp"
+
+using namespace rtx;
+
+int main(int argc, char* argv[])
+{
+    int width = 640, depth = 10, frames = 3;
+    double aspect = 1.0;   // ASPECT_RATIO = 4/3 is integer division = 1 in the reference (main.cpp:25)
+    std::string keys, out_ppm = "frame.ppm", out_raw;
+    for (int k = 1; k + 1 < argc; k += 2) {
+        const std::string a = argv[k];
+        if (a == "--width") width = std::atoi(argv[k + 1]);
+        else if (a == "--aspect") aspect = std::atof(argv[k + 1]);
+        else if (a == "--depth") depth = std::atoi(argv[k + 1]);
+        else if (a == "--frames") frames = std::atoi(argv[k + 1]);
+        else if (a == "--keys") keys = argv[k + 1];
+        else if (a == "--out") out_ppm = argv[k + 1];
+        else if (a == "--raw") out_raw = argv[k + 1];
+        else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
+    }
+    try {
+        Camera cam;                                   // main.cpp:146-154
+        cam.aspect_ratio = aspect;
+        cam.image_width = width;
+        cam.movement_speed = 0.1;
+        cam.vfov = 90;
+        cam.position = point3(0, 0, 0);
+        cam.lookat = point3(-1, 0, 0);
+        cam.vup = vec3(0, 0, -1);
+        auto u = cam.init();
+
+        Scene scene;                                  // main.cpp:156-163
+        scene.push_back(std::make_unique<Sphere>(Material(RGB(0, 1, 0), 0.5), point3(1.5, 0, 0), .5));
+        scene.push_back(std::make_unique<Wall>(Material(RGB(0, 0, 1)), point3(3.0, 2, 0), vec3(0, -1, 0), 1, 1));
+        scene.push_back(std::make_unique<Wall>(Material(RGB(0, 1, 0)), point3(3.0, -3, 0), vec3(0, 1, 0), 2, 2));
+
+        const int H = static_cast<int>(cam.image_height), W = width;
+        std::vector<uint32_t> surface(static_cast<size_t>(W) * H);
+        const int pitch = W * 4;
+        std::vector<std::vector<RGB>> frame_buffer(H, std::vector<RGB>(W, RGB(0, 0, 0)));   // [row][column]
+
+        Renderer renderer(0);
+        renderer.params.max_depth = depth;
+        std::vector<int64_t> total_times, rt_times, surface_update_times;
+        std::vector<double> device_rt_ms, device_surface_ms;
+        for (int frame = 0; frame < frames; frame++) {
+            if (frame < static_cast<int>(keys.size())) {   // one key event per frame (main.cpp:262-306)
+                switch (keys[frame]) {
+                    case 'w': cam.forward(); break;
+                    case 's': cam.backward(); break;
+                    case 'a': cam.left(); break;
+                    case 'd': cam.right(); break;
+                    default: break;
+                }
+            }
+            auto rt_start = std::chrono::high_resolution_clock::now();
+            renderer.rt_scene(u, scene, cam, frame_buffer);
+            auto rt_end = std::chrono::high_resolution_clock::now();
+            device_rt_ms.push_back(renderer.stats.raytracing_ms);
+            renderer.update_surface(frame_buffer, H, W, surface.data(), pitch);
+            auto surface_end = std::chrono::high_resolution_clock::now();
+            device_surface_ms.push_back(renderer.stats.surface_update_ms);
+            rt_times.push_back(std::chrono::duration_cast<std::chrono::microseconds>(rt_end - rt_start).count());
+            surface_update_times.push_back(std::chrono::duration_cast<std::chrono::milliseconds>(surface_end - rt_end).count());
+            total_times.push_back(std::chrono::duration_cast<std::chrono::milliseconds>(surface_end - rt_start).count());
+        }
+
+        if (!out_ppm.empty()) {
+            FILE* f = std::fopen(out_ppm.c_str(), "wb");
+            if (!f) throw std::runtime_error("cannot open " + out_ppm);
+            std::fprintf(f, "P6\n%d %d\n255\n", W, H);
+            for (uint32_t p : surface) {
+                const unsigned char rgb[3] = {static_cast<unsigned char>(p >> 24), static_cast<unsigned char>(p >> 16), static_cast<unsigned char>(p >> 8)};
+                std::fwrite(rgb, 1, 3, f);
+            }
+            std::fclose(f);
+        }
+        if (!out_raw.empty()) {
+            FILE* f = std::fopen(out_raw.c_str(), "wb");
+            if (!f) throw std::runtime_error("cannot open " + out_raw);
+            std::fwrite(surface.data(), 4, surface.size(), f);
+            std::fclose(f);
+        }
+
+        auto mean = [](const std::vector<int64_t>& v) { return v.empty() ? 0 : std::accumulate(v.begin(), v.end(), int64_t{0}) / static_cast<int64_t>(v.size()); };
+        auto meand = [](const std::vector<double>& v) { return v.empty() ? 0.0 : std::accumulate(v.begin(), v.end(), 0.0) / v.size(); };
+        std::cout << "Number of frames: " << frames << " : " << mean(total_times) << " ms average frame time\n";
+        std::cout << "   " << mean(rt_times) << " microseconds for average raytracing\n";
+        std::cout << "   " << mean(surface_update_times) << " milliseconds for surface average update\n";
+        std::cout << "   device (CUDA events): " << meand(device_rt_ms) << " ms raytracing, " << meand(device_surface_ms) << " ms surface update, "
+                  << renderer.stats.over_range_pixels << " over-range pixels in the last frame\n";
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "rtx_headless: %s\n", e.what());
+        return 1;
+    }
+}

@@ -1,0 +1,274 @@
+// rtx_scene.hpp — C++ host façade over the C ABI (include/rtx_b200.h).
+//
+// Mirrors the reference's scene interface so that its main loop body (main.cpp:329-347) becomes two calls:
+//
+//     rtx::rt_scene(u, scene, cam, frame_buffer);            // was rt_scene(...)            main.cpp:329
+//     rtx::update_surface(frame_buffer, pixels, pitch);      // was the quantise loop       main.cpp:338-347
+//
+// Same class names, constructor argument order and defaults as scene.h / vec.h (Material's metallic-before-
+// ambient order, DEFAULT_MAT's positional quirk, Wall normalising its normal, ray(direction, origin), Camera
+// fields and init() returning {pixel_delta_x, pixel_delta_y}). The reference's members are private without
+// getters (scene.h:64-67,77-78), so here every geometry can DESCRIBE itself as the rtx_object POD the C ABI
+// takes: the description is the source of truth. No pixel is computed on the host: there is no CPU fallback,
+// a missing GPU is a thrown std::runtime_error.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rtx_b200.h"
+
+namespace rtx {
+
+// ---- vec3 (vec.h:12-40): three doubles, the reference's operation order -------------------------------------
+class vec3 {
+public:
+    double x, y, z;
+    vec3() : x{0}, y{0}, z{0} {}
+    vec3(double xv, double yv, double zv) : x{xv}, y{yv}, z{zv} {}
+    double length_squared() const { return x * x + y * y + z * z; }
+    double length() const { return std::sqrt(length_squared()); }
+    vec3 operator/(double t) const { return {x / t, y / t, z / t}; }
+    vec3 normalize() const { return *this / length(); }                       // three divides (vec.cpp:21-24)
+    vec3 operator+(const vec3& o) const { return {x + o.x, y + o.y, z + o.z}; }
+    vec3 operator-(const vec3& o) const { return {x - o.x, y - o.y, z - o.z}; }
+    vec3 operator-() const { return {-x, -y, -z}; }
+    vec3 operator*(const vec3& o) const { return {x * o.x, y * o.y, z * o.z}; }
+    vec3 operator*(double d) const { return {x * d, y * d, z * d}; }
+    static double dot(const vec3& a, const vec3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+    static vec3 cross(const vec3& u, const vec3& v) { return {u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x}; }
+    static vec3 linear_interp(const vec3& a, const vec3& b, double d) { return {a.x + d * (b.x - a.x), a.y + d * (b.y - a.y), a.z + d * (b.z - a.z)}; }
+    static vec3 reflect(const vec3& v, const vec3& normal)
+    {
+        const vec3 nn = normal.normalize(), nv = v.normalize();
+        return nv - nn * (2 * dot(nv, nn));
+    }
+    rtx_vec3 pod() const { return rtx_vec3{x, y, z}; }
+};
+using point3 = vec3;
+using RGB = vec3;
+
+// ---- ray (scene.h:5-25): constructor order is (direction, origin) -----------------------------------------------
+class ray {
+    vec3 direction;
+    point3 origin;
+public:
+    ray() {}
+    ray(const vec3& dir, const point3& org) : direction{dir}, origin{org} {}
+    point3 at(double t) const { return origin + direction * t; }
+    vec3 get_direction() const { return direction; }
+    vec3 get_origin() const { return origin; }
+};
+
+// ---- Material (scene.h:35-49) ------------------------------------------------------------------------------------------
+struct Material {
+    RGB color;
+    double ambient, metallic, diffuse, specular, specular_exponent;
+    Material(RGB color, double metallic = .5, double ambient = .1, double diffuse = .9, double specular = .4, double specular_exponent = 50)
+        : color{color}, ambient{ambient}, metallic{metallic}, diffuse{diffuse}, specular{specular}, specular_exponent{specular_exponent} {}
+    rtx_material pod() const { return rtx_material{color.pod(), ambient, metallic, diffuse, specular, specular_exponent}; }
+};
+// DEFAULT_MAT (scene.h:3) binds positionally to metallic .9, ambient .9, diffuse .3, specular 30, exponent 50.
+inline Material default_mat() { return Material(RGB(1, 1, 1), .9, .9, .3, 30); }
+
+// ---- SceneGeometry / Sphere / Wall (scene.h:51-84) -------------------------------------------------------------
+class SceneGeometry {
+    Material mat;
+public:
+    explicit SceneGeometry(Material m) : mat(m) {}
+    virtual ~SceneGeometry() {}
+    Material get_material() const { return mat; }
+    virtual rtx_object describe() const = 0;     // replaces the virtual intersect(): the GPU does the intersecting
+};
+
+class Sphere : public SceneGeometry {
+    point3 center;
+    double radius;
+public:
+    Sphere(Material m = default_mat(), point3 center = point3(0, 0, 0), double radius = 1.0) : SceneGeometry{m}, center{center}, radius{radius} {}
+    rtx_object describe() const override
+    {
+        rtx_object o{};
+        o.kind = RTX_SPHERE;
+        o.mat = get_material().pod();
+        o.p = center.pod();
+        o.a = radius;
+        return o;
+    }
+};
+
+class Wall : public SceneGeometry {
+    point3 position;   // a corner of the rectangle
+    vec3 normal;       // stored as given; the library normalises it like the reference ctor (scene.h:71)
+    double length, width;
+public:
+    Wall(Material m = default_mat(), point3 position = point3(0, 0, 0), vec3 normal = vec3(0, 0, 0), double length = 1.0, double width = 1.0)
+        : SceneGeometry{m}, position{position}, normal{normal}, length{length}, width{width} {}
+    rtx_object describe() const override
+    {
+        rtx_object o{};
+        o.kind = RTX_WALL;
+        o.mat = get_material().pod();
+        o.p = position.pod();
+        o.n = normal.pod();
+        o.a = length;
+        o.b = width;
+        return o;
+    }
+};
+
+using Scene = std::vector<std::unique_ptr<SceneGeometry>>;
+
+// ---- Camera (scene.h:86-112, scene.cpp:80-165) ---------------------------------------------------------------------
+class Camera {
+    vec3 forward_vec() const { return direction.normalize(); }
+    vec3 right_vec() const { return vec3::cross(direction, vup).normalize(); }
+public:
+    vec3 direction, image_top_left;
+    double movement_speed = 0.1, aspect_ratio = 1.0, image_width = 640, image_height = 0, focal_length = 0, vfov = 90;
+    point3 position = point3(0, 0, -1);
+    point3 lookat = point3(0, 0, 0);
+    vec3 vup = vec3(0, 1, 0);
+
+    // Camera::init through the library's host code (rtx_camera_init): one implementation of the 3.14 / int()
+    // quirks. Returns {pixel_delta_x, pixel_delta_y}; like the reference it is NOT re-run by the move methods.
+    std::vector<vec3> init()
+    {
+        rtx_camera_desc d{position.pod(), lookat.pod(), vup.pod(), vfov, aspect_ratio, image_width};
+        rtx_camera c{};
+        if (rtx_camera_init(&d, &c) != RTX_OK) throw std::runtime_error("rtx_camera_init failed");
+        image_height = c.height;
+        focal_length = (position - lookat).length();
+        direction = (position - lookat).normalize();
+        image_top_left = vec3(c.image_top_left.x, c.image_top_left.y, c.image_top_left.z);
+        return {vec3(c.delta_x.x, c.delta_x.y, c.delta_x.z), vec3(c.delta_y.x, c.delta_y.y, c.delta_y.z)};
+    }
+    void forward() { position = position + forward_vec() * movement_speed; }     // scene.cpp:121-123
+    void backward() { position = position - forward_vec() * movement_speed; }
+    void right() { position = position + right_vec() * movement_speed; }
+    void left() { position = position - right_vec() * movement_speed; }
+
+    rtx_camera pod(const std::vector<vec3>& u) const
+    {
+        rtx_camera c{};
+        c.position = position.pod();
+        c.image_top_left = image_top_left.pod();
+        c.delta_x = u.at(0).pod();
+        c.delta_y = u.at(1).pod();
+        c.width = static_cast<int32_t>(image_width);
+        c.height = static_cast<int32_t>(image_height);
+        return c;
+    }
+};
+
+// ---- the renderer: one rtx_ctx -------------------------------------------------------------------------------------------
+class Renderer {
+    rtx_ctx* ctx = nullptr;
+    const Scene* uploaded = nullptr;
+    size_t uploaded_size = 0;
+    void check(int rc, const char* what) const
+    {
+        if (rc != RTX_OK) throw std::runtime_error(std::string(what) + ": " + rtx_status_string(rc) + ": " + rtx_last_error(ctx));
+    }
+public:
+    rtx_params params;
+    rtx_stats stats{};
+    explicit Renderer(int device = 0)
+    {
+        rtx_default_params(&params);
+        const int rc = rtx_create(&ctx, device);
+        if (rc != RTX_OK) throw std::runtime_error(std::string("rtx_create: ") + rtx_status_string(rc) + ": " + rtx_last_error(nullptr));
+    }
+    ~Renderer() { rtx_destroy(ctx); }
+    Renderer(const Renderer&) = delete;
+    Renderer& operator=(const Renderer&) = delete;
+
+    void set_scene(const Scene& scene)
+    {
+        std::vector<rtx_object> objs;
+        objs.reserve(scene.size());
+        for (const auto& g : scene) objs.push_back(g->describe());
+        check(rtx_set_scene(ctx, objs.data(), static_cast<int32_t>(objs.size())), "rtx_set_scene");
+        uploaded = &scene;
+        uploaded_size = scene.size();
+    }
+
+    // rt_scene (main.cpp:124-139): fills frame_buffer[i][j] (row i, column j) with the radiance of every pixel.
+    // The scene is uploaded on first use and whenever a different scene object (or size) is passed.
+    void rt_scene(const std::vector<vec3>& u, const Scene& scene, const Camera& cam, std::vector<std::vector<RGB>>& frame_buffer)
+    {
+        if (uploaded != &scene || uploaded_size != scene.size()) set_scene(scene);
+        const rtx_camera c = cam.pod(u);
+        const size_t W = c.width, H = c.height;
+        if (frame_buffer.size() < H) throw std::out_of_range("frame_buffer has fewer rows than image_height");   // .at(i), main.cpp:136
+        radiance.resize(W * H * 3);
+        rtx_outputs out{};
+        out.memory = RTX_MEM_HOST;
+        out.radiance_f64 = radiance.data();
+        check(rtx_render(ctx, &c, 1, &params, &out, &stats), "rtx_render");
+        for (size_t i = 0; i < H; i++) {
+            std::vector<RGB>& row = frame_buffer[i];
+            if (row.size() < W) throw std::out_of_range("frame_buffer row shorter than image_width");
+            const double* src = &radiance[i * W * 3];
+            for (size_t j = 0; j < W; j++) row[j] = RGB(src[3 * j], src[3 * j + 1], src[3 * j + 2]);
+        }
+    }
+
+    // One call for both stages when only the 8-bit surface is wanted (what main.cpp:329-347 produces):
+    // pixels[i * pitch/4 + j] = RGBA8888 word. pitch in bytes, as SDL_Surface::pitch.
+    void render_surface(const std::vector<vec3>& u, const Scene& scene, const Camera& cam, uint32_t* pixels, int pitch)
+    {
+        if (uploaded != &scene || uploaded_size != scene.size()) set_scene(scene);
+        const rtx_camera c = cam.pod(u);
+        const size_t W = c.width, H = c.height;
+        rtx_outputs out{};
+        out.memory = RTX_MEM_HOST;
+        if (static_cast<size_t>(pitch) == W * 4) {
+            out.rgba8 = pixels;
+            check(rtx_render(ctx, &c, 1, &params, &out, &stats), "rtx_render");
+        } else {
+            surface.resize(W * H);
+            out.rgba8 = surface.data();
+            check(rtx_render(ctx, &c, 1, &params, &out, &stats), "rtx_render");
+            for (size_t i = 0; i < H; i++)
+                for (size_t j = 0; j < W; j++) pixels[i * (pitch / 4) + j] = surface[i * W + j];
+        }
+    }
+
+    // The quantise loop (main.cpp:338-347) on a frame buffer the caller already holds.
+    void update_surface(const std::vector<std::vector<RGB>>& frame_buffer, size_t H, size_t W, uint32_t* pixels, int pitch)
+    {
+        radiance.resize(W * H * 3);
+        for (size_t i = 0; i < H; i++)
+            for (size_t j = 0; j < W; j++) {
+                const RGB& v = frame_buffer.at(i).at(j);
+                double* dst = &radiance[(i * W + j) * 3];
+                dst[0] = v.x; dst[1] = v.y; dst[2] = v.z;
+            }
+        surface.resize(W * H);
+        check(rtx_quantise(ctx, nullptr, radiance.data(), static_cast<int64_t>(W * H), params.quantise_mode, surface.data(), RTX_MEM_HOST, &stats),
+              "rtx_quantise");
+        for (size_t i = 0; i < H; i++)
+            for (size_t j = 0; j < W; j++) pixels[i * (pitch / 4) + j] = surface[i * W + j];
+    }
+
+private:
+    std::vector<double> radiance;
+    std::vector<uint32_t> surface;
+};
+
+// Free-function form with the reference's exact signature shape (main.cpp:124-125); uses one process-wide renderer.
+inline Renderer& default_renderer()
+{
+    static Renderer r(0);
+    return r;
+}
+inline void rt_scene(std::vector<vec3> u, const Scene& scene, const Camera& cam, std::vector<std::vector<RGB>>& frame_buffer)
+{
+    default_renderer().rt_scene(u, scene, cam, frame_buffer);
+}
+
+}  // namespace rtx

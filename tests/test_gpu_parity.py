@@ -265,3 +265,24 @@ def test_ray_far_outside_scene_bound_falls_back_to_exact(gpu, renderer_mod, port
     pod = cam.pod()
     got, st = render(gpu, renderer_mod, scene, pod, 8)
     check_frame(got, port.render(scene, pod, 8), st)
+
+
+def test_cpp_headless_main_matches_reference_main_loop(tmp_path, port, S, renderer_mod):
+    """The C++ host facade (host/rtx_scene.hpp) driving the C ABI like the reference's main loop (main.cpp:250-375):
+    frame 0 at the start position, frame 1 after a 'w' key (Camera::forward, init() NOT re-run, as the reference)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(renderer_mod.LIB_PATH), "rtx_headless")
+    assert os.path.exists(exe), "build() must produce rtx_headless"
+    raw, ppm = tmp_path / "f.rgba", tmp_path / "f.ppm"
+    out = subprocess.run([exe, "--width", "320", "--frames", "2", "--keys", "xw", "--raw", str(raw), "--out", str(ppm)],
+                         check=True, capture_output=True, text=True).stdout
+    assert "microseconds for average raytracing" in out and "milliseconds for surface average update" in out
+    cam = S.default_camera(320, 1.0)
+    pod = cam.pod()
+    pod.position = type(pod.position)(0.1, 0.0, 0.0)        # forward(): position + normalize(direction) * 0.1, direction = (1,0,0)
+    exp = port.render(S.default_scene(), pod, 10, want=("rgba8",))["rgba8"]
+    got = np.fromfile(raw, dtype=np.uint32).reshape(320, 320)
+    assert np.array_equal(got, exp)
+    data = open(ppm, "rb").read()
+    assert data.startswith(b"P6\n320 320\n255\n") and len(data) == 15 + 320 * 320 * 3
