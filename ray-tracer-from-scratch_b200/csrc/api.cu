@@ -84,7 +84,10 @@ int grow(rtx_ctx* ctx, void** p, size_t* cap, size_t need)
     return RTX_OK;
 }
 
-constexpr int kPad = 8;   // entries per hot-loop iteration of trace.cu (kPairsPerIter * 2)
+#ifndef RTX_PAIRS
+#define RTX_PAIRS 6
+#endif
+constexpr int kPad = 2 * RTX_PAIRS;   // entries per hot-loop iteration of trace.cu (kPairsPerIter * 2)
 
 }  // namespace
 
@@ -439,10 +442,10 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
     a.reflect_offset = p.reflect_offset;
     a.sky_exponent = p.sky_exponent;
     // FP32 screen error bound (derivation in DESIGN.md §3.2): with B = scene/camera extent and ray origins
-    // within 2B, the line-distance error is below 1.1e-6*B; 4e-6*B leaves a 4x margin. Origins beyond 2B
+    // within 2B, the line-distance error is below 1.7e-6*B; 8e-6*B leaves a 4x margin. Origins beyond 2B
     // (primary-ray overshoot) fall back to exact tests lane by lane.
     const double B = std::fmax(std::fmax(ctx->scene_bound, cam_bound), 1e-3);
-    a.filter_eps = static_cast<float>(4e-6 * B);
+    a.filter_eps = static_cast<float>(8e-6 * B);
     a.origin_bound = static_cast<float>(2.0 * B);
     a.rgba8 = unfused ? nullptr : static_cast<uint32_t*>(dev[0]);
     a.rad32 = static_cast<float*>(dev[1]);

@@ -12,11 +12,11 @@
 //    (main.cpp:117) becomes a front-to-back accumulation: colour = sum_k W_k (1-m_k) L_k + W_end * T.
 //
 //  * Exact decisions, FP32 search. The reference is IEEE double. Every (ray, object) pair is first screened by a
-//    CONSERVATIVE FP32 test: squared distance from the object's centre to the ray's line, |c x d^ - o x d^|^2,
-//    against (r + E)^2, E bounding the FP32 error (filter_eps). The cross-product form has no |oc|^2 - b^2
-//    cancellation: its error grows with |c|, not |c|^2. Walls take part through their bounding sphere.
-//    The screen is 9 packed FFMA2 (fma.rn.f32x2, two spheres per instruction) + 2 funnel shifts per two pairs;
-//    each broadcast LDS.128 of sphere data feeds four pairs (2 spheres x 2 chains).
+//    CONSERVATIVE FP32 test: squared distance from the object's centre to the ray's line, computed in a per-ray
+//    frame (u, v perpendicular to the ray): (u.c - u.o)^2 + (v.c - v.o)^2, against (r + E)^2, E bounding the FP32
+//    error (filter_eps). The projected form has no |oc|^2 - b^2 cancellation: its error grows with |c|, not |c|^2.
+//    Walls take part through their bounding sphere. The screen is 8 packed FFMA2 (fma.rn.f32x2, two entries per
+//    instruction) + 2 funnel shifts per two pairs; each broadcast LDS.128 feeds four pairs (2 entries x 2 chains).
 //    Survivors (a few per ray) are queued per chain and, after the scan, evaluated with the reference's own
 //    double arithmetic, operation for operation, many lanes at a time, and compared with the reference's rule
 //    (distance > 0, strictly smaller, lowest scene index on ties). The FP32 stage can only discard pairs the
@@ -29,9 +29,18 @@
 
 namespace rtx {
 
-constexpr int kThreads = 512;         // 16 warps per SM, 4 per scheduler
+#ifndef RTX_THREADS
+#define RTX_THREADS 512
+#endif
+#ifndef RTX_PAIRS
+#define RTX_PAIRS 6
+#endif
+#ifndef RTX_ORDER
+#define RTX_ORDER 0
+#endif
+constexpr int kThreads = RTX_THREADS; // 16 warps per SM, 4 per scheduler
 constexpr int kChains = 2;            // pixels in flight per lane
-constexpr int kPairsPerIter = 4;      // sphere pairs (8 entries) per hot-loop iteration
+constexpr int kPairsPerIter = RTX_PAIRS;   // sphere pairs (8 entries) per hot-loop iteration
 constexpr int kQueue = 24;            // screen survivors buffered per chain before an early flush
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kMaxSmemBytes = 227 * 1024;
@@ -101,11 +110,13 @@ struct Chain {
     int queue[kQueue];  // entry indices that passed the FP32 screen
 };
 
-// Screen constants of one chain. Kept as scalars and widened with dup() at each use, so that ptxas emits the
-// FFMA2 operand form that broadcasts ONE 32-bit register to both halves (".F32") instead of reading a pair:
-// register-file bandwidth, not the FMA pipe, bounds the screen.
+// Screen constants of one chain: two unit axes u, v spanning the plane perpendicular to the ray, and -u.o, -v.o.
+// The squared distance from a centre c to the ray's line is (u.c - u.o)^2 + (v.c - v.o)^2.
+// Kept as scalars and widened with dup() at each use, so that ptxas emits the FFMA2 operand form that broadcasts
+// ONE 32-bit register to both halves (".F32") instead of reading a pair: register-file bandwidth, not the FMA
+// pipe, bounds the screen.
 struct Packed {
-    float dx, dy, dz, nkx, nky, nkz;
+    float ux, uy, uz, nuo, vx, vy, vz, nvo;
 };
 
 __device__ __forceinline__ float2 dup(float v) { return make_float2(v, v); }
@@ -125,8 +136,8 @@ __device__ __forceinline__ Packed setup_chain(Chain& c, float origin_bound)
     Packed k;
     if (!c.active) {
         // idle chain (only while the frame drains): m = -k is huge, nothing passes
-        k.dx = k.dy = k.dz = 0.f;
-        k.nkx = k.nky = k.nkz = 1e15f;
+        k.ux = k.uy = k.uz = k.vx = k.vy = k.vz = 0.f;
+        k.nuo = k.nvo = 1e15f;          // pu = pv = 1e15: nothing passes
         c.qn = 0;
         return k;
     }
@@ -137,24 +148,34 @@ __device__ __forceinline__ Packed setup_chain(Chain& c, float origin_bound)
     c.best_hi = __int_as_float(0x7f800000);
     c.qn = 0;
     const double inv = 1.0 / c.dlen;
-    const float fx = static_cast<float>(c.d.x * inv), fy = static_cast<float>(c.d.y * inv), fz = static_cast<float>(c.d.z * inv);
-    const double ux = fx, uy = fy, uz = fz;          // the ROUNDED direction: k must match what the FMAs see
-    const float kx = static_cast<float>(c.o.y * uz - c.o.z * uy);
-    const float ky = static_cast<float>(c.o.z * ux - c.o.x * uz);
-    const float kz = static_cast<float>(c.o.x * uy - c.o.y * ux);
+    const double hx = c.d.x * inv, hy = c.d.y * inv, hz = c.d.z * inv;      // d^ (plain double: not a parity value)
+    // u = normalize(d^ x e), e = the coordinate axis least aligned with d^; v = d^ x u
+    const double ax = fabs(hx), ay = fabs(hy), az = fabs(hz);
+    double ex = 0.0, ey = 0.0, ez = 0.0;
+    if (ax <= ay && ax <= az) ex = 1.0; else if (ay <= az) ey = 1.0; else ez = 1.0;
+    double ux = hy * ez - hz * ey, uy = hz * ex - hx * ez, uz = hx * ey - hy * ex;
+    const double un = rsqrt(ux * ux + uy * uy + uz * uz);
+    ux *= un; uy *= un; uz *= un;
+    const double vx = hy * uz - hz * uy, vy = hz * ux - hx * uz, vz = hx * uy - hy * ux;
+    // the FMAs see the ROUNDED axes: the offsets must be computed from those
+    const float fux = static_cast<float>(ux), fuy = static_cast<float>(uy), fuz = static_cast<float>(uz);
+    const float fvx = static_cast<float>(vx), fvy = static_cast<float>(vy), fvz = static_cast<float>(vz);
+    const float fx = static_cast<float>(hx), fy = static_cast<float>(hy), fz = static_cast<float>(hz);
     c.fdx = fx;
     c.fdy = fy;
     c.fdz = fz;
-    c.fd_o = static_cast<float>(ux * c.o.x + uy * c.o.y + uz * c.o.z);
+    c.fd_o = static_cast<float>(static_cast<double>(fx) * c.o.x + static_cast<double>(fy) * c.o.y + static_cast<double>(fz) * c.o.z);
     c.inv_dlen_lo = __double2float_rd(inv) * 0.999999f;
     const double om = fmax(fabs(c.o.x), fmax(fabs(c.o.y), fabs(c.o.z)));
     const bool ok = (om <= static_cast<double>(origin_bound)) && (c.dlen > 0.0) && (c.dlen < 1e300);
     if (ok) {
-        k.dx = fx; k.dy = fy; k.dz = fz;
-        k.nkx = -kx; k.nky = -ky; k.nkz = -kz;
+        k.ux = fux; k.uy = fuy; k.uz = fuz;
+        k.vx = fvx; k.vy = fvy; k.vz = fvz;
+        k.nuo = -static_cast<float>(static_cast<double>(fux) * c.o.x + static_cast<double>(fuy) * c.o.y + static_cast<double>(fuz) * c.o.z);
+        k.nvo = -static_cast<float>(static_cast<double>(fvx) * c.o.x + static_cast<double>(fvy) * c.o.y + static_cast<double>(fvz) * c.o.z);
     } else {
-        // m = 0 for every entry -> q - w = -w < 0 -> everything passes; NaN makes the second screen pass too
-        k.dx = k.dy = k.dz = k.nkx = k.nky = k.nkz = 0.f;
+        // pu = pv = 0 for every entry -> q - w = -w < 0 -> everything passes; NaN makes the second screen pass too
+        k.ux = k.uy = k.uz = k.vx = k.vy = k.vz = k.nuo = k.nvo = 0.f;
         c.fdx = c.fdy = c.fdz = c.fd_o = __int_as_float(0x7fc00000);
     }
     return k;
@@ -212,36 +233,41 @@ __device__ __forceinline__ float4 lds128(unsigned addr)
 
 // The packed screen of kPairsPerIter entry pairs against one chain; returns the sign history (one bit per entry,
 // first entry in the highest of the 2*kPairsPerIter low bits).
-//   m = c x d^ - o x d^   (squared length = squared distance from the centre to the ray's line),  q - w = |m|^2 - w
+//   pu = u.c - u.o,  pv = v.c - v.o,  q - w = pu^2 + pv^2 - w      8 FFMA2 per two entries
 // Written constant-major (the same per-ray constant through all pairs before the next constant): the FMA pipe
-// accepts one FFMA2 per two cycles only if the instruction reads at most four fresh registers; keeping the ray
-// constant in the operand-reuse cache across the run is what makes that true.
+// accepts one FFMA2 per two cycles only if the instruction reads at most four fresh registers.
 __device__ __forceinline__ unsigned screen_pairs(const float2 (&cx)[kPairsPerIter], const float2 (&cy)[kPairsPerIter],
                                                  const float2 (&cz)[kPairsPerIter], const float2 (&nw)[kPairsPerIter],
                                                  const Packed& k)
 {
-    float2 t[kPairsPerIter], mx[kPairsPerIter], my[kPairsPerIter], mz[kPairsPerIter], q[kPairsPerIter];
-    const float2 dx = dup(k.dx), dy = dup(k.dy), dz = dup(k.dz);
-    const float2 ndx = dup(-k.dx), ndy = dup(-k.dy), ndz = dup(-k.dz);
-    const float2 nkx = dup(k.nkx), nky = dup(k.nky), nkz = dup(k.nkz);
+    float2 pu[kPairsPerIter], pv[kPairsPerIter], q[kPairsPerIter];
+    const float2 ux = dup(k.ux), uy = dup(k.uy), uz = dup(k.uz), nuo = dup(k.nuo);
+    const float2 vx = dup(k.vx), vy = dup(k.vy), vz = dup(k.vz), nvo = dup(k.nvo);
+#if RTX_ORDER == 1
 #pragma unroll
-    for (int u = 0; u < kPairsPerIter; u++) t[u] = __ffma2_rn(cz[u], ndy, nkx);
+    for (int u = 0; u < kPairsPerIter; u++) {
+        pu[u] = __ffma2_rn(cx[u], ux, __ffma2_rn(cy[u], uy, __ffma2_rn(cz[u], uz, nuo)));
+        pv[u] = __ffma2_rn(cx[u], vx, __ffma2_rn(cy[u], vy, __ffma2_rn(cz[u], vz, nvo)));
+        q[u] = __ffma2_rn(pu[u], pu[u], __ffma2_rn(pv[u], pv[u], nw[u]));
+    }
+#else
 #pragma unroll
-    for (int u = 0; u < kPairsPerIter; u++) mx[u] = __ffma2_rn(cy[u], dz, t[u]);
+    for (int u = 0; u < kPairsPerIter; u++) pu[u] = __ffma2_rn(cz[u], uz, nuo);
 #pragma unroll
-    for (int u = 0; u < kPairsPerIter; u++) t[u] = __ffma2_rn(cx[u], ndz, nky);
+    for (int u = 0; u < kPairsPerIter; u++) pv[u] = __ffma2_rn(cz[u], vz, nvo);
 #pragma unroll
-    for (int u = 0; u < kPairsPerIter; u++) my[u] = __ffma2_rn(cz[u], dx, t[u]);
+    for (int u = 0; u < kPairsPerIter; u++) pu[u] = __ffma2_rn(cy[u], uy, pu[u]);
 #pragma unroll
-    for (int u = 0; u < kPairsPerIter; u++) t[u] = __ffma2_rn(cy[u], ndx, nkz);
+    for (int u = 0; u < kPairsPerIter; u++) pv[u] = __ffma2_rn(cy[u], vy, pv[u]);
 #pragma unroll
-    for (int u = 0; u < kPairsPerIter; u++) mz[u] = __ffma2_rn(cx[u], dy, t[u]);
+    for (int u = 0; u < kPairsPerIter; u++) pu[u] = __ffma2_rn(cx[u], ux, pu[u]);
 #pragma unroll
-    for (int u = 0; u < kPairsPerIter; u++) q[u] = __ffma2_rn(mz[u], mz[u], nw[u]);
+    for (int u = 0; u < kPairsPerIter; u++) pv[u] = __ffma2_rn(cx[u], vx, pv[u]);
 #pragma unroll
-    for (int u = 0; u < kPairsPerIter; u++) q[u] = __ffma2_rn(my[u], my[u], q[u]);
+    for (int u = 0; u < kPairsPerIter; u++) q[u] = __ffma2_rn(pv[u], pv[u], nw[u]);
 #pragma unroll
-    for (int u = 0; u < kPairsPerIter; u++) q[u] = __ffma2_rn(mx[u], mx[u], q[u]);
+    for (int u = 0; u < kPairsPerIter; u++) q[u] = __ffma2_rn(pu[u], pu[u], q[u]);
+#endif
     unsigned h = 0u;
 #pragma unroll
     for (int u = 0; u < kPairsPerIter; u++) {

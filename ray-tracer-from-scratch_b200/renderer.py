@@ -17,7 +17,8 @@ import numpy as np
 from . import abi, scene as scene_mod
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtx_b200.so")
+# RTX_B200_LIB lets a developer time an alternative build of the same library (tools/variants.sh)
+LIB_PATH = os.environ.get("RTX_B200_LIB") or os.path.join(_HERE, "librtx_b200.so")
 
 _lib = None
 
