@@ -176,7 +176,9 @@ void rtx_destroy(rtx_ctx* ctx);
 const char* rtx_last_error(const rtx_ctx* ctx);
 
 /* Use an externally owned cudaStream_t (passed as void*) for all work of this context, e.g. the
- * caller's current stream so that its own events bracket the kernels. NULL restores the private stream. */
+ * caller's current stream so that its own events bracket the kernels. NULL is CUDA's default stream (a valid
+ * stream handle); RTX_STREAM_PRIVATE restores the context's own non-blocking stream. */
+#define RTX_STREAM_PRIVATE ((void*)(intptr_t)-1)
 int rtx_set_stream(rtx_ctx* ctx, void* cuda_stream);
 
 /* Replaces the scene.push_back(...) sequence (main.cpp:156-163): copies n objects in scene order,

@@ -171,7 +171,7 @@ const char* rtx_last_error(const rtx_ctx* ctx) { return ctx ? ctx->error.c_str()
 int rtx_set_stream(rtx_ctx* ctx, void* cuda_stream)
 {
     if (!ctx) return RTX_ERR_INVALID;
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = cuda_stream == RTX_STREAM_PRIVATE ? ctx->own_stream : static_cast<cudaStream_t>(cuda_stream);
     return RTX_OK;
 }
 

@@ -163,8 +163,10 @@ class Renderer:
             raise RtxError(rc, (self.lib.rtx_last_error(self._ctx) or b"").decode())
 
     def set_stream(self, cuda_stream_handle):
-        """cuda_stream_handle: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or None."""
-        self._check(self.lib.rtx_set_stream(self._ctx, C.c_void_p(cuda_stream_handle or 0)))
+        """cuda_stream_handle: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream; 0 is CUDA's
+        default stream) or None for the context's private stream."""
+        h = C.c_void_p(-1) if cuda_stream_handle is None else C.c_void_p(int(cuda_stream_handle))
+        self._check(self.lib.rtx_set_stream(self._ctx, h))
 
     def set_scene(self, scene):
         """scene: list of scene.Sphere / scene.Wall in scene order, or a ctypes array of rtx_object."""
