@@ -154,6 +154,8 @@ typedef struct rtx_stats {
     double   max_luminance;      /* max over pixels of (R+G+B)/3; diagnostic only, never alters pixels */
     int32_t  launches;           /* kernels launched by the call */
     int32_t  reserved;
+    double   drain_ms;           /* trace kernel: from the pixel pool running empty to the last warp's exit */
+    double   exit_spread_ms;     /* trace kernel: first warp exit to last warp exit */
 } rtx_stats;
 
 typedef struct rtx_ctx rtx_ctx;

@@ -63,7 +63,8 @@ class Stats(C.Structure):
                 ("d2h_ms", C.c_double), ("total_ms", C.c_double),
                 ("total_rays", C.c_uint64), ("sphere_tests", C.c_uint64), ("wall_tests", C.c_uint64),
                 ("over_range_pixels", C.c_uint64), ("max_luminance", C.c_double),
-                ("launches", C.c_int32), ("reserved", C.c_int32)]
+                ("launches", C.c_int32), ("reserved", C.c_int32),
+                ("drain_ms", C.c_double), ("exit_spread_ms", C.c_double)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_ if not name.startswith("reserved")}

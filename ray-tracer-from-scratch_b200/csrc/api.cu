@@ -459,6 +459,7 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_cameras, ctx->h_cameras, sizeof(rtx_camera) * n_frames, cudaMemcpyHostToDevice, st));
     RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 4, 0xFF, 3 * sizeof(unsigned long long), st));   // atomicMin slots
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     RTX_CUDA(ctx, launch_trace(a, ctx->n_sms, st, &launches));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
@@ -493,6 +494,11 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
         long long bits = static_cast<long long>(ctx->h_counters[3]);
         std::memcpy(&stats->max_luminance, &bits, sizeof bits);
         stats->launches = launches;
+        const unsigned long long t0 = ctx->h_counters[4], dry = ctx->h_counters[5], first = ctx->h_counters[6], last = ctx->h_counters[7];
+        if (t0 != ~0ull && last >= t0) {
+            stats->drain_ms = (dry != ~0ull && last >= dry) ? (last - dry) * 1e-6 : 0.0;
+            stats->exit_spread_ms = (first != ~0ull && last >= first) ? (last - first) * 1e-6 : 0.0;
+        }
     }
     ctx->error.clear();
     return RTX_OK;

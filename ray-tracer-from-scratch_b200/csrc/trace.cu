@@ -326,6 +326,13 @@ __device__ __forceinline__ void fill_tile(float4* tile, const float4* __restrict
     }
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct FrameTotals {
     unsigned long long rays, over;
     double maxlum;
@@ -472,6 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
         ch[i].rays = 0;
     }
     FrameTotals tot{0ull, 0ull, 0.0};
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMin(&a.counters[4], globaltimer_ns());   // kernel start
 
     for (;;) {
         __syncwarp();
@@ -484,6 +492,8 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
             if (lane_id == 0) base = atomicAdd(&a.counters[0], static_cast<unsigned long long>(n0 + n1));
             base = __shfl_sync(kFull, base, 0);
             const unsigned below = (1u << lane_id) - 1u;
+            if (lane_id == 0 && base + n0 + n1 > total_pixels && base <= total_pixels)   // this fetch emptied the pool
+                atomicMin(&a.counters[5], globaltimer_ns());
             if (!ch[0].active) {
                 const unsigned long long p = base + __popc(idle0 & below);
                 if (p < total_pixels) start_pixel(ch[0], p, a);
@@ -525,6 +535,11 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
 
     // ---- diagnostics: warp-shuffle reduction, one atomic per warp (never alters a pixel) ----------------------
     __syncwarp();
+    if (lane_id == 0) {   // drain profile: when the first and the last warp ran out of work
+        const unsigned long long now = globaltimer_ns();
+        atomicMin(&a.counters[6], now);
+        atomicMax(&a.counters[7], now);
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         tot.rays += __shfl_down_sync(kFull, tot.rays, off);
