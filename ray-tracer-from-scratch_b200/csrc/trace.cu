@@ -42,6 +42,16 @@ constexpr int kThreads = RTX_THREADS; // 16 warps per SM, 4 per scheduler
 constexpr int kChains = 2;            // pixels in flight per lane
 constexpr int kPairsPerIter = RTX_PAIRS;   // sphere pairs (8 entries) per hot-loop iteration
 constexpr int kQueue = 24;            // screen survivors buffered per chain before an early flush
+#ifndef RTX_COOP_MAX
+#define RTX_COOP_MAX 32
+#endif
+constexpr int kCoopMax = RTX_COOP_MAX;   // cooperative drain when a warp has at most this many live chains (0 = off)
+constexpr int kMboxCap = 96;          // cooperative drain: survivors one chain may receive per scan
+constexpr int kWarps = kThreads / 32;
+struct Mailbox {                      // one per warp, in shared memory behind the entry tile
+    int count[2];
+    int items[2][kMboxCap];
+};
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kMaxSmemBytes = 227 * 1024;
 
@@ -106,6 +116,7 @@ struct Chain {
     int first_id;       // primary hit id
     int rays;
     int active;
+    int fallback;       // 1: origin outside the error bound's assumption -> every entry goes to the exact test
     int qn;
     int queue[kQueue];  // entry indices that passed the FP32 screen
 };
@@ -139,6 +150,7 @@ __device__ __forceinline__ Packed setup_chain(Chain& c, float origin_bound)
         k.ux = k.uy = k.uz = k.vx = k.vy = k.vz = 0.f;
         k.nuo = k.nvo = 1e15f;          // pu = pv = 1e15: nothing passes
         c.qn = 0;
+        c.fallback = 0;
         return k;
     }
     c.a_dd = ex::len2(c.d);
@@ -168,6 +180,7 @@ __device__ __forceinline__ Packed setup_chain(Chain& c, float origin_bound)
     c.inv_dlen_lo = __double2float_rd(inv) * 0.999999f;
     const double om = fmax(fabs(c.o.x), fmax(fabs(c.o.y), fabs(c.o.z)));
     const bool ok = (om <= static_cast<double>(origin_bound)) && (c.dlen > 0.0) && (c.dlen < 1e300);
+    c.fallback = ok ? 0 : 1;
     if (ok) {
         k.ux = fux; k.uy = fuy; k.uz = fuz;
         k.vx = fvx; k.vy = fvy; k.vz = fvz;
@@ -310,6 +323,81 @@ __device__ __forceinline__ void scan_tile(unsigned tile_addr, int n_pairs, int b
             }
         }
     }
+}
+
+// ---- cooperative drain ---------------------------------------------------------------------------------------------
+// When the pixel pool is empty the frame is finished by the chains still in flight, and a late chain needs up to
+// `depth` more scans: scanning all N entries per lane then leaves a constant tail (measured 3.8 ms on B200,
+// DESIGN.md §3.6). In this mode the warp takes its live chains two at a time, broadcasts their screen constants,
+// and its 32 lanes split the entry array (lane l screens pairs l, l+32, ...). Survivors are posted to the owner
+// through a per-warp shared-memory mailbox and then go through the same queue / exact path as always, so results
+// are unchanged (the acceptance rule is order independent).
+__device__ __forceinline__ float2 screen_one(const float4 p0, const float4 p1, const Packed& k)
+{
+    const float2 cx = make_float2(p0.x, p0.y), cy = make_float2(p0.z, p0.w);
+    const float2 cz = make_float2(p1.x, p1.y), nw = make_float2(p1.z, p1.w);
+    const float2 pu = __ffma2_rn(cx, dup(k.ux), __ffma2_rn(cy, dup(k.uy), __ffma2_rn(cz, dup(k.uz), dup(k.nuo))));
+    const float2 pv = __ffma2_rn(cx, dup(k.vx), __ffma2_rn(cy, dup(k.vy), __ffma2_rn(cz, dup(k.vz), dup(k.nvo))));
+    return __ffma2_rn(pu, pu, __ffma2_rn(pv, pv, nw));
+}
+
+__device__ __forceinline__ void post(Mailbox* mb, int which, int entry)
+{
+    const int slot = atomicAdd(&mb->count[which], 1);
+    if (slot < kMboxCap) mb->items[which][slot] = entry;
+}
+
+__device__ __forceinline__ Packed bcast(const Packed& k, int src)
+{
+    Packed r;
+    r.ux = __shfl_sync(kFull, k.ux, src); r.uy = __shfl_sync(kFull, k.uy, src); r.uz = __shfl_sync(kFull, k.uz, src);
+    r.nuo = __shfl_sync(kFull, k.nuo, src);
+    r.vx = __shfl_sync(kFull, k.vx, src); r.vy = __shfl_sync(kFull, k.vy, src); r.vz = __shfl_sync(kFull, k.vz, src);
+    r.nvo = __shfl_sync(kFull, k.nvo, src);
+    return r;
+}
+
+__device__ __forceinline__ void coop_scan(unsigned tile_addr, int total_pairs, const Packed& ka, const Packed& kb, Mailbox* mb,
+                                          unsigned lane)
+{
+    constexpr int kStep = 2;   // pairs per lane per iteration
+#pragma unroll 1
+    for (int pair = lane; pair < total_pairs; pair += 32 * kStep) {
+        float4 p0[kStep], p1[kStep];
+#pragma unroll
+        for (int u = 0; u < kStep; u++) {
+            const int p = pair + 32 * u;
+            if (p < total_pairs) {
+                p0[u] = lds128(tile_addr + p * 32u);
+                p1[u] = lds128(tile_addr + p * 32u + 16u);
+            } else {
+                p0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                p1[u] = make_float4(0.f, 0.f, 1.f, 1.f);   // -w = +1: never passes
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kStep; u++) {
+            const float2 qa = screen_one(p0[u], p1[u], ka);
+            const float2 qb = screen_one(p0[u], p1[u], kb);
+            const unsigned any = __float_as_uint(qa.x) | __float_as_uint(qa.y) | __float_as_uint(qb.x) | __float_as_uint(qb.y);
+            if (any & 0x80000000u) {
+                const int e = 2 * (pair + 32 * u);
+                if (__float_as_uint(qa.x) & 0x80000000u) post(mb, 0, e);
+                if (__float_as_uint(qa.y) & 0x80000000u) post(mb, 0, e + 1);
+                if (__float_as_uint(qb.x) & 0x80000000u) post(mb, 1, e);
+                if (__float_as_uint(qb.y) & 0x80000000u) post(mb, 1, e + 1);
+            }
+        }
+    }
+}
+
+// Pops the next live chain: lowest lane of the first-chain mask, then of the second-chain mask.
+__device__ __forceinline__ bool pop_chain(unsigned& r0, unsigned& r1, int& src, int& which)
+{
+    if (r0) { src = __ffs(r0) - 1; r0 &= r0 - 1; which = 0; return true; }
+    if (r1) { src = __ffs(r1) - 1; r1 &= r1 - 1; which = 1; return true; }
+    src = 0; which = 0;
+    return false;
 }
 
 // Cooperative tile fill: entries (cx, cy, cz, r) -> pair-interleaved (cx_a,cx_b,cy_a,cy_b)(cz_a,cz_b,-w_a,-w_b),
@@ -479,6 +567,8 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
         ch[i].rays = 0;
     }
     FrameTotals tot{0ull, 0ull, 0.0};
+    bool pool_dry = false;             // warp-uniform: a fetch of this warp found the pixel pool empty
+    Mailbox* const mbox = reinterpret_cast<Mailbox*>(s_tile + (STREAM ? 2 * tile_pairs : sc.n_entries_padded)) + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicMin(&a.counters[4], globaltimer_ns());   // kernel start
 
     for (;;) {
@@ -492,6 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
             if (lane_id == 0) base = atomicAdd(&a.counters[0], static_cast<unsigned long long>(n0 + n1));
             base = __shfl_sync(kFull, base, 0);
             const unsigned below = (1u << lane_id) - 1u;
+            if (base + n0 + n1 > total_pixels) pool_dry = true;
             if (lane_id == 0 && base + n0 + n1 > total_pixels && base <= total_pixels)   // this fetch emptied the pool
                 atomicMin(&a.counters[5], globaltimer_ns());
             if (!ch[0].active) {
@@ -523,7 +614,51 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
                 scan_tile(tile_addr, count, 2 * first_pair, k0, k1, ch[0], ch[1], sc, a.filter_eps);
             }
         } else {
-            scan_tile(tile_addr, total_pairs, 0, k0, k1, ch[0], ch[1], sc, a.filter_eps);
+            const unsigned m0 = __ballot_sync(kFull, ch[0].active), m1 = __ballot_sync(kFull, ch[1].active);
+            bool coop = kCoopMax > 0 && pool_dry && (__popc(m0) + __popc(m1)) <= kCoopMax;
+            if (coop) coop = !__any_sync(kFull, (ch[0].active && ch[0].fallback) || (ch[1].active && ch[1].fallback));
+            if (coop) {
+                unsigned r0 = m0, r1 = m1;
+                bool overflow = false;
+                int src_a, which_a, src_b, which_b;
+                while (pop_chain(r0, r1, src_a, which_a)) {
+                    const bool have_b = pop_chain(r0, r1, src_b, which_b);
+                    const Packed ka = bcast(which_a ? k1 : k0, src_a);
+                    Packed kb = bcast(which_b ? k1 : k0, src_b);
+                    if (!have_b) {
+                        kb.ux = kb.uy = kb.uz = kb.vx = kb.vy = kb.vz = 0.f;
+                        kb.nuo = kb.nvo = 1e15f;
+                    }
+                    if (lane_id == 0) mbox->count[0] = mbox->count[1] = 0;
+                    __syncwarp();
+                    coop_scan(tile_addr, total_pairs, ka, kb, mbox, lane_id);
+                    __syncwarp();
+                    if (static_cast<int>(lane_id) == src_a) {
+                        const int n = mbox->count[0];
+                        if (n > kMboxCap) overflow = true;
+                        for (int i = 0; i < min(n, kMboxCap); i++) {
+                            if (which_a) enqueue(ch[1], mbox->items[0][i], sc, a.filter_eps);
+                            else enqueue(ch[0], mbox->items[0][i], sc, a.filter_eps);
+                        }
+                    }
+                    if (have_b && static_cast<int>(lane_id) == src_b) {
+                        const int n = mbox->count[1];
+                        if (n > kMboxCap) overflow = true;
+                        for (int i = 0; i < min(n, kMboxCap); i++) {
+                            if (which_b) enqueue(ch[1], mbox->items[1][i], sc, a.filter_eps);
+                            else enqueue(ch[0], mbox->items[1][i], sc, a.filter_eps);
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (__any_sync(kFull, overflow)) {   // a mailbox overflowed: redo this segment the ordinary way
+                    ch[0].qn = ch[1].qn = 0;
+                    if (ch[0].active) { ch[0].best_dist = 1.7976931348623157e308; ch[0].best_id = -1; ch[0].best_hi = __int_as_float(0x7f800000); }
+                    if (ch[1].active) { ch[1].best_dist = 1.7976931348623157e308; ch[1].best_id = -1; ch[1].best_hi = __int_as_float(0x7f800000); }
+                    coop = false;
+                }
+            }
+            if (!coop) scan_tile(tile_addr, total_pairs, 0, k0, k1, ch[0], ch[1], sc, a.filter_eps);
         }
         drain_queue(ch[0], sc, a.filter_eps);
         drain_queue(ch[1], sc, a.filter_eps);
@@ -557,10 +692,12 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
 cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, int* launches)
 {
     constexpr int iter_bytes = kPairsPerIter * 32;
+    const size_t mbox_bytes = sizeof(Mailbox) * kWarps;
     const size_t need = static_cast<size_t>(args.scene.n_entries_padded) * sizeof(float4);
-    const bool stream_tiles = need > static_cast<size_t>(kMaxSmemBytes);
-    const size_t smem = stream_tiles ? static_cast<size_t>(kMaxSmemBytes) / iter_bytes * iter_bytes : (need ? need : iter_bytes);
-    const int tile_pairs = static_cast<int>(smem / 32);
+    const bool stream_tiles = need + mbox_bytes > static_cast<size_t>(kMaxSmemBytes);
+    const size_t tile_bytes = stream_tiles ? (static_cast<size_t>(kMaxSmemBytes) - mbox_bytes) / iter_bytes * iter_bytes : (need ? need : iter_bytes);
+    const int tile_pairs = static_cast<int>(tile_bytes / 32);
+    const size_t smem = tile_bytes + mbox_bytes;
     const unsigned long long total =
         static_cast<unsigned long long>(args.n_frames) * static_cast<unsigned long long>(args.local_rows) * args.width;
     if (total == 0) return cudaSuccess;
