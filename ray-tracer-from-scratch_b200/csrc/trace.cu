@@ -46,7 +46,10 @@ constexpr int kQueue = 24;            // screen survivors buffered per chain bef
 #define RTX_COOP_MAX 32
 #endif
 constexpr int kCoopMax = RTX_COOP_MAX;   // cooperative drain when a warp has at most this many live chains (0 = off)
-constexpr int kMboxCap = 96;          // cooperative drain: survivors one chain may receive per scan
+#ifndef RTX_MBOX_CAP
+#define RTX_MBOX_CAP 96
+#endif
+constexpr int kMboxCap = RTX_MBOX_CAP;   // cooperative drain: survivors one chain may receive per scan
 constexpr int kWarps = kThreads / 32;
 struct Mailbox {                      // one per warp, in shared memory behind the entry tile
     int count[2];

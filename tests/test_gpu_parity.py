@@ -6,6 +6,7 @@ identical — the kernel takes every hit decision in the reference's own double 
 libm-vs-CUDA pow (<= 2 ulp) and the front-to-back accumulation order of the reflection lerp.
 """
 import hashlib
+import sys
 
 import numpy as np
 import pytest
@@ -286,3 +287,49 @@ def test_cpp_headless_main_matches_reference_main_loop(tmp_path, port, S, render
     assert np.array_equal(got, exp)
     data = open(ppm, "rb").read()
     assert data.startswith(b"P6\n320 320\n255\n") and len(data) == 15 + 320 * 320 * 3
+
+
+def test_scene_larger_than_shared_memory_streams_tiles(gpu, renderer_mod, port, S):
+    """More entries than fit the 227 KB shared-memory tile (~13.8k): the kernel streams tiles through the same
+    buffer in a CTA-synchronous loop (template STREAM). Same parity bar."""
+    scene = S.synthetic_scene(16000, 40, seed=0x51)
+    pod = S.default_camera(48, 16.0 / 9.0).pod()
+    got, st = render(gpu, renderer_mod, scene, pod, 4)
+    check_frame(got, port.render(scene, pod, 4), st)
+    assert st.sphere_tests == st.total_rays * 16000
+
+
+def test_cooperative_drain_mailbox_overflow_redoes_the_segment(tmp_path, renderer_mod, port, S):
+    """The cooperative drain posts screen survivors through a fixed-size mailbox; if it overflows the segment is
+    redone the ordinary way. Build the library with a 1-slot mailbox to force that path and check parity."""
+    import os
+    import subprocess
+    pkg_dir = os.path.dirname(os.path.abspath(renderer_mod.__file__))
+    root = os.path.dirname(pkg_dir)
+    lib = str(tmp_path / "librtx_b200_mbox1.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off",
+                    "-DRTX_MBOX_CAP=1", "-I" + os.path.join(root, "include"), "-I" + os.path.join(pkg_dir, "csrc"), "-shared",
+                    os.path.join(pkg_dir, "csrc", "api.cu"), os.path.join(pkg_dir, "csrc", "trace.cu"),
+                    os.path.join(pkg_dir, "csrc", "aux_kernels.cu"), "-o", lib], check=True)
+    code = r"""
+import importlib, os, sys
+import numpy as np
+sys.path.insert(0, %r)
+R = importlib.import_module("ray-tracer-from-scratch_b200.renderer")
+S = importlib.import_module("ray-tracer-from-scratch_b200").scene
+from oracle import binding as ob
+port = ob.load_port()
+scene = S.synthetic_scene(3000, 24, seed=9)
+pod = S.default_camera(96, 16.0 / 9.0).pod()
+r = R.Renderer(0)
+r.set_scene(scene)
+got, st = r.render([pod], R.default_params(max_depth=10), want=("rgba8", "object_id", "ray_count"))
+exp = port.render(scene, pod, 10)
+assert np.array_equal(got["rgba8"][0], exp["rgba8"]) and np.array_equal(got["object_id"][0], exp["object_id"])
+assert np.array_equal(got["ray_count"][0], exp["ray_count"]) and st.total_rays == exp["total_rays"]
+print("ok")
+""" % root
+    env = dict(os.environ, RTX_B200_LIB=lib)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
