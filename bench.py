@@ -294,6 +294,8 @@ def main():
     frame_bytes = H * W * 4 * len(pods)
     host_frame = torch.empty((len(pods), H, W), dtype=torch.int32, pin_memory=True) if rank == 0 else None
 
+    drain = []
+
     def step(e2e):
         """One step. Returns (rays on this rank, kernel ms, launches)."""
         if e2e:
@@ -316,6 +318,8 @@ def main():
                 o.memory, o.rgba8 = abi.RTX_MEM_DEVICE, dev_frame.data_ptr()
             st = r.render_raw(pods, R.default_params(max_depth=spec["depth"]), o)
             launches = st.launches
+        if st:
+            drain.append(st.drain_ms)
         return (st.total_rays if st else 0), (st.raytracing_ms if st else 0.0), launches
 
     dev_frame = torch.empty((len(pods), H, W), dtype=torch.int32, device=dev) if world == 1 and spec["name"] != "c5" else None
@@ -368,10 +372,12 @@ def main():
         achieved = flops_per_step / world / (kernel_ms / args.steps * 1e-3) / 1e12
         ffma2, _ = r.ffma_peak(1)
         ffma1, _ = r.ffma_peak(0)
-        traffic = None
+        traffic = traffic_note = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(spec["name"])
+            t = json.load(open(tp)).get(spec["name"])
+            if t:
+                traffic, traffic_note = t["dram_bytes_per_launch"], t.get("note")
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -384,8 +390,9 @@ def main():
                        "mpixel_per_s": H * W * len(pods) / (ms / args.steps * 1e-3) / 1e6,
                        "l2": "256 MiB written between steps (L2 flush), outside the per-step CUDA events"},
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "rtx::trace_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
+                         "traffic": traffic, "traffic_note": traffic_note, "kernel": "rtx::trace_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
                          "algorithmic_flop_per_step": flops_per_step, "peak_source": peak_src,
+                         "drain_ms_per_step_rank0": sum(drain) / max(1, len(drain)),
                          "peak_measured_ffma2_tflops": ffma2, "peak_measured_ffma_scalar_tflops": ffma1,
                          "frac_of_measured_ffma2": achieved / ffma2 if ffma2 else None,
                          "hbm_write_gbs": frame_bytes / world / (kernel_ms / args.steps * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak_gbs()[0]},
