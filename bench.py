@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--band-rows", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "allgather"],
+                    help="N > 1: peer-memory stores from the trace kernel (fused) or all-gather + unpermute")
     ap.add_argument("--scale", type=float, default=1.0, help="developer knob: shrink the frame (not a valid bench)")
     return ap.parse_args()
 
@@ -286,7 +288,7 @@ def main():
     r = R.Renderer(local_rank)
     r.set_stream(torch.cuda.current_stream().cuda_stream)     # torch events then bracket our kernels
     r.set_scene(objs)
-    sh = SH.ShardedRenderer(r, rank, world, band_rows=args.band_rows)
+    sh = SH.ShardedRenderer(r, rank, world, band_rows=args.band_rows, fused=args.gather == "fused")
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=dev)
 
     import ctypes
@@ -384,8 +386,9 @@ def main():
             "vs_baseline": None, "dtype": "f32 screen + f64 decisions/shading", "data": "synthetic",
             "config": {"workload": spec["label"], "width": W, "height": H, "frames_per_step": len(pods), "depth": spec["depth"],
                        "n_spheres": n_spheres, "n_walls": n_walls, "band_rows": args.band_rows if world > 1 else None,
-                       "parallelism": "1 process per GPU; cyclic row bands + NCCL all-gather to rank 0" if world > 1 and spec["name"] != "c5"
-                       else ("frames sharded over ranks + NCCL all-gather" if world > 1 else "single GPU"),
+                       "parallelism": ("1 process per GPU; " + ("cyclic row bands" if spec["name"] != "c5" else "frames sharded over ranks") +
+                                       ("; pixels stored into rank 0's frame over NVLink peer memory by the trace kernel + 1 barrier"
+                                        if args.gather == "fused" else "; NCCL all-gather to rank 0 + unpermute")) if world > 1 else "single GPU",
                        "rays_per_step": rays_per_step, "ms_per_frame": ms / args.steps / len(pods),
                        "mpixel_per_s": H * W * len(pods) / (ms / args.steps * 1e-3) / 1e6,
                        "l2": "256 MiB written between steps (L2 flush), outside the per-step CUDA events"},
@@ -407,6 +410,7 @@ def main():
             except Exception as e:  # the oracle is optional equipment; say why it is missing
                 line["cpu_baseline"] = {"unavailable": repr(e)}
         print(json.dumps(line), flush=True)
+    sh.close()
     r.close()
     if world > 1:
         dist.destroy_process_group()

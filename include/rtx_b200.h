@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RTX_ABI_VERSION 1
+#define RTX_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------- */
 #define RTX_OK              0
@@ -118,6 +118,10 @@ typedef struct rtx_params {
     int32_t  n_ranks;
     int32_t  rank;
     int32_t  reserved2;
+    /* Camera paths sharded by frame: camera k of this call is frame (frame_offset + k * frame_stride) of the whole
+     * path. Only used to place pixels in rtx_outputs.frame_rgba8. Defaults 0, 1. */
+    int32_t  frame_offset;
+    int32_t  frame_stride;
 } rtx_params;
 
 #define RTX_MAX_DEPTH 254     /* ray_count is a uint8: depth+1 rays per pixel at most */
@@ -137,6 +141,12 @@ typedef struct rtx_outputs {
     uint8_t*  ray_count;     /* rays traced for the pixel (primary + reflections), 1..max_depth+1 */
     int32_t   memory;        /* RTX_MEM_HOST | RTX_MEM_DEVICE */
     int32_t   reserved;
+    /* Fused multi-GPU gather: a DEVICE pointer (regardless of `memory`) to a whole row-major frame set
+     * [total_frames][height][width] of RGBA8888 words, typically rank 0's buffer mapped into this process with
+     * rtx_buffer_import (peer memory over NVLink). The trace kernel stores every finished pixel at its GLOBAL
+     * position (global row from the band map, global frame from frame_offset/frame_stride), so no all-gather and
+     * no unpermute pass is needed: a barrier after the call completes the frame. NULL = not wanted. */
+    uint32_t* frame_rgba8;
 } rtx_outputs;
 
 /* Device-side timing and diagnostics of the last rtx_render / rtx_quantise on a context.
@@ -217,6 +227,16 @@ int rtx_quantise(rtx_ctx* ctx, const float* radiance_f32, const double* radiance
  * elem_bytes in {1,4}. rows_per_rank must be >= every rank's rtx_local_rows(). */
 int rtx_unpermute_bands(rtx_ctx* ctx, const void* band_major, void* row_major, int32_t height, int32_t width,
                         int32_t elem_bytes, int32_t band_rows, int32_t n_ranks, int32_t rows_per_rank);
+
+/* Device buffers that can be shared between the per-GPU processes of one box (CUDA IPC): rank 0 allocates the
+ * frame and exports a 64-byte handle, the other ranks import it and pass the mapped pointer as
+ * rtx_outputs.frame_rgba8. Import enables peer access (NVLink) lazily. */
+#define RTX_IPC_HANDLE_BYTES 64
+int rtx_buffer_alloc(rtx_ctx* ctx, uint64_t bytes, void** device_ptr);
+int rtx_buffer_free(rtx_ctx* ctx, void* device_ptr);
+int rtx_buffer_export(rtx_ctx* ctx, void* device_ptr, uint8_t handle[RTX_IPC_HANDLE_BYTES]);
+int rtx_buffer_import(rtx_ctx* ctx, const uint8_t handle[RTX_IPC_HANDLE_BYTES], void** device_ptr);
+int rtx_buffer_release(rtx_ctx* ctx, void* imported_ptr);
 
 /* FP32 FFMA throughput microbenchmark (the roofline denominator has no entry in MEASURED_PEAKS.json):
  * returns achieved TFLOP/s of a dependent-chain-free FFMA loop over the whole chip. variant 0 = scalar

@@ -239,6 +239,8 @@ void orc_default_params(rtx_params* p)
     p->band_rows = 4;
     p->n_ranks = 1;
     p->rank = 0;
+    p->frame_offset = 0;
+    p->frame_stride = 1;
 }
 
 int orc_abi_version(void) { return RTX_ABI_VERSION; }

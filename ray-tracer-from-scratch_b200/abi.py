@@ -5,7 +5,7 @@ the reference code (file:line) every field stands for.
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 RTX_OK, RTX_ERR_INVALID, RTX_ERR_CUDA, RTX_ERR_NO_SCENE, RTX_ERR_NOMEM = 0, 1, 2, 3, 4
 RTX_SPHERE, RTX_WALL = 0, 1
@@ -49,13 +49,14 @@ class Params(C.Structure):
                 ("reserved", C.c_int32),
                 ("light_pos", Vec3), ("ground_color", Vec3), ("sky_low", Vec3), ("sky_high", Vec3),
                 ("reflect_offset", C.c_double), ("sky_exponent", C.c_double),
-                ("band_rows", C.c_int32), ("n_ranks", C.c_int32), ("rank", C.c_int32), ("reserved2", C.c_int32)]
+                ("band_rows", C.c_int32), ("n_ranks", C.c_int32), ("rank", C.c_int32), ("reserved2", C.c_int32),
+                ("frame_offset", C.c_int32), ("frame_stride", C.c_int32)]
 
 
 class Outputs(C.Structure):
     _fields_ = [("rgba8", C.c_void_p), ("radiance_f32", C.c_void_p), ("radiance_f64", C.c_void_p),
                 ("object_id", C.c_void_p), ("hit_mask", C.c_void_p), ("ray_count", C.c_void_p),
-                ("memory", C.c_int32), ("reserved", C.c_int32)]
+                ("memory", C.c_int32), ("reserved", C.c_int32), ("frame_rgba8", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -75,4 +76,5 @@ EXPORTS = (
     "rtx_abi_version", "rtx_status_string", "rtx_create", "rtx_destroy", "rtx_last_error", "rtx_set_stream",
     "rtx_set_scene", "rtx_camera_init", "rtx_default_params", "rtx_local_rows", "rtx_global_row",
     "rtx_render", "rtx_quantise", "rtx_unpermute_bands", "rtx_ffma_peak",
+    "rtx_buffer_alloc", "rtx_buffer_free", "rtx_buffer_export", "rtx_buffer_import", "rtx_buffer_release",
 )

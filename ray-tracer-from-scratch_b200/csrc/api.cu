@@ -331,6 +331,8 @@ void rtx_default_params(rtx_params* p)
     p->band_rows = 4;
     p->n_ranks = 1;
     p->rank = 0;
+    p->frame_offset = 0;
+    p->frame_stride = 1;
 }
 
 int32_t rtx_local_rows(int32_t height, int32_t band_rows, int32_t n_ranks, int32_t rank)
@@ -409,7 +411,9 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
             dev[k] = user[k];
         }
     }
-    const bool unfused = !p.fuse_quantise && user[0];
+    if (outs->frame_rgba8 && (p.frame_stride < 1 || p.frame_offset < 0))
+        return fail(ctx, RTX_ERR_INVALID, "rtx_render: frame_offset/frame_stride must be >= 0 / >= 1");
+    const bool unfused = !p.fuse_quantise && user[0] && !outs->frame_rgba8;
     double* rad_for_quant = nullptr;
     if (unfused) {
         if (dev[2]) {
@@ -453,6 +457,9 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
     a.object_id = static_cast<int32_t*>(dev[3]);
     a.hit_mask = static_cast<uint8_t*>(dev[4]);
     a.ray_count = static_cast<uint8_t*>(dev[5]);
+    a.frame_rgba8 = outs->frame_rgba8;
+    a.frame_offset = p.frame_offset;
+    a.frame_stride = p.frame_stride;
     a.counters = ctx->d_counters;
 
     int launches = 0;
@@ -570,6 +577,52 @@ int rtx_unpermute_bands(rtx_ctx* ctx, const void* band_major, void* row_major, i
     RTX_CUDA(ctx, launch_unpermute(band_major, row_major, height, width, elem_bytes, band_rows, n_ranks, rows_per_rank, ctx->stream));
     RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->error.clear();
+    return RTX_OK;
+}
+
+int rtx_buffer_alloc(rtx_ctx* ctx, uint64_t bytes, void** device_ptr)
+{
+    if (!ctx || !device_ptr || bytes == 0) return fail(ctx, RTX_ERR_INVALID, "rtx_buffer_alloc: bad argument");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(device_ptr, bytes);
+    if (e != cudaSuccess) return fail(ctx, RTX_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return RTX_OK;
+}
+
+int rtx_buffer_free(rtx_ctx* ctx, void* device_ptr)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    RTX_CUDA(ctx, cudaFree(device_ptr));
+    return RTX_OK;
+}
+
+int rtx_buffer_export(rtx_ctx* ctx, void* device_ptr, uint8_t handle[RTX_IPC_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == RTX_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!ctx || !device_ptr || !handle) return fail(ctx, RTX_ERR_INVALID, "rtx_buffer_export: bad argument");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    RTX_CUDA(ctx, cudaIpcGetMemHandle(&h, device_ptr));
+    std::memcpy(handle, &h, sizeof h);
+    return RTX_OK;
+}
+
+int rtx_buffer_import(rtx_ctx* ctx, const uint8_t handle[RTX_IPC_HANDLE_BYTES], void** device_ptr)
+{
+    if (!ctx || !device_ptr || !handle) return fail(ctx, RTX_ERR_INVALID, "rtx_buffer_import: bad argument");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    RTX_CUDA(ctx, cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RTX_OK;
+}
+
+int rtx_buffer_release(rtx_ctx* ctx, void* imported_ptr)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    RTX_CUDA(ctx, cudaIpcCloseMemHandle(imported_ptr));
     return RTX_OK;
 }
 

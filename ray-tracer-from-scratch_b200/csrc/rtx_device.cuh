@@ -105,6 +105,8 @@ struct TraceArgs {
     int32_t* object_id;
     uint8_t* hit_mask;
     uint8_t* ray_count;
+    uint32_t* frame_rgba8;             // whole row-major frame set, possibly peer memory (fused gather); may be null
+    int32_t frame_offset, frame_stride;
     // counters: [0] next pixel, [1] total rays, [2] over-range pixels, [3] max luminance (double bits),
     // [4] kernel start, [5] pixel pool empty, [6] first warp exit, [7] last warp exit (globaltimer ns; [4..6] start at ~0)
     unsigned long long* counters;

@@ -293,6 +293,40 @@ __device__ __forceinline__ unsigned screen_pairs(const float2 (&cx)[kPairsPerIte
     return h;
 }
 
+// Both chains at once, entry-operand-major: the four FFMA2 that consume the same entry pair component (u and v
+// axis of chain 0, u and v axis of chain 1) are adjacent, so the pair stays in the operand-reuse cache and each
+// instruction reads at most three fresh registers.
+__device__ __forceinline__ void screen_both(const float2 (&cx)[kPairsPerIter], const float2 (&cy)[kPairsPerIter],
+                                            const float2 (&cz)[kPairsPerIter], const float2 (&nw)[kPairsPerIter],
+                                            const Packed& k0, const Packed& k1, unsigned& h0, unsigned& h1)
+{
+    h0 = 0u;
+    h1 = 0u;
+#pragma unroll
+    for (int u = 0; u < kPairsPerIter; u++) {
+        float2 pu0 = __ffma2_rn(cz[u], dup(k0.uz), dup(k0.nuo));
+        float2 pv0 = __ffma2_rn(cz[u], dup(k0.vz), dup(k0.nvo));
+        float2 pu1 = __ffma2_rn(cz[u], dup(k1.uz), dup(k1.nuo));
+        float2 pv1 = __ffma2_rn(cz[u], dup(k1.vz), dup(k1.nvo));
+        pu0 = __ffma2_rn(cy[u], dup(k0.uy), pu0);
+        pv0 = __ffma2_rn(cy[u], dup(k0.vy), pv0);
+        pu1 = __ffma2_rn(cy[u], dup(k1.uy), pu1);
+        pv1 = __ffma2_rn(cy[u], dup(k1.vy), pv1);
+        pu0 = __ffma2_rn(cx[u], dup(k0.ux), pu0);
+        pv0 = __ffma2_rn(cx[u], dup(k0.vx), pv0);
+        pu1 = __ffma2_rn(cx[u], dup(k1.ux), pu1);
+        pv1 = __ffma2_rn(cx[u], dup(k1.vx), pv1);
+        float2 q0 = __ffma2_rn(pv0, pv0, nw[u]);
+        float2 q1 = __ffma2_rn(pv1, pv1, nw[u]);
+        q0 = __ffma2_rn(pu0, pu0, q0);
+        q1 = __ffma2_rn(pu1, pu1, q1);
+        h0 = __funnelshift_l(__float_as_uint(q0.x), h0, 1);
+        h0 = __funnelshift_l(__float_as_uint(q0.y), h0, 1);
+        h1 = __funnelshift_l(__float_as_uint(q1.x), h1, 1);
+        h1 = __funnelshift_l(__float_as_uint(q1.y), h1, 1);
+    }
+}
+
 // The O(N) scan over one shared-memory tile: n_pairs entry pairs starting at entry index `base`.
 __device__ __forceinline__ void scan_tile(unsigned tile_addr, int n_pairs, int base, const Packed& k0, const Packed& k1,
                                           Chain& c0, Chain& c1, const SceneDev& sc, float eps)
@@ -311,8 +345,13 @@ __device__ __forceinline__ void scan_tile(unsigned tile_addr, int n_pairs, int b
             cz[u] = make_float2(p1.x, p1.y);
             nw[u] = make_float2(p1.z, p1.w);
         }
+#if RTX_ORDER == 2
+        unsigned h0, h1;                                  // sign history: bit set = q - w < 0 = survivor
+        screen_both(cx, cy, cz, nw, k0, k1, h0, h1);
+#else
         unsigned h0 = screen_pairs(cx, cy, cz, nw, k0);   // sign history: bit set = q - w < 0 = survivor
         unsigned h1 = screen_pairs(cx, cy, cz, nw, k1);
+#endif
         if (h0 | h1) {                                    // about 2e-4 of all pairs
             while (h0) {
                 const int bit = 31 - __clz(h0);
@@ -495,7 +534,23 @@ __device__ __noinline__ void shade_chain(Chain& c, const TraceArgs& a, FrameTota
     }
     if (done) {
         const unsigned long long p = c.pixel;
-        if (a.rgba8) a.rgba8[p] = pack_rgba(c.acc.x, c.acc.y, c.acc.z, a.quantise_mode);
+        const uint32_t word = (a.rgba8 || a.frame_rgba8) ? pack_rgba(c.acc.x, c.acc.y, c.acc.z, a.quantise_mode) : 0u;
+        if (a.rgba8) a.rgba8[p] = word;
+        if (a.frame_rgba8) {
+            // fused gather: store at the pixel's global position (possibly another GPU's memory, over NVLink)
+            const unsigned long long frame_pixels = static_cast<unsigned long long>(a.local_rows) * a.width;
+            const int frame = static_cast<int>(p / frame_pixels);
+            const unsigned rem = static_cast<unsigned>(p - frame * frame_pixels);
+            const int lrow = rem / a.width;
+            const int col = rem - lrow * a.width;
+            int grow = lrow;
+            if (a.n_ranks > 1) {
+                const int lb = lrow / a.band_rows;
+                grow = (lb * a.n_ranks + a.rank) * a.band_rows + (lrow - lb * a.band_rows);
+            }
+            const unsigned long long gframe = static_cast<unsigned long long>(a.frame_offset) + static_cast<unsigned long long>(frame) * a.frame_stride;
+            a.frame_rgba8[(gframe * a.height + grow) * a.width + col] = word;
+        }
         if (a.rad64) {
             a.rad64[3 * p + 0] = c.acc.x;
             a.rad64[3 * p + 1] = c.acc.y;

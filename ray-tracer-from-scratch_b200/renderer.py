@@ -76,6 +76,15 @@ def load_library(path=LIB_PATH):
     lib.rtx_unpermute_bands.argtypes = [ctx, C.c_void_p, C.c_void_p] + [C.c_int32] * 6
     lib.rtx_ffma_peak.restype = C.c_int
     lib.rtx_ffma_peak.argtypes = [ctx, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    for name in ("rtx_buffer_free", "rtx_buffer_release"):
+        getattr(lib, name).restype = C.c_int
+        getattr(lib, name).argtypes = [ctx, C.c_void_p]
+    lib.rtx_buffer_alloc.restype = C.c_int
+    lib.rtx_buffer_alloc.argtypes = [ctx, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.rtx_buffer_export.restype = C.c_int
+    lib.rtx_buffer_export.argtypes = [ctx, C.c_void_p, C.c_char_p]
+    lib.rtx_buffer_import.restype = C.c_int
+    lib.rtx_buffer_import.argtypes = [ctx, C.c_char_p, C.POINTER(C.c_void_p)]
     if lib.rtx_abi_version() != abi.ABI_VERSION:
         raise RuntimeError("librtx_b200.so ABI %d != binding ABI %d" % (lib.rtx_abi_version(), abi.ABI_VERSION))
     if path == LIB_PATH:
@@ -233,6 +242,28 @@ class Renderer:
                         rows_per_rank):
         self._check(self.lib.rtx_unpermute_bands(self._ctx, band_major_ptr, row_major_ptr, height, width, elem_bytes,
                                                  band_rows, n_ranks, rows_per_rank))
+
+    # -- shareable device buffers (fused multi-GPU gather) --------------------------------------------
+    def buffer_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self.lib.rtx_buffer_alloc(self._ctx, int(nbytes), C.byref(p)))
+        return p.value
+
+    def buffer_free(self, ptr):
+        self._check(self.lib.rtx_buffer_free(self._ctx, C.c_void_p(ptr)))
+
+    def buffer_export(self, ptr):
+        h = C.create_string_buffer(64)
+        self._check(self.lib.rtx_buffer_export(self._ctx, C.c_void_p(ptr), h))
+        return h.raw
+
+    def buffer_import(self, handle):
+        p = C.c_void_p()
+        self._check(self.lib.rtx_buffer_import(self._ctx, C.create_string_buffer(bytes(handle), 64), C.byref(p)))
+        return p.value
+
+    def buffer_release(self, ptr):
+        self._check(self.lib.rtx_buffer_release(self._ctx, C.c_void_p(ptr)))
 
     def ffma_peak(self, variant=0):
         t, m = C.c_double(), C.c_double()

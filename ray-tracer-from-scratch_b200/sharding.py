@@ -9,6 +9,15 @@ Pixels are independent (main.cpp:129-138 has no cross-iteration state), so the o
   * a camera path (config C5): frame f -> rank f % G, each rank renders its frames in one batched launch, ONE
     all-gather, rank 0 reorders frames.
 
+Two ways to bring the pixels to rank 0:
+
+  * fused (default): rank 0 allocates the frame with rtx_buffer_alloc and exports a CUDA-IPC handle; every other rank
+    maps it (rtx_buffer_import, peer access over NVLink) and passes it as rtx_outputs.frame_rgba8. The trace kernel
+    then stores each finished pixel directly at its global position in rank 0's memory — the gather is part of the
+    kernel, there is no all-gather and no unpermute pass, only one barrier.
+  * gather: packed local buffers + all_gather_into_tensor + rtx_unpermute_bands (kept for comparison and for the
+    optional object-id plane).
+
 No data-path collective happens during tracing. Everything here is host logic + collectives; pixels are computed
 only by the CUDA kernels behind the C ABI.
 """
@@ -41,13 +50,67 @@ def frame_owner(n_frames, world):
     return [list(range(r, n_frames, world)) for r in range(world)]
 
 
+class _DevicePtr:
+    """Wraps a raw device pointer for torch.as_tensor through the CUDA array interface."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+
+
 class ShardedRenderer:
     """Row-band / frame sharding around one Renderer per rank."""
 
-    def __init__(self, renderer, rank, world, band_rows=4, group=None):
+    def __init__(self, renderer, rank, world, band_rows=4, group=None, fused=True):
         self.r = renderer
         self.rank, self.world, self.band_rows, self.group = rank, world, band_rows, group
         self.device = torch.device("cuda", renderer.device)
+        self.fused = fused
+        self._frame = None      # (key, pointer valid in THIS process, tensor view on rank 0)
+        self._token = None
+
+    # -- the shared frame on rank 0 -------------------------------------------------------------------
+    def _shared_frame(self, n_frames, H, W):
+        key = (n_frames, H, W)
+        if self._frame is not None and self._frame[0] == key:
+            return self._frame[1], self._frame[2]
+        self.close()
+        handle = [None]
+        ptr = None
+        if self.rank == 0:
+            ptr = self.r.buffer_alloc(n_frames * H * W * 4)
+            handle[0] = self.r.buffer_export(ptr)
+        if self.world > 1:
+            dist.broadcast_object_list(handle, src=0, group=self.group)
+            if self.rank != 0:
+                ptr = self.r.buffer_import(handle[0])
+        view = torch.as_tensor(_DevicePtr(ptr, (n_frames, H, W)), device=self.device) if self.rank == 0 else None
+        self._frame = (key, ptr, view)
+        return ptr, view
+
+    def close(self):
+        if self._frame is not None:
+            _, ptr, _ = self._frame
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            if self.rank == 0:
+                self.r.buffer_free(ptr)
+            else:
+                self.r.buffer_release(ptr)
+            self._frame = None
+
+    def _fused_render(self, cam_pods, total_frames, H, W, params):
+        ptr, view = self._shared_frame(total_frames, H, W)
+        o = abi.Outputs()
+        o.memory = abi.RTX_MEM_DEVICE
+        o.frame_rgba8 = ptr
+        st = self.r.render_raw(cam_pods, params, o) if cam_pods else None
+        if self.world > 1:
+            # Stream-ordered barrier: a 1-element all-reduce completes on rank 0 only after every rank's contribution,
+            # which each rank enqueues behind its own trace kernel. Work queued after it on rank 0 sees the whole frame.
+            if self._token is None:
+                self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
+            dist.all_reduce(self._token, group=self.group)
+        return view, st, (st.launches if st else 0)
 
     def render_frame(self, cam_pod, max_depth=10, want_ids=False, **param_overrides):
         """Renders one frame across all ranks. Returns (frame, stats): frame is an int32 CUDA tensor [H][W] of
@@ -56,6 +119,9 @@ class ShardedRenderer:
         rpr = rows_per_rank(H, self.band_rows, self.world)
         p = default_params(max_depth=max_depth, band_rows=self.band_rows, n_ranks=self.world, rank=self.rank,
                            **param_overrides)
+        if self.fused and not want_ids:
+            view, st, launches = self._fused_render([cam_pod], 1, H, W, p)
+            return (view[0] if view is not None else None), st, launches
         local = torch.empty((rpr, W), dtype=torch.int32, device=self.device)
         ids = torch.empty((rpr, W), dtype=torch.int32, device=self.device) if want_ids else None
         o = abi.Outputs()
@@ -84,6 +150,9 @@ class ShardedRenderer:
         F = len(cam_pods)
         H, W = cam_pods[0].height, cam_pods[0].width
         mine = frame_owner(F, self.world)[self.rank]
+        if self.fused:
+            p = default_params(max_depth=max_depth, frame_offset=self.rank, frame_stride=self.world, **param_overrides)
+            return self._fused_render([cam_pods[f] for f in mine], F, H, W, p)
         per_rank = (F + self.world - 1) // self.world
         local = torch.zeros((per_rank, H, W), dtype=torch.int32, device=self.device)
         st = None

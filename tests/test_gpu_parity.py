@@ -333,3 +333,50 @@ print("ok")
     env = dict(os.environ, RTX_B200_LIB=lib)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_fused_frame_output_places_pixels_globally(gpu, renderer_mod, port, S, syn, pkg):
+    """rtx_outputs.frame_rgba8 (the fused multi-GPU gather): every rank's kernel stores its pixels at their GLOBAL
+    position of one shared row-major frame. Emulated on one GPU: 4 ranks x cyclic 3-row bands into one buffer
+    allocated with rtx_buffer_alloc, and 5 frames sharded over 2 ranks with frame_offset/frame_stride."""
+    import ctypes as C
+    import torch
+    a = pkg.abi
+    scene = syn[:300] + syn[10000:10010]
+    pod = S.default_camera(64, 64 / 50).pod()
+    H, W = pod.height, pod.width
+    assert H == 50
+    exp = port.render(scene, pod, 8, want=("rgba8",))["rgba8"]
+    gpu.set_scene(scene)
+    ptr = gpu.buffer_alloc(H * W * 4)
+    try:
+        handle = gpu.buffer_export(ptr)
+        assert len(handle) == 64
+        view = torch.as_tensor(type("P", (), {"__cuda_array_interface__": {"shape": (H, W), "typestr": "<i4", "data": (ptr, False), "version": 3}})(),
+                               device="cuda:0")
+        view.fill_(-1)
+        for r in range(4):
+            o = a.Outputs()
+            o.memory, o.frame_rgba8 = a.RTX_MEM_DEVICE, ptr
+            gpu.render_raw([pod], renderer_mod.default_params(max_depth=8, band_rows=3, n_ranks=4, rank=r), o)
+        assert np.array_equal(view.cpu().numpy().view(np.uint32), exp)
+    finally:
+        gpu.buffer_free(ptr)
+    # frames sharded over 2 ranks
+    cams = [c.pod() for c in S.flythrough_cameras(256, 48, 16.0 / 9.0)[::60]][:5]
+    h, w = cams[0].height, cams[0].width
+    gpu.set_scene(S.default_scene())
+    ptr = gpu.buffer_alloc(5 * h * w * 4)
+    try:
+        view = torch.as_tensor(type("P", (), {"__cuda_array_interface__": {"shape": (5, h, w), "typestr": "<i4", "data": (ptr, False), "version": 3}})(),
+                               device="cuda:0")
+        view.fill_(-1)
+        for r in range(2):
+            o = a.Outputs()
+            o.memory, o.frame_rgba8 = a.RTX_MEM_DEVICE, ptr
+            gpu.render_raw(cams[r::2], renderer_mod.default_params(frame_offset=r, frame_stride=2), o)
+        got = view.cpu().numpy().view(np.uint32)
+        for f, pod_f in enumerate(cams):
+            assert np.array_equal(got[f], port.render(S.default_scene(), pod_f, 10, want=("rgba8",))["rgba8"]), f
+    finally:
+        gpu.buffer_free(ptr)

@@ -35,8 +35,8 @@ def test_struct_sizes_match_header(pkg):
     assert C.sizeof(a.Vec3) == 24 and C.sizeof(a.MaterialPOD) == 64
     assert C.sizeof(a.ObjectPOD) == 8 + 64 + 24 + 24 + 16
     assert C.sizeof(a.CameraPOD) == 4 * 24 + 8 and C.sizeof(a.CameraDesc) == 3 * 24 + 24
-    assert C.sizeof(a.Params) == 16 + 4 * 24 + 16 + 16
-    assert C.sizeof(a.Outputs) == 6 * 8 + 8
+    assert C.sizeof(a.Params) == 16 + 4 * 24 + 16 + 16 + 8
+    assert C.sizeof(a.Outputs) == 6 * 8 + 8 + 8
     assert C.sizeof(a.Stats) == 5 * 8 + 4 * 8 + 8 + 8 + 16
 
 
