@@ -22,9 +22,10 @@
 //    (distance > 0, strictly smaller, lowest scene index on ties). The FP32 stage can only discard pairs the
 //    double test would also discard, so ids/distances equal the reference's bit for bit.
 //
-//  * Objects live in shared memory, pair-interleaved for FFMA2: (cx_a,cx_b,cy_a,cy_b)(cz_a,cz_b,-w_a,-w_b) with
-//    w = (r+E)^2. 10 064 entries = 161 KB, resident for the whole launch. Larger scenes stream tiles through the
-//    same buffer (CTA-synchronous loop).
+//  * Objects live in shared memory, pair-interleaved for FFMA2, in two planes: A[p] = (cx_a,cx_b,cy_a,cy_b) and
+//    B[p] = (cz_a,cz_b,-w_a,-w_b), w = (r+E)^2 (two planes so that both the broadcast loads of the ordinary scan and
+//    the lane-distinct loads of the cooperative drain are conflict-free). 10 064 entries = 161 KB, resident for the
+//    whole launch. Larger scenes stream tiles through the same buffer (CTA-synchronous loop).
 #include "rtx_device.cuh"
 
 namespace rtx {
@@ -52,8 +53,8 @@ constexpr int kCoopMax = RTX_COOP_MAX;   // cooperative drain when a warp has at
 constexpr int kMboxCap = RTX_MBOX_CAP;   // cooperative drain: survivors one chain may receive per scan
 constexpr int kWarps = kThreads / 32;
 struct Mailbox {                      // one per warp, in shared memory behind the entry tile
-    int count[2];
-    int items[2][kMboxCap];
+    int count[4];
+    int items[4][kMboxCap];
 };
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kMaxSmemBytes = 227 * 1024;
@@ -328,18 +329,18 @@ __device__ __forceinline__ void screen_both(const float2 (&cx)[kPairsPerIter], c
 }
 
 // The O(N) scan over one shared-memory tile: n_pairs entry pairs starting at entry index `base`.
-__device__ __forceinline__ void scan_tile(unsigned tile_addr, int n_pairs, int base, const Packed& k0, const Packed& k1,
-                                          Chain& c0, Chain& c1, const SceneDev& sc, float eps)
+__device__ __forceinline__ void scan_tile(unsigned tile_addr, unsigned plane_bytes, int n_pairs, int base, const Packed& k0,
+                                          const Packed& k1, Chain& c0, Chain& c1, const SceneDev& sc, float eps)
 {
     unsigned addr;
     asm volatile("mov.u32 %0, %1;" : "=r"(addr) : "r"(tile_addr));   // opaque: keeps the shared base in a register
     int entry = base;
 #pragma unroll 1
-    for (int it = n_pairs / kPairsPerIter; it > 0; --it, addr += kPairsPerIter * 32u, entry += 2 * kPairsPerIter) {
+    for (int it = n_pairs / kPairsPerIter; it > 0; --it, addr += kPairsPerIter * 16u, entry += 2 * kPairsPerIter) {
         float2 cx[kPairsPerIter], cy[kPairsPerIter], cz[kPairsPerIter], nw[kPairsPerIter];
 #pragma unroll
         for (int u = 0; u < kPairsPerIter; u++) {
-            const float4 p0 = lds128(addr + u * 32u), p1 = lds128(addr + u * 32u + 16u);
+            const float4 p0 = lds128(addr + u * 16u), p1 = lds128(addr + plane_bytes + u * 16u);
             cx[u] = make_float2(p0.x, p0.y);
             cy[u] = make_float2(p0.z, p0.w);
             cz[u] = make_float2(p1.x, p1.y);
@@ -399,35 +400,26 @@ __device__ __forceinline__ Packed bcast(const Packed& k, int src)
     return r;
 }
 
-__device__ __forceinline__ void coop_scan(unsigned tile_addr, int total_pairs, const Packed& ka, const Packed& kb, Mailbox* mb,
-                                          unsigned lane)
+constexpr int kCoopChains = 4;   // live chains screened per cooperative pass
+
+__device__ __forceinline__ void coop_scan(unsigned tile_addr, unsigned plane_bytes, int total_pairs,
+                                          const Packed (&k)[kCoopChains], Mailbox* mb, unsigned lane)
 {
-    constexpr int kStep = 2;   // pairs per lane per iteration
 #pragma unroll 1
-    for (int pair = lane; pair < total_pairs; pair += 32 * kStep) {
-        float4 p0[kStep], p1[kStep];
+    for (int pair = lane; pair < total_pairs; pair += 32) {
+        const float4 p0 = lds128(tile_addr + pair * 16u), p1 = lds128(tile_addr + plane_bytes + pair * 16u);
+        float2 q[kCoopChains];
+        unsigned any = 0u;
 #pragma unroll
-        for (int u = 0; u < kStep; u++) {
-            const int p = pair + 32 * u;
-            if (p < total_pairs) {
-                p0[u] = lds128(tile_addr + p * 32u);
-                p1[u] = lds128(tile_addr + p * 32u + 16u);
-            } else {
-                p0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                p1[u] = make_float4(0.f, 0.f, 1.f, 1.f);   // -w = +1: never passes
-            }
+        for (int c = 0; c < kCoopChains; c++) {
+            q[c] = screen_one(p0, p1, k[c]);
+            any |= __float_as_uint(q[c].x) | __float_as_uint(q[c].y);
         }
+        if (any & 0x80000000u) {
 #pragma unroll
-        for (int u = 0; u < kStep; u++) {
-            const float2 qa = screen_one(p0[u], p1[u], ka);
-            const float2 qb = screen_one(p0[u], p1[u], kb);
-            const unsigned any = __float_as_uint(qa.x) | __float_as_uint(qa.y) | __float_as_uint(qb.x) | __float_as_uint(qb.y);
-            if (any & 0x80000000u) {
-                const int e = 2 * (pair + 32 * u);
-                if (__float_as_uint(qa.x) & 0x80000000u) post(mb, 0, e);
-                if (__float_as_uint(qa.y) & 0x80000000u) post(mb, 0, e + 1);
-                if (__float_as_uint(qb.x) & 0x80000000u) post(mb, 1, e);
-                if (__float_as_uint(qb.y) & 0x80000000u) post(mb, 1, e + 1);
+            for (int c = 0; c < kCoopChains; c++) {
+                if (__float_as_uint(q[c].x) & 0x80000000u) post(mb, c, 2 * pair);
+                if (__float_as_uint(q[c].y) & 0x80000000u) post(mb, c, 2 * pair + 1);
             }
         }
     }
@@ -442,17 +434,17 @@ __device__ __forceinline__ bool pop_chain(unsigned& r0, unsigned& r1, int& src, 
     return false;
 }
 
-// Cooperative tile fill: entries (cx, cy, cz, r) -> pair-interleaved (cx_a,cx_b,cy_a,cy_b)(cz_a,cz_b,-w_a,-w_b),
-// w = (r + E)^2. Padding entries (r < 0) get -w = +1 and can never pass.
-__device__ __forceinline__ void fill_tile(float4* tile, const float4* __restrict__ src, int n_pairs, float eps)
+// Cooperative tile fill: entries (cx, cy, cz, r) -> planes A[i] = (cx_a,cx_b,cy_a,cy_b), B[i] = (cz_a,cz_b,-w_a,-w_b),
+// w = (r + E)^2, plane B starting plane_pairs float4 after plane A. Padding entries (r < 0) get -w = +1: never pass.
+__device__ __forceinline__ void fill_tile(float4* tile, int plane_pairs, const float4* __restrict__ src, int n_pairs, float eps)
 {
     for (int i = threadIdx.x; i < n_pairs; i += kThreads) {
         const float4 a = __ldg(&src[2 * i]), b = __ldg(&src[2 * i + 1]);
         const float ra = a.w + eps, rb = b.w + eps;
         const float nwa = a.w >= 0.f ? -(ra * ra) : 1.f;
         const float nwb = b.w >= 0.f ? -(rb * rb) : 1.f;
-        tile[2 * i] = make_float4(a.x, b.x, a.y, b.y);
-        tile[2 * i + 1] = make_float4(a.z, b.z, nwa, nwb);
+        tile[i] = make_float4(a.x, b.x, a.y, b.y);
+        tile[plane_pairs + i] = make_float4(a.z, b.z, nwa, nwb);
     }
 }
 
@@ -611,9 +603,11 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
     const int total_pairs = sc.n_entries_padded >> 1;
     const int n_tiles = STREAM ? (total_pairs + tile_pairs - 1) / tile_pairs : 1;
     const unsigned tile_addr = static_cast<unsigned>(__cvta_generic_to_shared(s_tile));
+    const int plane_pairs = STREAM ? tile_pairs : total_pairs;          // float4 per plane
+    const unsigned plane_bytes = static_cast<unsigned>(plane_pairs) * 16u;
 
     if (!STREAM) {
-        fill_tile(s_tile, sc.ent32, total_pairs, a.filter_eps);
+        fill_tile(s_tile, plane_pairs, sc.ent32, total_pairs, a.filter_eps);
         __syncthreads();
     }
 
@@ -626,7 +620,7 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
     }
     FrameTotals tot{0ull, 0ull, 0.0};
     bool pool_dry = false;             // warp-uniform: a fetch of this warp found the pixel pool empty
-    Mailbox* const mbox = reinterpret_cast<Mailbox*>(s_tile + (STREAM ? 2 * tile_pairs : sc.n_entries_padded)) + (threadIdx.x >> 5);
+    Mailbox* const mbox = reinterpret_cast<Mailbox*>(s_tile + 2 * plane_pairs) + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicMin(&a.counters[4], globaltimer_ns());   // kernel start
 
     for (;;) {
@@ -667,9 +661,9 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
                 const int first_pair = t * tile_pairs;
                 const int count = min(tile_pairs, total_pairs - first_pair);
                 __syncthreads();
-                fill_tile(s_tile, sc.ent32 + 2 * first_pair, count, a.filter_eps);
+                fill_tile(s_tile, plane_pairs, sc.ent32 + 2 * first_pair, count, a.filter_eps);
                 __syncthreads();
-                scan_tile(tile_addr, count, 2 * first_pair, k0, k1, ch[0], ch[1], sc, a.filter_eps);
+                scan_tile(tile_addr, plane_bytes, count, 2 * first_pair, k0, k1, ch[0], ch[1], sc, a.filter_eps);
             }
         } else {
             const unsigned m0 = __ballot_sync(kFull, ch[0].active), m1 = __ballot_sync(kFull, ch[1].active);
@@ -678,33 +672,32 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
             if (coop) {
                 unsigned r0 = m0, r1 = m1;
                 bool overflow = false;
-                int src_a, which_a, src_b, which_b;
-                while (pop_chain(r0, r1, src_a, which_a)) {
-                    const bool have_b = pop_chain(r0, r1, src_b, which_b);
-                    const Packed ka = bcast(which_a ? k1 : k0, src_a);
-                    Packed kb = bcast(which_b ? k1 : k0, src_b);
-                    if (!have_b) {
-                        kb.ux = kb.uy = kb.uz = kb.vx = kb.vy = kb.vz = 0.f;
-                        kb.nuo = kb.nvo = 1e15f;
-                    }
-                    if (lane_id == 0) mbox->count[0] = mbox->count[1] = 0;
-                    __syncwarp();
-                    coop_scan(tile_addr, total_pairs, ka, kb, mbox, lane_id);
-                    __syncwarp();
-                    if (static_cast<int>(lane_id) == src_a) {
-                        const int n = mbox->count[0];
-                        if (n > kMboxCap) overflow = true;
-                        for (int i = 0; i < min(n, kMboxCap); i++) {
-                            if (which_a) enqueue(ch[1], mbox->items[0][i], sc, a.filter_eps);
-                            else enqueue(ch[0], mbox->items[0][i], sc, a.filter_eps);
+                while (r0 | r1) {
+                    int src[kCoopChains], which[kCoopChains];
+                    bool have[kCoopChains];
+                    Packed kc[kCoopChains];
+#pragma unroll
+                    for (int c = 0; c < kCoopChains; c++) {
+                        have[c] = pop_chain(r0, r1, src[c], which[c]);
+                        kc[c] = bcast(which[c] ? k1 : k0, src[c]);
+                        if (!have[c]) {
+                            kc[c].ux = kc[c].uy = kc[c].uz = kc[c].vx = kc[c].vy = kc[c].vz = 0.f;
+                            kc[c].nuo = kc[c].nvo = 1e15f;
                         }
                     }
-                    if (have_b && static_cast<int>(lane_id) == src_b) {
-                        const int n = mbox->count[1];
-                        if (n > kMboxCap) overflow = true;
-                        for (int i = 0; i < min(n, kMboxCap); i++) {
-                            if (which_b) enqueue(ch[1], mbox->items[1][i], sc, a.filter_eps);
-                            else enqueue(ch[0], mbox->items[1][i], sc, a.filter_eps);
+                    if (lane_id < kCoopChains) mbox->count[lane_id] = 0;
+                    __syncwarp();
+                    coop_scan(tile_addr, plane_bytes, total_pairs, kc, mbox, lane_id);
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < kCoopChains; c++) {
+                        if (have[c] && static_cast<int>(lane_id) == src[c]) {
+                            const int n = mbox->count[c];
+                            if (n > kMboxCap) overflow = true;
+                            for (int i = 0; i < min(n, kMboxCap); i++) {
+                                if (which[c]) enqueue(ch[1], mbox->items[c][i], sc, a.filter_eps);
+                                else enqueue(ch[0], mbox->items[c][i], sc, a.filter_eps);
+                            }
                         }
                     }
                     __syncwarp();
@@ -716,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
                     coop = false;
                 }
             }
-            if (!coop) scan_tile(tile_addr, total_pairs, 0, k0, k1, ch[0], ch[1], sc, a.filter_eps);
+            if (!coop) scan_tile(tile_addr, plane_bytes, total_pairs, 0, k0, k1, ch[0], ch[1], sc, a.filter_eps);
         }
         drain_queue(ch[0], sc, a.filter_eps);
         drain_queue(ch[1], sc, a.filter_eps);
