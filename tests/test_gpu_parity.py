@@ -380,3 +380,33 @@ def test_fused_frame_output_places_pixels_globally(gpu, renderer_mod, port, S, s
             assert np.array_equal(got[f], port.render(S.default_scene(), pod_f, 10, want=("rgba8",))["rgba8"]), f
     finally:
         gpu.buffer_free(ptr)
+
+
+def test_non_finite_objects_and_extreme_depth(gpu, renderer_mod, port, S):
+    """Objects with NaN / inf geometry are never hit by the reference (comparisons with NaN are false) but must not
+    disturb the others: the FP32 screen degrades to "everything goes to the exact test". Depth cap 254 = the
+    largest the uint8 ray-count plane can carry."""
+    M = S.Material
+    nan, inf = float("nan"), float("inf")
+    scene = S.default_scene() + [
+        S.Sphere(M((1, 0, 0)), (nan, 0, 0), .5), S.Sphere(M((1, 0, 0)), (2, 0, 0), nan),
+        S.Wall(M((1, 1, 0)), (3, nan, 0), (0, 1, 0), 1, 1), S.Wall(M((1, 1, 0)), (2.5, 1, 0), (0, 0, 0), 1, 1),   # zero normal -> NaN
+        S.Sphere(M((0, 0, 1), .9), (2.0, 1.0, 0.5), 0.25), S.Sphere(M((0, 1, 1), .9), (2.0, -1.0, 0.5), -0.25),   # negative radius = same sphere
+    ]
+    pod = S.default_camera(64, 1.0).pod()
+    got, st = render(gpu, renderer_mod, scene, pod, 254)
+    exp = port.render(scene, pod, 254)
+    check_frame(got, exp, st)
+    assert set(np.unique(exp["object_id"])) >= {-1, 0, 7, 8} and not ({3, 4, 5, 6} & set(np.unique(exp["object_id"])))
+    scene_inf = S.default_scene() + [S.Sphere(M((1, 0, 0)), (inf, 0, 0), .5)]
+    got, st = render(gpu, renderer_mod, scene_inf, pod, 4)
+    check_frame(got, port.render(scene_inf, pod, 4), st)
+
+
+def test_one_row_and_one_column_frames(gpu, renderer_mod, port, S):
+    scene = S.default_scene()
+    for width, aspect in ((200, 200.0), (1, 0.01), (7, 7.0 / 3)):
+        pod = S.default_camera(width, aspect).pod()
+        got, st = render(gpu, renderer_mod, scene, pod, 10)
+        assert got["rgba8"].shape == (pod.height, pod.width)
+        check_frame(got, port.render(scene, pod, 10), st)
