@@ -36,9 +36,6 @@ namespace rtx {
 #ifndef RTX_PAIRS
 #define RTX_PAIRS 6
 #endif
-#ifndef RTX_ORDER
-#define RTX_ORDER 0
-#endif
 constexpr int kThreads = RTX_THREADS; // 16 warps per SM, 4 per scheduler
 constexpr int kChains = 2;            // pixels in flight per lane
 constexpr int kPairsPerIter = RTX_PAIRS;   // sphere pairs (8 entries) per hot-loop iteration
@@ -260,14 +257,6 @@ __device__ __forceinline__ unsigned screen_pairs(const float2 (&cx)[kPairsPerIte
     float2 pu[kPairsPerIter], pv[kPairsPerIter], q[kPairsPerIter];
     const float2 ux = dup(k.ux), uy = dup(k.uy), uz = dup(k.uz), nuo = dup(k.nuo);
     const float2 vx = dup(k.vx), vy = dup(k.vy), vz = dup(k.vz), nvo = dup(k.nvo);
-#if RTX_ORDER == 1
-#pragma unroll
-    for (int u = 0; u < kPairsPerIter; u++) {
-        pu[u] = __ffma2_rn(cx[u], ux, __ffma2_rn(cy[u], uy, __ffma2_rn(cz[u], uz, nuo)));
-        pv[u] = __ffma2_rn(cx[u], vx, __ffma2_rn(cy[u], vy, __ffma2_rn(cz[u], vz, nvo)));
-        q[u] = __ffma2_rn(pu[u], pu[u], __ffma2_rn(pv[u], pv[u], nw[u]));
-    }
-#else
 #pragma unroll
     for (int u = 0; u < kPairsPerIter; u++) pu[u] = __ffma2_rn(cz[u], uz, nuo);
 #pragma unroll
@@ -284,7 +273,6 @@ __device__ __forceinline__ unsigned screen_pairs(const float2 (&cx)[kPairsPerIte
     for (int u = 0; u < kPairsPerIter; u++) q[u] = __ffma2_rn(pv[u], pv[u], nw[u]);
 #pragma unroll
     for (int u = 0; u < kPairsPerIter; u++) q[u] = __ffma2_rn(pu[u], pu[u], q[u]);
-#endif
     unsigned h = 0u;
 #pragma unroll
     for (int u = 0; u < kPairsPerIter; u++) {
@@ -292,40 +280,6 @@ __device__ __forceinline__ unsigned screen_pairs(const float2 (&cx)[kPairsPerIte
         h = __funnelshift_l(__float_as_uint(q[u].y), h, 1);
     }
     return h;
-}
-
-// Both chains at once, entry-operand-major: the four FFMA2 that consume the same entry pair component (u and v
-// axis of chain 0, u and v axis of chain 1) are adjacent, so the pair stays in the operand-reuse cache and each
-// instruction reads at most three fresh registers.
-__device__ __forceinline__ void screen_both(const float2 (&cx)[kPairsPerIter], const float2 (&cy)[kPairsPerIter],
-                                            const float2 (&cz)[kPairsPerIter], const float2 (&nw)[kPairsPerIter],
-                                            const Packed& k0, const Packed& k1, unsigned& h0, unsigned& h1)
-{
-    h0 = 0u;
-    h1 = 0u;
-#pragma unroll
-    for (int u = 0; u < kPairsPerIter; u++) {
-        float2 pu0 = __ffma2_rn(cz[u], dup(k0.uz), dup(k0.nuo));
-        float2 pv0 = __ffma2_rn(cz[u], dup(k0.vz), dup(k0.nvo));
-        float2 pu1 = __ffma2_rn(cz[u], dup(k1.uz), dup(k1.nuo));
-        float2 pv1 = __ffma2_rn(cz[u], dup(k1.vz), dup(k1.nvo));
-        pu0 = __ffma2_rn(cy[u], dup(k0.uy), pu0);
-        pv0 = __ffma2_rn(cy[u], dup(k0.vy), pv0);
-        pu1 = __ffma2_rn(cy[u], dup(k1.uy), pu1);
-        pv1 = __ffma2_rn(cy[u], dup(k1.vy), pv1);
-        pu0 = __ffma2_rn(cx[u], dup(k0.ux), pu0);
-        pv0 = __ffma2_rn(cx[u], dup(k0.vx), pv0);
-        pu1 = __ffma2_rn(cx[u], dup(k1.ux), pu1);
-        pv1 = __ffma2_rn(cx[u], dup(k1.vx), pv1);
-        float2 q0 = __ffma2_rn(pv0, pv0, nw[u]);
-        float2 q1 = __ffma2_rn(pv1, pv1, nw[u]);
-        q0 = __ffma2_rn(pu0, pu0, q0);
-        q1 = __ffma2_rn(pu1, pu1, q1);
-        h0 = __funnelshift_l(__float_as_uint(q0.x), h0, 1);
-        h0 = __funnelshift_l(__float_as_uint(q0.y), h0, 1);
-        h1 = __funnelshift_l(__float_as_uint(q1.x), h1, 1);
-        h1 = __funnelshift_l(__float_as_uint(q1.y), h1, 1);
-    }
 }
 
 // The O(N) scan over one shared-memory tile: n_pairs entry pairs starting at entry index `base`.
@@ -346,13 +300,8 @@ __device__ __forceinline__ void scan_tile(unsigned tile_addr, unsigned plane_byt
             cz[u] = make_float2(p1.x, p1.y);
             nw[u] = make_float2(p1.z, p1.w);
         }
-#if RTX_ORDER == 2
-        unsigned h0, h1;                                  // sign history: bit set = q - w < 0 = survivor
-        screen_both(cx, cy, cz, nw, k0, k1, h0, h1);
-#else
         unsigned h0 = screen_pairs(cx, cy, cz, nw, k0);   // sign history: bit set = q - w < 0 = survivor
         unsigned h1 = screen_pairs(cx, cy, cz, nw, k1);
-#endif
         if (h0 | h1) {                                    // about 2e-4 of all pairs
             while (h0) {
                 const int bit = 31 - __clz(h0);
