@@ -411,7 +411,7 @@ struct FrameTotals {
 
 // Shade one finished segment of a chain (recursive_ray_tracing, main.cpp:89-119) and either set up the
 // reflected ray or write the pixel.
-__device__ __noinline__ void shade_chain(Chain& c, const TraceArgs& a, FrameTotals& tot)
+__device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, FrameTotals& tot)
 {
     using namespace ex;
     const SceneDev& sc = a.scene;
@@ -514,7 +514,7 @@ __device__ __noinline__ void shade_chain(Chain& c, const TraceArgs& a, FrameTota
 }
 
 // Primary ray of packed pixel index p (main.cpp:129-134).
-__device__ __noinline__ void start_pixel(Chain& c, unsigned long long p, const TraceArgs& a)
+__device__ __forceinline__ void start_pixel_body(Chain& c, unsigned long long p, const TraceArgs& a)
 {
     using namespace ex;
     const unsigned long long frame_pixels = static_cast<unsigned long long>(a.local_rows) * a.width;
@@ -539,6 +539,75 @@ __device__ __noinline__ void start_pixel(Chain& c, unsigned long long p, const T
     c.first_id = -1;
     c.rays = 0;
     c.active = 1;
+}
+
+// Out-of-line wrappers for the big kernel (its chains live in local memory; the hot loop should stay small).
+__device__ __noinline__ void shade_chain(Chain& c, const TraceArgs& a, FrameTotals& tot) { shade_body(c, a, tot); }
+__device__ __noinline__ void start_pixel(Chain& c, unsigned long long p, const TraceArgs& a) { start_pixel_body(c, p, a); }
+
+// ---- small scenes ---------------------------------------------------------------------------------------------------
+// A handful of objects (the reference's own scene has three) needs no screen: the frame is bound by the double
+// shading and, in the big kernel, by instruction-cache misses and local-memory round trips of the chain state
+// (ncu on config C2: no_instruction 3.5, long_scoreboard 3.8 warps per issue; profiles/r1_trace_c2_ncu.md).
+// This kernel is the same algorithm without the machinery: one chain per lane held in registers, every object tested
+// with the exact double routines, persistent lanes refilled from the same pixel counter. Results are identical by
+// construction (same sphere_exact / wall_exact / better / shade_body).
+constexpr int kSmallScene = 16;       // objects
+constexpr int kSmallThreads = 256;
+
+__global__ void __launch_bounds__(kSmallThreads) trace_small_kernel(const TraceArgs a)
+{
+    const SceneDev& sc = a.scene;
+    const unsigned lane_id = threadIdx.x & 31u;
+    const unsigned long long total_pixels =
+        static_cast<unsigned long long>(a.n_frames) * static_cast<unsigned long long>(a.local_rows) * a.width;
+    Chain c;
+    c.active = 0;
+    c.rays = 0;
+    FrameTotals tot{0ull, 0ull, 0.0};
+    for (;;) {
+        __syncwarp();
+        const unsigned idle = __ballot_sync(kFull, !c.active);
+        if (idle) {
+            unsigned long long base = 0;
+            if (lane_id == 0) base = atomicAdd(&a.counters[0], static_cast<unsigned long long>(__popc(idle)));
+            base = __shfl_sync(kFull, base, 0);
+            if (!c.active) {
+                const unsigned long long p = base + __popc(idle & ((1u << lane_id) - 1u));
+                if (p < total_pixels) start_pixel_body(c, p, a);
+            }
+        }
+        if (__ballot_sync(kFull, c.active) == 0u) break;
+        if (c.active) {
+            c.a_dd = ex::len2(c.d);
+            c.dlen = ex::sqrt(c.a_dd);
+            c.best_dist = 1.7976931348623157e308;   // DBL_MAX, main.cpp:70
+            c.best_id = -1;
+            for (int i = 0; i < sc.n_spheres; i++) {
+                const double dist = sphere_exact(c.o, c.d, c.a_dd, c.dlen, sc.sph64[i], nullptr);
+                const int id = sc.sph_id[i];
+                if (better(dist, id, c.best_dist, c.best_id)) { c.best_dist = dist; c.best_id = id; }
+            }
+            for (int i = 0; i < sc.n_walls; i++) {
+                const WallDev& w = sc.walls[i];
+                const double t = wall_exact(c.o, c.d, w);
+                if (better(t, w.id, c.best_dist, c.best_id)) { c.best_dist = t; c.best_id = w.id; }
+            }
+            shade_body(c, a, tot);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        tot.rays += __shfl_down_sync(kFull, tot.rays, off);
+        tot.over += __shfl_down_sync(kFull, tot.over, off);
+        tot.maxlum = fmax(tot.maxlum, __shfl_down_sync(kFull, tot.maxlum, off));
+    }
+    if (lane_id == 0) {
+        if (tot.rays) atomicAdd(&a.counters[1], tot.rays);
+        if (tot.over) atomicAdd(&a.counters[2], tot.over);
+        if (tot.maxlum > 0.0) atomicMax(&a.counters[3], static_cast<unsigned long long>(__double_as_longlong(tot.maxlum)));
+    }
 }
 
 template <bool STREAM>
@@ -701,6 +770,19 @@ cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, 
     const unsigned long long total =
         static_cast<unsigned long long>(args.n_frames) * static_cast<unsigned long long>(args.local_rows) * args.width;
     if (total == 0) return cudaSuccess;
+    if (args.scene.n_objects <= kSmallScene) {
+        static int per_sm = 0;
+        if (per_sm == 0) {
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_small_kernel, kSmallThreads, 0);
+            if (e != cudaSuccess) return e;
+            if (per_sm < 1) per_sm = 1;
+        }
+        unsigned long long small_blocks = (total + kSmallThreads - 1) / kSmallThreads;
+        if (small_blocks > static_cast<unsigned long long>(n_sms) * per_sm) small_blocks = static_cast<unsigned long long>(n_sms) * per_sm;
+        trace_small_kernel<<<static_cast<unsigned>(small_blocks), kSmallThreads, 0, stream>>>(args);
+        if (launches) (*launches)++;
+        return cudaGetLastError();
+    }
     unsigned long long blocks = (total + kThreads * kChains - 1) / (kThreads * kChains);
     if (blocks > static_cast<unsigned long long>(n_sms)) blocks = n_sms;
     cudaError_t err;

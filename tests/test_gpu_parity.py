@@ -410,3 +410,20 @@ def test_one_row_and_one_column_frames(gpu, renderer_mod, port, S):
         got, st = render(gpu, renderer_mod, scene, pod, 10)
         assert got["rgba8"].shape == (pod.height, pod.width)
         check_frame(got, port.render(scene, pod, 10), st)
+
+
+def test_small_scene_kernel_boundary(gpu, renderer_mod, port, S):
+    """Scenes of up to 16 objects run the compact register-resident kernel (every object tested exactly), larger ones
+    the screened kernel: both sides of the switch must match the oracle, for spheres-only, walls-only and mixed."""
+    pod = S.default_camera(72, 16.0 / 9.0).pod()
+    for n_s, n_w in ((16, 0), (17, 0), (0, 16), (0, 17), (9, 7), (9, 8), (1, 0), (0, 1)):
+        scene = S.synthetic_scene(n_s, n_w, seed=100 + n_s * 31 + n_w)
+        for g in scene:                      # pull the random objects in front of the default camera
+            if g.kind == 0:
+                g.center = (2.0 + g.center[0] / 16.0, g.center[1] / 12.0, g.center[2] / 12.0)
+            else:
+                g.position = (2.0 + g.position[0] / 16.0, g.position[1] / 12.0, g.position[2] / 12.0)
+        got, st = render(gpu, renderer_mod, scene, pod, 10)
+        exp = port.render(scene, pod, 10)
+        check_frame(got, exp, st)
+        assert exp["hit_mask"].any(), (n_s, n_w)
