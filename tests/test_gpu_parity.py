@@ -427,3 +427,38 @@ def test_small_scene_kernel_boundary(gpu, renderer_mod, port, S):
         exp = port.render(scene, pod, 10)
         check_frame(got, exp, st)
         assert exp["hit_mask"].any(), (n_s, n_w)
+
+
+def test_grazing_spheres_never_lose_a_hit(gpu, renderer_mod, port, S):
+    """Adversarial input for the conservative FP32 screen: spheres TANGENT to camera rays (distance from the centre
+    to the ray = r * (1 + delta), |delta| from 1e-9 to 1e-5, both signs), far from the origin, so that hit / miss is
+    decided in the last bits of the double discriminant. If the screen's error bound were too tight, true hits would
+    be dropped and ids would differ from the reference arithmetic."""
+    import math
+    import random
+    rng = random.Random(0xE)
+    cam = S.default_camera(96, 1.0)
+    pod = cam.pod()
+    tl, dx, dy = pod.image_top_left.tuple(), pod.delta_x.tuple(), pod.delta_y.tuple()
+    scene = []
+    deltas = [0.0] + [s * 10.0 ** -k for k in range(5, 10) for s in (1, -1)]
+    for n in range(330):
+        i, j = rng.randrange(96), rng.randrange(96)
+        centre = [tl[k] + dx[k] * j + dy[k] * i for k in range(3)]
+        d = [-c for c in centre]                                   # position (0,0,0) - pixel centre
+        L = math.sqrt(sum(x * x for x in d))
+        dh = [x / L for x in d]
+        a = [rng.uniform(-1, 1) for _ in range(3)]
+        dot = sum(a[k] * dh[k] for k in range(3))
+        nrm = [a[k] - dot * dh[k] for k in range(3)]
+        nl = math.sqrt(sum(x * x for x in nrm))
+        nrm = [x / nl for x in nrm]
+        t = rng.uniform(20.0, 900.0)
+        r = rng.uniform(0.05, 3.0)
+        off = r * (1.0 + deltas[n % len(deltas)])
+        c = tuple(t * dh[k] + off * nrm[k] for k in range(3))
+        scene.append(S.Sphere(S.Material((rng.uniform(.1, 1), rng.uniform(.1, 1), rng.uniform(.1, 1)), rng.uniform(0, .8)), c, r))
+    got, st = render(gpu, renderer_mod, scene, pod, 6)
+    exp = port.render(scene, pod, 6)
+    check_frame(got, exp, st)
+    assert (exp["object_id"] >= 0).sum() > 50          # the construction does produce hits (and near-misses)
