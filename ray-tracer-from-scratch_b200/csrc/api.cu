@@ -136,7 +136,10 @@ int rtx_create(rtx_ctx** out, int device)
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (auto& ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaHostAlloc(&ctx->h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&ctx->h_counters, 16 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
+    if (ok) {   // [0..7] read-back area, [8..15] reset template
+        for (int k = 0; k < 8; k++) ctx->h_counters[8 + k] = (k >= 4 && k <= 6) ? ~0ull : 0ull;
+    }
     if (!ok) {
         g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
         rtx_destroy(ctx);
@@ -465,8 +468,8 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
     int launches = 0;
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_cameras, ctx->h_cameras, sizeof(rtx_camera) * n_frames, cudaMemcpyHostToDevice, st));
-    RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
-    RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 4, 0xFF, 3 * sizeof(unsigned long long), st));   // atomicMin slots
+    // counters: [0..3] = 0, [4..6] = ~0 (atomicMin slots), [7] = 0 — one copy from a pinned template
+    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_counters, ctx->h_counters + 8, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     RTX_CUDA(ctx, launch_trace(a, ctx->n_sms, st, &launches));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));

@@ -786,13 +786,20 @@ cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, 
     unsigned long long blocks = (total + kThreads * kChains - 1) / (kThreads * kChains);
     if (blocks > static_cast<unsigned long long>(n_sms)) blocks = n_sms;
     cudaError_t err;
+    static thread_local size_t smem_set[2] = {0, 0};   // the attribute is sticky per function: raise it only when needed
     if (stream_tiles) {
-        err = cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (err != cudaSuccess) return err;
+        if (smem > smem_set[1]) {
+            err = cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (err != cudaSuccess) return err;
+            smem_set[1] = smem;
+        }
         trace_kernel<true><<<static_cast<unsigned>(blocks), kThreads, smem, stream>>>(args, tile_pairs);
     } else {
-        err = cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (err != cudaSuccess) return err;
+        if (smem > smem_set[0]) {
+            err = cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (err != cudaSuccess) return err;
+            smem_set[0] = smem;
+        }
         trace_kernel<false><<<static_cast<unsigned>(blocks), kThreads, smem, stream>>>(args, tile_pairs);
     }
     if (launches) (*launches)++;
