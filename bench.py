@@ -406,6 +406,25 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if world == 1:
+            # HBM side: the standalone quantise kernel (main.cpp:338-347) on a device-resident radiance frame of the
+            # same size; algorithmic bytes = 12 (f32) or 24 (f64) read + 4 written per pixel; L2 flushed before each launch.
+            hbm_peak, hbm_src = hbm_peak_gbs()
+            npx = H * W * len(pods)
+            qout = torch.empty(npx, dtype=torch.int32, device=dev)
+            line["roofline_quantise"] = {}
+            for name, dt, bpp in (("f32", torch.float32, 16), ("f64", torch.float64, 28)):
+                rad = torch.rand(npx * 3, dtype=dt, device=dev) * 1.3
+                ts = []
+                for _ in range(7):
+                    flush.add_(1)
+                    torch.cuda.synchronize()
+                    ts.append(r.quantise_device(rad.data_ptr(), dt == torch.float32, npx, qout.data_ptr()).surface_update_ms)
+                ms_q = sorted(ts[2:])[len(ts[2:]) // 2]
+                line["roofline_quantise"][name] = {"bound": "hbm", "achieved": npx * bpp / (ms_q * 1e-3) / 1e9, "peak": hbm_peak,
+                                                   "unit": "GB/s", "frac": npx * bpp / (ms_q * 1e-3) / 1e9 / hbm_peak, "ms": ms_q,
+                                                   "bytes_per_pixel": bpp, "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)"}
+                del rad
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(args, spec, S, scene, pods)

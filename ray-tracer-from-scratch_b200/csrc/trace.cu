@@ -1,5 +1,6 @@
 // trace.cu — the hot path: ray generation, nearest hit over all objects, the reflection chain,
-// Blinn-Phong, sky and the 8-bit pack, as ONE persistent sm_100a kernel.
+// Blinn-Phong, sky and the 8-bit pack, as ONE persistent sm_100a kernel (trace_kernel; scenes of up to 16 objects
+// take the compact trace_small_kernel at the end of this file's device code).
 //
 // Replaces rt_scene -> recursive_ray_tracing -> find_closest_hit -> SceneGeometry::intersect
 // (main.cpp:67-139, scene.cpp:4-78) and, when fused, the quantise loop (main.cpp:338-347).
@@ -38,7 +39,7 @@ namespace rtx {
 #endif
 constexpr int kThreads = RTX_THREADS; // 16 warps per SM, 4 per scheduler
 constexpr int kChains = 2;            // pixels in flight per lane
-constexpr int kPairsPerIter = RTX_PAIRS;   // sphere pairs (8 entries) per hot-loop iteration
+constexpr int kPairsPerIter = RTX_PAIRS;   // entry pairs per hot-loop iteration (6 pairs = 12 entries x 2 chains = 96 FFMA2)
 constexpr int kQueue = 24;            // screen survivors buffered per chain before an early flush
 #ifndef RTX_COOP_MAX
 #define RTX_COOP_MAX 32
@@ -320,7 +321,7 @@ __device__ __forceinline__ void scan_tile(unsigned tile_addr, unsigned plane_byt
 // ---- cooperative drain ---------------------------------------------------------------------------------------------
 // When the pixel pool is empty the frame is finished by the chains still in flight, and a late chain needs up to
 // `depth` more scans: scanning all N entries per lane then leaves a constant tail (measured 3.8 ms on B200,
-// DESIGN.md §3.6). In this mode the warp takes its live chains two at a time, broadcasts their screen constants,
+// DESIGN.md §3.5). In this mode the warp takes its live chains four at a time, broadcasts their screen constants,
 // and its 32 lanes split the entry array (lane l screens pairs l, l+32, ...). Survivors are posted to the owner
 // through a per-warp shared-memory mailbox and then go through the same queue / exact path as always, so results
 // are unchanged (the acceptance rule is order independent).
