@@ -17,11 +17,15 @@ struct FrameStats {
     double maxlum;
 };
 
-__device__ __forceinline__ void stats_add(FrameStats& s, double r, double g, double b)
+// One pixel: RGBA8888 word + statistics (over-range count, max luminance) from one set of products.
+__device__ __forceinline__ uint32_t quantise_pixel(FrameStats& s, double r, double g, double b, int mode)
 {
-    if (over_range(r, g, b)) s.over++;
+    bool over;
+    const uint32_t word = pack_rgba_flag(r, g, b, mode, over);
+    if (over) s.over++;
     const double lum = (r + g + b) * (1.0 / 3.0);
     if (lum > s.maxlum) s.maxlum = lum;
+    return word;
 }
 
 __device__ __forceinline__ void stats_commit(FrameStats s, unsigned long long* counters)
@@ -51,22 +55,17 @@ __global__ void __launch_bounds__(256) quantise_f32_kernel(const float* __restri
         const float4 b = __ldcs(&in4[3 * qd + 1]);
         const float4 c = __ldcs(&in4[3 * qd + 2]);
         uint4 o;
-        o.x = pack_rgba(a.x, a.y, a.z, mode);
-        o.y = pack_rgba(a.w, b.x, b.y, mode);
-        o.z = pack_rgba(b.z, b.w, c.x, mode);
-        o.w = pack_rgba(c.y, c.z, c.w, mode);
-        stats_add(st, a.x, a.y, a.z);
-        stats_add(st, a.w, b.x, b.y);
-        stats_add(st, b.z, b.w, c.x);
-        stats_add(st, c.y, c.z, c.w);
+        o.x = quantise_pixel(st, a.x, a.y, a.z, mode);
+        o.y = quantise_pixel(st, a.w, b.x, b.y, mode);
+        o.z = quantise_pixel(st, b.z, b.w, c.x, mode);
+        o.w = quantise_pixel(st, c.y, c.z, c.w, mode);
         __stcs(&out4[qd], o);
     }
     // ragged tail (n_pixels not a multiple of 4)
     if (blockIdx.x == 0 && threadIdx.x < (n_pixels & 3)) {
         const long long p = (n_quads << 2) + threadIdx.x;
         const double r = rad[3 * p], g = rad[3 * p + 1], b = rad[3 * p + 2];
-        out[p] = pack_rgba(r, g, b, mode);
-        stats_add(st, r, g, b);
+        out[p] = quantise_pixel(st, r, g, b, mode);
     }
     stats_commit(st, counters);
 }
@@ -85,21 +84,16 @@ __global__ void __launch_bounds__(256) quantise_f64_kernel(const double* __restr
 #pragma unroll
         for (int k = 0; k < 6; k++) v[k] = __ldcs(&in2[6 * qd + k]);
         uint4 o;
-        o.x = pack_rgba(v[0].x, v[0].y, v[1].x, mode);
-        o.y = pack_rgba(v[1].y, v[2].x, v[2].y, mode);
-        o.z = pack_rgba(v[3].x, v[3].y, v[4].x, mode);
-        o.w = pack_rgba(v[4].y, v[5].x, v[5].y, mode);
-        stats_add(st, v[0].x, v[0].y, v[1].x);
-        stats_add(st, v[1].y, v[2].x, v[2].y);
-        stats_add(st, v[3].x, v[3].y, v[4].x);
-        stats_add(st, v[4].y, v[5].x, v[5].y);
+        o.x = quantise_pixel(st, v[0].x, v[0].y, v[1].x, mode);
+        o.y = quantise_pixel(st, v[1].y, v[2].x, v[2].y, mode);
+        o.z = quantise_pixel(st, v[3].x, v[3].y, v[4].x, mode);
+        o.w = quantise_pixel(st, v[4].y, v[5].x, v[5].y, mode);
         __stcs(&out4[qd], o);
     }
     if (blockIdx.x == 0 && threadIdx.x < (n_pixels & 3)) {
         const long long p = (n_quads << 2) + threadIdx.x;
         const double r = rad[3 * p], g = rad[3 * p + 1], b = rad[3 * p + 2];
-        out[p] = pack_rgba(r, g, b, mode);
-        stats_add(st, r, g, b);
+        out[p] = quantise_pixel(st, r, g, b, mode);
     }
     stats_commit(st, counters);
 }

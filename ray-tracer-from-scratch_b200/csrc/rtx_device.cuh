@@ -138,6 +138,22 @@ __device__ __forceinline__ uint32_t pack_rgba(double r, double g, double b, int 
     }
     return (ur << 24) | (ug << 16) | (ub << 8) | 0xFFu;
 }
+// Pack + "over range" flag from ONE set of products (the streaming quantise kernel is bound by its double
+// arithmetic for float input, so the products are not formed twice).
+__device__ __forceinline__ uint32_t pack_rgba_flag(double r, double g, double b, int mode, bool& over)
+{
+    const double R = ex::mul(r, 255.0), G = ex::mul(g, 255.0), B = ex::mul(b, 255.0);
+    over = !(R >= 0.0 && R < 256.0 && G >= 0.0 && G < 256.0 && B >= 0.0 && B < 256.0);
+    uint32_t ur, ug, ub;
+    if (mode == RTX_QUANT_SATURATE) {
+        ur = to_u8_sat(R); ug = to_u8_sat(G); ub = to_u8_sat(B);
+    } else if (!over) {   // in range: plain truncation, no wrap or NaN handling needed
+        ur = static_cast<uint32_t>(__double2int_rz(R)); ug = static_cast<uint32_t>(__double2int_rz(G)); ub = static_cast<uint32_t>(__double2int_rz(B));
+    } else {
+        ur = to_u8_wrap(R); ug = to_u8_wrap(G); ub = to_u8_wrap(B);
+    }
+    return (ur << 24) | (ug << 16) | (ub << 8) | 0xFFu;
+}
 // A channel is "over range" when the reference's wrap would alter it: v*255 outside [0,256).
 __device__ __forceinline__ bool over_range(double r, double g, double b)
 {
