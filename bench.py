@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--band-rows", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary configs[1] (c2) measurement in the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="fused", choices=["fused", "allgather"],
                     help="N > 1: peer-memory stores from the trace kernel (fused) or all-gather + unpermute")
@@ -237,10 +238,11 @@ def run_reference_arm(args, spec, S):
 
 
 def cpu_baseline(args, spec, S, scene, pods):
-    """The reference's CPU path on a bounded sample of the same workload (rank 0, N = 1): best of two passes."""
+    """The reference's CPU path on a bounded sample of the same workload (rank 0, N = 1): one pass of about
+    args.cpu_seconds on all host threads (the calibration probe tends to undershoot, hence the 1.5x)."""
     oracle, kind = reference_oracle()
-    cs = CpuSample(oracle, S.flatten(scene), pods, spec["depth"], args.cpu_seconds / 2)
-    secs = min(cs.time_once(), cs.time_once())
+    cs = CpuSample(oracle, S.flatten(scene), pods, spec["depth"], args.cpu_seconds * 1.5)
+    secs = cs.time_once()
     return {"value": cs.rays / secs / 1e6, "unit": "Mrays/s", "cores": cs.threads, "kind": kind,
             "sample": cs.describe() + ", %.2f s" % secs,
             "ms_per_frame_extrapolated": secs / (len(cs.rows) * len(cs.pods)) * cs.height * 1e3}
@@ -425,6 +427,47 @@ def main():
                                                    "unit": "GB/s", "frac": npx * bpp / (ms_q * 1e-3) / 1e9 / hbm_peak, "ms": ms_q,
                                                    "bytes_per_pixel": bpp, "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)"}
                 del rad
+        if world == 1 and args.workload == "auto" and not args.no_also:
+            # BASELINE.json configs[1] (1080p default scene, depth 8) in the same run: device-resident and end to end
+            spec2 = workload_spec("c2", 1)
+            scene2 = build_scene(S, spec2["scene"])
+            pod2 = S.default_camera(spec2["width"], 16.0 / 9.0).pod()
+            r.set_scene(S.flatten(scene2))
+            p2 = R.default_params(max_depth=spec2["depth"])
+            dev2 = torch.empty((pod2.height, pod2.width), dtype=torch.int32, device=dev)
+            host2 = torch.empty((pod2.height, pod2.width), dtype=torch.int32, pin_memory=True)
+            o_dev, o_host = abi.Outputs(), abi.Outputs()
+            o_dev.memory, o_dev.rgba8 = abi.RTX_MEM_DEVICE, dev2.data_ptr()
+            o_host.memory, o_host.rgba8 = abi.RTX_MEM_HOST, host2.data_ptr()
+            res = {}
+            for key, out_desc in (("device", o_dev), ("e2e", o_host)):
+                for _ in range(3):
+                    st2 = r.render_raw([pod2], p2, out_desc)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                tot_ms, kern = 0.0, 0.0
+                for _ in range(20):
+                    flush.add_(1)
+                    e0.record()
+                    if key == "e2e":
+                        r.set_scene(S.flatten(scene2))
+                    st2 = r.render_raw([pod2], p2, out_desc)
+                    e1.record()
+                    e1.synchronize()
+                    tot_ms += e0.elapsed_time(e1)
+                    kern += st2.raytracing_ms
+                res[key] = {"ms_per_frame": tot_ms / 20, "mrays_s": st2.total_rays / (tot_ms / 20 * 1e-3) / 1e6, "kernel_ms": kern / 20}
+            line["also"] = {"c2": {"workload": spec2["label"], "rays_per_frame": st2.total_rays, **res}}
+            if not args.no_cpu_baseline:
+                try:
+                    oracle2, kind2 = reference_oracle()
+                    cs2 = CpuSample(oracle2, S.flatten(scene2), [pod2], spec2["depth"], 2.0)
+                    secs2 = min(cs2.time_once(), cs2.time_once())
+                    line["also"]["c2"]["cpu_baseline"] = {"value": cs2.rays / secs2 / 1e6, "unit": "Mrays/s", "cores": cs2.threads, "kind": kind2,
+                                                          "sample": cs2.describe() + ", %.3f s" % secs2,
+                                                          "ms_per_frame_extrapolated": secs2 / len(cs2.rows) * cs2.height * 1e3}
+                except Exception as e:
+                    line["also"]["c2"]["cpu_baseline"] = {"unavailable": repr(e)}
+            r.set_scene(objs)
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(args, spec, S, scene, pods)
