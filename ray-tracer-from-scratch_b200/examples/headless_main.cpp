@@ -8,6 +8,8 @@
 // CUDA-event times. The window/renderer/texture calls are replaced by a binary PPM (or raw RGBA8888) file.
 //
 //   rtx_headless [--width 640] [--aspect 1] [--depth 10] [--frames 3] [--keys wwad] [--out frame.ppm] [--raw frame.rgba]
+//                [--png frame.png]
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -20,11 +22,69 @@
 
 using namespace rtx;
 
+// Minimal PNG writer (8-bit RGB, "stored" deflate blocks: no zlib needed).
+static void put32(std::vector<unsigned char>& v, uint32_t x) { for (int s = 24; s >= 0; s -= 8) v.push_back(static_cast<unsigned char>(x >> s)); }
+static uint32_t crc32_of(const unsigned char* p, size_t n)
+{
+    static uint32_t table[256];
+    if (!table[1]) for (uint32_t i = 0; i < 256; i++) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; table[i] = c; }
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; i++) c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+    return c ^ 0xFFFFFFFFu;
+}
+static void png_chunk(FILE* f, const char tag[4], const std::vector<unsigned char>& data)
+{
+    std::vector<unsigned char> buf(tag, tag + 4);
+    buf.insert(buf.end(), data.begin(), data.end());
+    std::vector<unsigned char> len, crc;
+    put32(len, static_cast<uint32_t>(data.size()));
+    put32(crc, crc32_of(buf.data(), buf.size()));
+    std::fwrite(len.data(), 1, 4, f);
+    std::fwrite(buf.data(), 1, buf.size(), f);
+    std::fwrite(crc.data(), 1, 4, f);
+}
+static void write_png(const std::string& path, const std::vector<uint32_t>& surface, int W, int H)
+{
+    std::vector<unsigned char> raw;
+    raw.reserve(static_cast<size_t>(H) * (W * 3 + 1));
+    for (int i = 0; i < H; i++) {
+        raw.push_back(0);   // filter type 0
+        for (int j = 0; j < W; j++) {
+            const uint32_t p = surface[static_cast<size_t>(i) * W + j];
+            raw.push_back(static_cast<unsigned char>(p >> 24)); raw.push_back(static_cast<unsigned char>(p >> 16)); raw.push_back(static_cast<unsigned char>(p >> 8));
+        }
+    }
+    std::vector<unsigned char> z = {0x78, 0x01};
+    uint32_t a = 1, b = 0;
+    for (size_t pos = 0; pos < raw.size() || pos == 0; pos += 65535) {
+        const size_t n = std::min<size_t>(65535, raw.size() - pos);
+        z.push_back(pos + n >= raw.size() ? 1 : 0);
+        z.push_back(static_cast<unsigned char>(n)); z.push_back(static_cast<unsigned char>(n >> 8));
+        z.push_back(static_cast<unsigned char>(~n)); z.push_back(static_cast<unsigned char>((~n) >> 8));
+        z.insert(z.end(), raw.begin() + pos, raw.begin() + pos + n);
+        if (raw.empty()) break;
+    }
+    for (unsigned char c : raw) { a = (a + c) % 65521u; b = (b + a) % 65521u; }
+    put32(z, (b << 16) | a);
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot open " + path);
+    const unsigned char sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+    std::fwrite(sig, 1, 8, f);
+    std::vector<unsigned char> ihdr;
+    put32(ihdr, static_cast<uint32_t>(W)); put32(ihdr, static_cast<uint32_t>(H));
+    const unsigned char tail[5] = {8, 2, 0, 0, 0};
+    ihdr.insert(ihdr.end(), tail, tail + 5);
+    png_chunk(f, "IHDR", ihdr);
+    png_chunk(f, "IDAT", z);
+    png_chunk(f, "IEND", {});
+    std::fclose(f);
+}
+
 int main(int argc, char* argv[])
 {
     int width = 640, depth = 10, frames = 3;
     double aspect = 1.0;   // ASPECT_RATIO = 4/3 is integer division = 1 in the reference (main.cpp:25)
-    std::string keys, out_ppm = "frame.ppm", out_raw;
+    std::string keys, out_ppm = "frame.ppm", out_raw, out_png;
     for (int k = 1; k + 1 < argc; k += 2) {
         const std::string a = argv[k];
         if (a == "--width") width = std::atoi(argv[k + 1]);
@@ -34,6 +94,7 @@ int main(int argc, char* argv[])
         else if (a == "--keys") keys = argv[k + 1];
         else if (a == "--out") out_ppm = argv[k + 1];
         else if (a == "--raw") out_raw = argv[k + 1];
+        else if (a == "--png") out_png = argv[k + 1];
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     try {
@@ -99,6 +160,8 @@ int main(int argc, char* argv[])
             std::fwrite(surface.data(), 4, surface.size(), f);
             std::fclose(f);
         }
+
+        if (!out_png.empty()) write_png(out_png, surface, W, H);
 
         auto mean = [](const std::vector<int64_t>& v) { return v.empty() ? 0 : std::accumulate(v.begin(), v.end(), int64_t{0}) / static_cast<int64_t>(v.size()); };
         auto meand = [](const std::vector<double>& v) { return v.empty() ? 0.0 : std::accumulate(v.begin(), v.end(), 0.0) / v.size(); };

@@ -292,6 +292,23 @@ def rt_scene(u, scene, cam, frame_buffer, max_depth=10):
     return fb
 
 
+def write_png(path, rgba8):
+    """Headless output: 8-bit RGB PNG from RGBA8888 words (alpha is always 0xFF in the reference's surface)."""
+    import struct
+    import zlib
+    a = np.asarray(rgba8, dtype=np.uint32)
+    h, w = a.shape
+    rgb = np.stack([(a >> 24) & 0xFF, (a >> 16) & 0xFF, (a >> 8) & 0xFF], axis=-1).astype(np.uint8)
+    raw = b"".join(b"\x00" + rgb[i].tobytes() for i in range(h))      # filter type 0 per scanline
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) +
+                chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+
+
 def write_ppm(path, rgba8):
     """Headless output (replaces the SDL present, main.cpp:351-358): binary PPM from RGBA8888 words."""
     a = np.asarray(rgba8, dtype=np.uint32)

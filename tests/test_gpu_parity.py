@@ -275,8 +275,8 @@ def test_cpp_headless_main_matches_reference_main_loop(tmp_path, port, S, render
     import subprocess
     exe = os.path.join(os.path.dirname(renderer_mod.LIB_PATH), "rtx_headless")
     assert os.path.exists(exe), "build() must produce rtx_headless"
-    raw, ppm = tmp_path / "f.rgba", tmp_path / "f.ppm"
-    out = subprocess.run([exe, "--width", "320", "--frames", "2", "--keys", "xw", "--raw", str(raw), "--out", str(ppm)],
+    raw, ppm, png = tmp_path / "f.rgba", tmp_path / "f.ppm", tmp_path / "f.png"
+    out = subprocess.run([exe, "--width", "320", "--frames", "2", "--keys", "xw", "--raw", str(raw), "--out", str(ppm), "--png", str(png)],
                          check=True, capture_output=True, text=True).stdout
     assert "microseconds for average raytracing" in out and "milliseconds for surface average update" in out
     cam = S.default_camera(320, 1.0)
@@ -287,6 +287,30 @@ def test_cpp_headless_main_matches_reference_main_loop(tmp_path, port, S, render
     assert np.array_equal(got, exp)
     data = open(ppm, "rb").read()
     assert data.startswith(b"P6\n320 320\n255\n") and len(data) == 15 + 320 * 320 * 3
+    # the PNG (stored deflate) decodes to the same pixels
+    import struct
+    import zlib
+    blob = open(png, "rb").read()
+    assert blob[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat = 8, b""
+    while pos < len(blob):
+        n, tag = struct.unpack(">I4s", blob[pos:pos + 8])
+        body = blob[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", blob[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + body) & 0xFFFFFFFF
+        if tag == b"IDAT":
+            idat += body
+        pos += 12 + n
+    rows = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(320, 1 + 320 * 3)
+    assert (rows[:, 0] == 0).all() and rows[:, 1:].tobytes() == data[15:]
+    # a longer scripted walk: forward, right, backward (Camera::forward/right/backward, scene.cpp:121-135), init() never re-run
+    raw2 = tmp_path / "g.rgba"
+    subprocess.run([exe, "--width", "200", "--frames", "4", "--keys", "xwds", "--raw", str(raw2), "--out", ""], check=True, capture_output=True)
+    cam2 = S.default_camera(200, 1.0)
+    pod2 = cam2.pod()
+    pos_x = (0.0 + 0.1) - 0.1                               # forward then backward along direction (1,0,0)
+    pod2.position = type(pod2.position)(pos_x, 0.1, 0.0)    # right_vec = normalize(cross(direction, vup)) = (0,1,0)
+    exp2 = port.render(S.default_scene(), pod2, 10, want=("rgba8",))["rgba8"]
+    assert np.array_equal(np.fromfile(raw2, dtype=np.uint32).reshape(200, 200), exp2)
 
 
 def test_scene_larger_than_shared_memory_streams_tiles(gpu, renderer_mod, port, S):
