@@ -260,6 +260,46 @@ __global__ void __launch_bounds__(512) ffma_peak_operands(float* sink, float a, 
     if (blockIdx.x == 0 && threadIdx.x == 0) clocks[0] = t1 - t0;
 }
 
+// variant 5: packed and scalar FMAs interleaved (8 FFMA2 + NS scalar FFMA per iteration, all operands in the
+// full-rate forms): is there FP32 capacity beyond what FFMA2 alone reaches (a second pipe for scalar FFMA)?
+template <int NS>
+__global__ void __launch_bounds__(512) ffma_peak_mixed(float* sink, float a, float b, long long* clocks)
+{
+    unsigned long long acc[8];
+    float sc[NS > 0 ? NS : 1];
+    unsigned long long av, bv;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const float lo = threadIdx.x * 1e-3f + k, hi = lo + 0.5f;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(acc[k]) : "f"(lo), "f"(hi));
+    }
+#pragma unroll
+    for (int k = 0; k < NS; k++) sc[k] = threadIdx.x * 2e-3f + k;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kPeakIters; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[k]) : "l"(av), "l"(bv));
+            if (k < NS) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(sc[k]) : "f"(a), "f"(b));
+        }
+    }
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[k]));
+        s += lo + hi;
+    }
+#pragma unroll
+    for (int k = 0; k < NS; k++) s += sc[k];
+    if (s == 123.456f) sink[0] = s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) clocks[0] = t1 - t0;
+}
+
 cudaError_t run_ffma_peak(int variant, int n_sms, cudaStream_t stream, double* tflops, double* mhz)
 {
     float* sink = nullptr;
@@ -283,6 +323,10 @@ cudaError_t run_ffma_peak(int variant, int n_sms, cudaStream_t stream, double* t
             ffma_peak_operands<3><<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
         else if (variant == 4)
             ffma_peak_operands<4><<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
+        else if (variant == 5)
+            ffma_peak_mixed<4><<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
+        else if (variant == 6)
+            ffma_peak_mixed<8><<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
         else
             ffma_peak_scalar<<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
         cudaEventRecord(e1, stream);
@@ -294,7 +338,8 @@ cudaError_t run_ffma_peak(int variant, int n_sms, cudaStream_t stream, double* t
     }
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err == cudaSuccess) {
-        const double flops = 2.0 * kPeakChains * kPeakIters * static_cast<double>(blocks) * threads;
+        const double per_iter = variant == 5 ? 2.0 * (16 + 4) : variant == 6 ? 2.0 * (16 + 8) : 2.0 * kPeakChains;
+        const double flops = per_iter * kPeakIters * static_cast<double>(blocks) * threads;
         if (tflops) *tflops = flops / (best_ms * 1e-3) / 1e12;
         long long h_clocks = 0;
         cudaMemcpy(&h_clocks, clocks, sizeof h_clocks, cudaMemcpyDeviceToHost);
