@@ -391,7 +391,8 @@ def main():
             "config": {"workload": spec["label"], "width": W, "height": H, "frames_per_step": len(pods), "depth": spec["depth"],
                        "n_spheres": n_spheres, "n_walls": n_walls, "band_rows": args.band_rows if world > 1 else None,
                        "parallelism": ("1 process per GPU; " + ("cyclic row bands" if spec["name"] != "c5" else "frames sharded over ranks") +
-                                       ("; pixels stored into rank 0's frame over NVLink peer memory by the trace kernel + 1 barrier"
+                                       (("; pixels stored into rank 0's frame over NVLink peer memory by the trace kernel + 1 barrier" if spec["name"] != "c5"
+                                         else "; finished frame chunks bulk-copied into rank 0's frame set over NVLink, overlapped with rendering")
                                         if args.gather == "fused" else "; NCCL all-gather to rank 0 + unpermute")) if world > 1 else "single GPU",
                        "rays_per_step": rays_per_step, "ms_per_frame": ms / args.steps / len(pods),
                        "mpixel_per_s": H * W * len(pods) / (ms / args.steps * 1e-3) / 1e6,

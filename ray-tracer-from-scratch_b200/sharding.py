@@ -6,8 +6,9 @@ Pixels are independent (main.cpp:129-138 has no cross-iteration state), so the o
     (contiguous stripes are measurably imbalanced: SURVEY.md §7 hard part 4). Each rank renders its rows with
     rtx_render(n_ranks=G, rank=r) into a packed device buffer; ONE all-gather delivers the band-major frame; rank 0
     scatters it to row-major with the rtx_unpermute_bands kernel.
-  * a camera path (config C5): frame f -> rank f % G, each rank renders its frames in one batched launch, ONE
-    all-gather, rank 0 reorders frames.
+  * a camera path (config C5): frame f -> rank f % G; each rank renders its frames in chunks and bulk-copies every
+    finished chunk into rank 0's frame set over NVLink while the next chunk renders (or, in gather mode, one batched
+    launch + ONE all-gather + a reindexing on rank 0).
 
 Two ways to bring the pixels to rank 0:
 
@@ -67,6 +68,8 @@ class ShardedRenderer:
         self.fused = fused
         self._frame = None      # (key, pointer valid in THIS process, tensor view on rank 0)
         self._token = None
+        self._side = None       # side stream + double buffers of the pipelined camera-path gather
+        self._bufs = {}
 
     # -- the shared frame on rank 0 -------------------------------------------------------------------
     def _shared_frame(self, n_frames, H, W):
@@ -112,6 +115,51 @@ class ShardedRenderer:
             dist.all_reduce(self._token, group=self.group)
         return view, st, (st.launches if st else 0)
 
+    def _pipelined_frames(self, cam_pods, mine, F, H, W, params, chunk=8):
+        """Camera path, whole frames per rank: a frame is 8 MB, so instead of scattering 4-byte pixel stores over
+        NVLink (fine for one frame spread over ranks, wasteful for gigabytes) each rank renders chunks of frames into
+        local double buffers and copies every finished chunk into rank 0's IPC-mapped frame set with bulk peer copies
+        on a side stream, overlapped with the rendering of the next chunk."""
+        ptr, view = self._shared_frame(F, H, W)
+        dest = view if self.rank == 0 else torch.as_tensor(_DevicePtr(ptr, (F, H, W)), device=self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._bufs = {}
+        key = (chunk, H, W)
+        if key not in self._bufs:
+            self._bufs = {key: ([torch.empty((chunk, H, W), dtype=torch.int32, device=self.device) for _ in range(2)],
+                                [torch.cuda.Event(), torch.cuda.Event()])}
+        bufs, events = self._bufs[key]
+        o = abi.Outputs()
+        o.memory = abi.RTX_MEM_DEVICE
+        total = None
+        launches = 0
+        for ci, start in enumerate(range(0, len(mine), chunk)):
+            frames = mine[start:start + chunk]
+            buf = bufs[ci % 2]
+            if ci >= 2:
+                events[ci % 2].synchronize()           # the copies that read this buffer two chunks ago are done
+            o.rgba8 = buf.data_ptr()
+            st = self.r.render_raw([cam_pods[f] for f in frames], params, o)      # returns when the chunk is rendered
+            launches += st.launches
+            if total is None:
+                total = st
+            else:
+                total.total_rays += st.total_rays
+                total.raytracing_ms += st.raytracing_ms
+                total.sphere_tests += st.sphere_tests
+                total.wall_tests += st.wall_tests
+            with torch.cuda.stream(self._side):
+                for k, f in enumerate(frames):
+                    dest[f].copy_(buf[k], non_blocking=True)
+                events[ci % 2].record(self._side)
+        torch.cuda.current_stream().wait_stream(self._side)
+        if self.world > 1:
+            if self._token is None:
+                self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
+            dist.all_reduce(self._token, group=self.group)     # stream-ordered barrier: all copies have landed
+        return view, total, launches
+
     def render_frame(self, cam_pod, max_depth=10, want_ids=False, **param_overrides):
         """Renders one frame across all ranks. Returns (frame, stats): frame is an int32 CUDA tensor [H][W] of
         RGBA8888 words on rank 0 (None elsewhere); with want_ids also the object-id plane."""
@@ -151,8 +199,7 @@ class ShardedRenderer:
         H, W = cam_pods[0].height, cam_pods[0].width
         mine = frame_owner(F, self.world)[self.rank]
         if self.fused:
-            p = default_params(max_depth=max_depth, frame_offset=self.rank, frame_stride=self.world, **param_overrides)
-            return self._fused_render([cam_pods[f] for f in mine], F, H, W, p)
+            return self._pipelined_frames(cam_pods, mine, F, H, W, default_params(max_depth=max_depth, **param_overrides))
         per_rank = (F + self.world - 1) // self.world
         local = torch.zeros((per_rank, H, W), dtype=torch.int32, device=self.device)
         st = None
