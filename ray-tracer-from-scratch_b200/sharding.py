@@ -115,13 +115,25 @@ class ShardedRenderer:
             dist.all_reduce(self._token, group=self.group)
         return view, st, (st.launches if st else 0)
 
-    def _pipelined_frames(self, cam_pods, mine, F, H, W, params, chunk=8):
+    def _pipelined_frames(self, cam_pods, mine, F, H, W, params, n_chunks=4):
         """Camera path, whole frames per rank: a frame is 8 MB, so instead of scattering 4-byte pixel stores over
         NVLink (fine for one frame spread over ranks, wasteful for gigabytes) each rank renders chunks of frames into
         local double buffers and copies every finished chunk into rank 0's IPC-mapped frame set with bulk peer copies
         on a side stream, overlapped with the rendering of the next chunk."""
         ptr, view = self._shared_frame(F, H, W)
-        dest = view if self.rank == 0 else torch.as_tensor(_DevicePtr(ptr, (F, H, W)), device=self.device)
+        if self.rank == 0:
+            # rank 0 owns the frame set: one launch, pixels stored straight at their place (local stores, no copies)
+            params.frame_offset, params.frame_stride = 0, self.world
+            o = abi.Outputs()
+            o.memory, o.frame_rgba8 = abi.RTX_MEM_DEVICE, ptr
+            st = self.r.render_raw([cam_pods[f] for f in mine], params, o) if mine else None
+            if self.world > 1:
+                if self._token is None:
+                    self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
+                dist.all_reduce(self._token, group=self.group)
+            return view, st, (st.launches if st else 0)
+        dest = torch.as_tensor(_DevicePtr(ptr, (F, H, W)), device=self.device)
+        chunk = max(1, (len(mine) + n_chunks - 1) // n_chunks)
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
             self._bufs = {}
