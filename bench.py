@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="fused", choices=["fused", "allgather"],
                     help="N > 1: peer-memory stores from the trace kernel (fused) or all-gather + unpermute")
+    ap.add_argument("--verify", action="store_true",
+                    help="N > 1: rank 0 re-renders the frame(s) alone and compares them bit for bit with the gathered result")
     ap.add_argument("--scale", type=float, default=1.0, help="developer knob: shrink the frame (not a valid bench)")
     return ap.parse_args()
 
@@ -364,6 +366,27 @@ def main():
             kernel_max = kernel_ms
         return ms, rays, kernel_max, int(launches), clocks
 
+    verified = None
+    if args.verify and world > 1:
+        # every rank takes part in the sharded render; rank 0 then renders everything alone for comparison
+        if spec["name"] == "c5":
+            got, _, _ = sh.render_frames(pods, max_depth=spec["depth"])
+        else:
+            got, _, _ = sh.render_frame(pods[0], max_depth=spec["depth"])
+        torch.cuda.synchronize()
+        if rank == 0:
+            got = got.clone().reshape(len(pods), H, W)
+            ok = True
+            for f0 in range(0, len(pods), 16):
+                part = pods[f0:f0 + 16]
+                alone = torch.empty((len(part), H, W), dtype=torch.int32, device=dev)
+                o = abi.Outputs()
+                o.memory, o.rgba8 = abi.RTX_MEM_DEVICE, alone.data_ptr()
+                r.render_raw(part, R.default_params(max_depth=spec["depth"]), o)
+                ok = ok and bool(torch.equal(alone, got[f0:f0 + len(part)]))
+            verified = ok
+        dist.barrier()
+
     sampler = ClockSampler(visible_index(local_rank)) if rank == 0 else None
     ms, rays, kernel_ms, launches, clocks = timed_region(False, args.steps, args.warmup, sampler)
     ms_e, rays_e, _, _, _ = timed_region(True, max(2, min(args.steps, 5)), 1)
@@ -409,6 +432,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if verified is not None:
+            line["verified_against_single_gpu"] = verified
         if world == 1:
             # HBM side: the standalone quantise kernel (main.cpp:338-347) on a device-resident radiance frame of the
             # same size; algorithmic bytes = 12 (f32) or 24 (f64) read + 4 written per pixel; L2 flushed before each launch.
