@@ -556,7 +556,10 @@ __device__ __noinline__ void start_pixel(Chain& c, unsigned long long p, const T
 constexpr int kSmallScene = 16;       // objects
 constexpr int kSmallThreads = 256;
 
-__global__ void __launch_bounds__(kSmallThreads) trace_small_kernel(const TraceArgs a)
+#ifndef RTX_SMALL_MINBLOCKS
+#define RTX_SMALL_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(kSmallThreads, RTX_SMALL_MINBLOCKS) trace_small_kernel(const TraceArgs a)
 {
     const SceneDev& sc = a.scene;
     const unsigned lane_id = threadIdx.x & 31u;

@@ -27,6 +27,17 @@ def main():
             _, st = r.render([pod], R.default_params(max_depth=8), want=("rgba8",))
             print("c2", st.as_dict(), flush=True)
         out["c2"] = st.as_dict()
+    if "c5" in which:
+        r.set_scene(S.default_scene())
+        pods = [c.pod() for c in S.flythrough_cameras(256, 1920, 16.0 / 9.0)]
+        import torch
+        buf = torch.empty((256, 1080, 1920), dtype=torch.int32, device="cuda")
+        o = pkg.abi.Outputs()
+        o.memory, o.rgba8 = pkg.abi.RTX_MEM_DEVICE, buf.data_ptr()
+        for it in range(3):
+            st = r.render_raw(pods, R.default_params(max_depth=10), o)
+            print("c5", st.as_dict(), flush=True)
+        out["c5"] = st.as_dict()
     if "c3" in which or "c3small" in which:
         t0 = time.time()
         syn = S.synthetic_scene()
