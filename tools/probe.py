@@ -38,6 +38,17 @@ def main():
             st = r.render_raw(pods, R.default_params(max_depth=10), o)
             print("c5", st.as_dict(), flush=True)
         out["c5"] = st.as_dict()
+    for name, ns in (("big12k", 12500), ("big20k", 20000), ("big40k", 40000)):
+        if name in which:
+            r.set_scene(S.synthetic_scene(ns, 64))
+            pod = S.default_camera(1920, 16.0 / 9.0).pod()
+            for it in range(3):
+                _, st = r.render([pod], R.default_params(max_depth=10), want=("rgba8",))
+            d = st.as_dict()
+            d["tflops_algorithmic"] = (st.sphere_tests * 20 + st.wall_tests * 33) / (st.raytracing_ms * 1e-3) / 1e12
+            d["mrays_s"] = st.total_rays / (st.raytracing_ms * 1e-3) / 1e6
+            print(name, d, flush=True)
+            out[name] = d
     if "c3" in which or "c3small" in which:
         t0 = time.time()
         syn = S.synthetic_scene()
