@@ -16,7 +16,7 @@
 //    CONSERVATIVE FP32 test: squared distance from the object's centre to the ray's line, computed in a per-ray
 //    frame (u, v perpendicular to the ray): (u.c - u.o)^2 + (v.c - v.o)^2, against (r + E)^2, E bounding the FP32
 //    error (filter_eps). The projected form has no |oc|^2 - b^2 cancellation: its error grows with |c|, not |c|^2.
-//    Walls take part through their bounding sphere. The screen is 8 packed FFMA2 (fma.rn.f32x2, two entries per
+//    Walls take part through their bounding sphere. The screen is 7 packed FFMA2 (fma.rn.f32x2, two entries per
 //    instruction) + 2 funnel shifts per two pairs; each broadcast LDS.128 feeds four pairs (2 entries x 2 chains).
 //    Survivors (a few per ray) are queued per chain and, after the scan, evaluated with the reference's own
 //    double arithmetic, operation for operation, many lanes at a time, and compared with the reference's rule
@@ -125,11 +125,14 @@ struct Chain {
 
 // Screen constants of one chain: two unit axes u, v spanning the plane perpendicular to the ray, and -u.o, -v.o.
 // The squared distance from a centre c to the ray's line is (u.c - u.o)^2 + (v.c - v.o)^2.
+// u = normalize(d^ x z) has no z component for ANY ray, so u.c costs two FMAs instead of three — uniformly across
+// the warp, which is what matters in SIMT (v = d^ x u is general). Rays (anti)parallel to z within 1e-10 take the
+// exact fallback.
 // Kept as scalars and widened with dup() at each use, so that ptxas emits the FFMA2 operand form that broadcasts
 // ONE 32-bit register to both halves (".F32") instead of reading a pair: register-file bandwidth, not the FMA
 // pipe, bounds the screen.
 struct Packed {
-    float ux, uy, uz, nuo, vx, vy, vz, nvo;
+    float ux, uy, nuo, vx, vy, vz, nvo;    // u is chosen perpendicular to the z axis: uz == 0 for every ray
 };
 
 __device__ __forceinline__ float2 dup(float v) { return make_float2(v, v); }
@@ -149,7 +152,7 @@ __device__ __forceinline__ Packed setup_chain(Chain& c, float origin_bound)
     Packed k;
     if (!c.active) {
         // idle chain (only while the frame drains): m = -k is huge, nothing passes
-        k.ux = k.uy = k.uz = k.vx = k.vy = k.vz = 0.f;
+        k.ux = k.uy = k.vx = k.vy = k.vz = 0.f;
         k.nuo = k.nvo = 1e15f;          // pu = pv = 1e15: nothing passes
         c.qn = 0;
         c.fallback = 0;
@@ -163,16 +166,13 @@ __device__ __forceinline__ Packed setup_chain(Chain& c, float origin_bound)
     c.qn = 0;
     const double inv = 1.0 / c.dlen;
     const double hx = c.d.x * inv, hy = c.d.y * inv, hz = c.d.z * inv;      // d^ (plain double: not a parity value)
-    // u = normalize(d^ x e), e = the coordinate axis least aligned with d^; v = d^ x u
-    const double ax = fabs(hx), ay = fabs(hy), az = fabs(hz);
-    double ex = 0.0, ey = 0.0, ez = 0.0;
-    if (ax <= ay && ax <= az) ex = 1.0; else if (ay <= az) ey = 1.0; else ez = 1.0;
-    double ux = hy * ez - hz * ey, uy = hz * ex - hx * ez, uz = hx * ey - hy * ex;
-    const double un = rsqrt(ux * ux + uy * uy + uz * uz);
-    ux *= un; uy *= un; uz *= un;
+    // u = normalize(d^ x z) = (hy, -hx, 0) / sqrt(hx^2 + hy^2); v = d^ x u
+    const double hxy2 = hx * hx + hy * hy;
+    const double un = rsqrt(hxy2);
+    const double ux = hy * un, uy = -hx * un, uz = 0.0;
     const double vx = hy * uz - hz * uy, vy = hz * ux - hx * uz, vz = hx * uy - hy * ux;
     // the FMAs see the ROUNDED axes: the offsets must be computed from those
-    const float fux = static_cast<float>(ux), fuy = static_cast<float>(uy), fuz = static_cast<float>(uz);
+    const float fux = static_cast<float>(ux), fuy = static_cast<float>(uy);
     const float fvx = static_cast<float>(vx), fvy = static_cast<float>(vy), fvz = static_cast<float>(vz);
     const float fx = static_cast<float>(hx), fy = static_cast<float>(hy), fz = static_cast<float>(hz);
     c.fdx = fx;
@@ -181,16 +181,16 @@ __device__ __forceinline__ Packed setup_chain(Chain& c, float origin_bound)
     c.fd_o = static_cast<float>(static_cast<double>(fx) * c.o.x + static_cast<double>(fy) * c.o.y + static_cast<double>(fz) * c.o.z);
     c.inv_dlen_lo = __double2float_rd(inv) * 0.999999f;
     const double om = fmax(fabs(c.o.x), fmax(fabs(c.o.y), fabs(c.o.z)));
-    const bool ok = (om <= static_cast<double>(origin_bound)) && (c.dlen > 0.0) && (c.dlen < 1e300);
+    const bool ok = (om <= static_cast<double>(origin_bound)) && (c.dlen > 0.0) && (c.dlen < 1e300) && (hxy2 > 1e-20);
     c.fallback = ok ? 0 : 1;
     if (ok) {
-        k.ux = fux; k.uy = fuy; k.uz = fuz;
+        k.ux = fux; k.uy = fuy;
         k.vx = fvx; k.vy = fvy; k.vz = fvz;
-        k.nuo = -static_cast<float>(static_cast<double>(fux) * c.o.x + static_cast<double>(fuy) * c.o.y + static_cast<double>(fuz) * c.o.z);
+        k.nuo = -static_cast<float>(static_cast<double>(fux) * c.o.x + static_cast<double>(fuy) * c.o.y);
         k.nvo = -static_cast<float>(static_cast<double>(fvx) * c.o.x + static_cast<double>(fvy) * c.o.y + static_cast<double>(fvz) * c.o.z);
     } else {
         // pu = pv = 0 for every entry -> q - w = -w < 0 -> everything passes; NaN makes the second screen pass too
-        k.ux = k.uy = k.uz = k.vx = k.vy = k.vz = k.nuo = k.nvo = 0.f;
+        k.ux = k.uy = k.vx = k.vy = k.vz = k.nuo = k.nvo = 0.f;
         c.fdx = c.fdy = c.fdz = c.fd_o = __int_as_float(0x7fc00000);
     }
     return k;
@@ -248,7 +248,7 @@ __device__ __forceinline__ float4 lds128(unsigned addr)
 
 // The packed screen of kPairsPerIter entry pairs against one chain; returns the sign history (one bit per entry,
 // first entry in the highest of the 2*kPairsPerIter low bits).
-//   pu = u.c - u.o,  pv = v.c - v.o,  q - w = pu^2 + pv^2 - w      8 FFMA2 per two entries
+//   pu = u.c - u.o (u has no z component),  pv = v.c - v.o,  q - w = pu^2 + pv^2 - w      7 FFMA2 per two entries
 // Written constant-major (the same per-ray constant through all pairs before the next constant): the FMA pipe
 // accepts one FFMA2 per two cycles only if the instruction reads at most four fresh registers.
 __device__ __forceinline__ unsigned screen_pairs(const float2 (&cx)[kPairsPerIter], const float2 (&cy)[kPairsPerIter],
@@ -256,14 +256,12 @@ __device__ __forceinline__ unsigned screen_pairs(const float2 (&cx)[kPairsPerIte
                                                  const Packed& k)
 {
     float2 pu[kPairsPerIter], pv[kPairsPerIter], q[kPairsPerIter];
-    const float2 ux = dup(k.ux), uy = dup(k.uy), uz = dup(k.uz), nuo = dup(k.nuo);
+    const float2 ux = dup(k.ux), uy = dup(k.uy), nuo = dup(k.nuo);
     const float2 vx = dup(k.vx), vy = dup(k.vy), vz = dup(k.vz), nvo = dup(k.nvo);
-#pragma unroll
-    for (int u = 0; u < kPairsPerIter; u++) pu[u] = __ffma2_rn(cz[u], uz, nuo);
 #pragma unroll
     for (int u = 0; u < kPairsPerIter; u++) pv[u] = __ffma2_rn(cz[u], vz, nvo);
 #pragma unroll
-    for (int u = 0; u < kPairsPerIter; u++) pu[u] = __ffma2_rn(cy[u], uy, pu[u]);
+    for (int u = 0; u < kPairsPerIter; u++) pu[u] = __ffma2_rn(cy[u], uy, nuo);
 #pragma unroll
     for (int u = 0; u < kPairsPerIter; u++) pv[u] = __ffma2_rn(cy[u], vy, pv[u]);
 #pragma unroll
@@ -329,7 +327,7 @@ __device__ __forceinline__ float2 screen_one(const float4 p0, const float4 p1, c
 {
     const float2 cx = make_float2(p0.x, p0.y), cy = make_float2(p0.z, p0.w);
     const float2 cz = make_float2(p1.x, p1.y), nw = make_float2(p1.z, p1.w);
-    const float2 pu = __ffma2_rn(cx, dup(k.ux), __ffma2_rn(cy, dup(k.uy), __ffma2_rn(cz, dup(k.uz), dup(k.nuo))));
+    const float2 pu = __ffma2_rn(cx, dup(k.ux), __ffma2_rn(cy, dup(k.uy), dup(k.nuo)));
     const float2 pv = __ffma2_rn(cx, dup(k.vx), __ffma2_rn(cy, dup(k.vy), __ffma2_rn(cz, dup(k.vz), dup(k.nvo))));
     return __ffma2_rn(pu, pu, __ffma2_rn(pv, pv, nw));
 }
@@ -343,7 +341,7 @@ __device__ __forceinline__ void post(Mailbox* mb, int which, int entry)
 __device__ __forceinline__ Packed bcast(const Packed& k, int src)
 {
     Packed r;
-    r.ux = __shfl_sync(kFull, k.ux, src); r.uy = __shfl_sync(kFull, k.uy, src); r.uz = __shfl_sync(kFull, k.uz, src);
+    r.ux = __shfl_sync(kFull, k.ux, src); r.uy = __shfl_sync(kFull, k.uy, src);
     r.nuo = __shfl_sync(kFull, k.nuo, src);
     r.vx = __shfl_sync(kFull, k.vx, src); r.vy = __shfl_sync(kFull, k.vy, src); r.vz = __shfl_sync(kFull, k.vz, src);
     r.nvo = __shfl_sync(kFull, k.nvo, src);
@@ -703,7 +701,7 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
                         have[c] = pop_chain(r0, r1, src[c], which[c]);
                         kc[c] = bcast(which[c] ? k1 : k0, src[c]);
                         if (!have[c]) {
-                            kc[c].ux = kc[c].uy = kc[c].uz = kc[c].vx = kc[c].vy = kc[c].vz = 0.f;
+                            kc[c].ux = kc[c].uy = kc[c].vx = kc[c].vy = kc[c].vz = 0.f;
                             kc[c].nuo = kc[c].nvo = 1e15f;
                         }
                     }
