@@ -40,7 +40,10 @@ namespace rtx {
 constexpr int kThreads = RTX_THREADS; // 16 warps per SM, 4 per scheduler
 constexpr int kChains = 2;            // pixels in flight per lane
 constexpr int kPairsPerIter = RTX_PAIRS;   // entry pairs per hot-loop iteration (6 pairs = 12 entries x 2 chains = 96 FFMA2)
-constexpr int kQueue = 24;            // screen survivors buffered per chain before an early flush
+#ifndef RTX_QUEUE_CAP
+#define RTX_QUEUE_CAP 24
+#endif
+constexpr int kQueue = RTX_QUEUE_CAP; // screen survivors buffered per chain before an early flush
 #ifndef RTX_COOP_MAX
 #define RTX_COOP_MAX 32
 #endif

@@ -323,19 +323,27 @@ def test_scene_larger_than_shared_memory_streams_tiles(gpu, renderer_mod, port, 
     assert st.sphere_tests == st.total_rays * 16000
 
 
-def test_cooperative_drain_mailbox_overflow_redoes_the_segment(tmp_path, renderer_mod, port, S):
-    """The cooperative drain posts screen survivors through a fixed-size mailbox; if it overflows the segment is
-    redone the ordinary way. Build the library with a 1-slot mailbox to force that path and check parity."""
+@pytest.mark.parametrize("flag", ["-DRTX_MBOX_CAP=1", "-DRTX_QUEUE_CAP=1"])
+def test_overflow_paths_of_the_trace_kernel(tmp_path, renderer_mod, port, S, flag):
+    """Two fixed-size buffers of the trace kernel have overflow paths that ordinary scenes rarely take:
+    the cooperative drain's per-warp mailbox (overflow: the segment is redone the ordinary way) and a chain's queue of
+    screen survivors (full: flushed early, in the middle of the scan). Build the library with 1-slot buffers to force
+    those paths everywhere and check parity."""
     import os
     import subprocess
     pkg_dir = os.path.dirname(os.path.abspath(renderer_mod.__file__))
     root = os.path.dirname(pkg_dir)
-    lib = str(tmp_path / "librtx_b200_mbox1.so")
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off",
-                    "-DRTX_MBOX_CAP=1", "-I" + os.path.join(root, "include"), "-I" + os.path.join(pkg_dir, "csrc"), "-shared",
-                    os.path.join(pkg_dir, "csrc", "api.cu"), os.path.join(pkg_dir, "csrc", "trace.cu"),
-                    os.path.join(pkg_dir, "csrc", "aux_kernels.cu"), "-o", lib], check=True)
+    sources = [os.path.join(pkg_dir, "csrc", f) for f in ("api.cu", "trace.cu", "aux_kernels.cu")]
+    lib = os.path.join(pkg_dir, "test_builds", "librtx_b200_%s.so" % flag[2:])      # prebuilt by build.sh
+    headers = [os.path.join(pkg_dir, "csrc", "rtx_device.cuh"), os.path.join(root, "include", "rtx_b200.h")]
+    digest = hashlib.sha256(b"".join(open(f, "rb").read() for f in sources + headers)).hexdigest()
+    stamp = os.path.join(pkg_dir, "test_builds", "SOURCES.sha256")
+    if not (os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == digest):   # stale or absent
+        lib = str(tmp_path / "librtx_b200_small_buffers.so")
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off",
+                        flag, "-I" + os.path.join(root, "include"), "-I" + os.path.join(pkg_dir, "csrc"), "-shared"] + sources + ["-o", lib],
+                       check=True)
     code = r"""
 import importlib, os, sys
 import numpy as np
@@ -357,6 +365,25 @@ print("ok")
     env = dict(os.environ, RTX_B200_LIB=lib)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n_row,n_other", [(2400, 40), (3000, 11000)])
+def test_ray_threading_thousands_of_spheres_flushes_the_survivor_queue(gpu, renderer_mod, port, S, n_row, n_other):
+    """Thousands of nested spheres around the central line of sight: the central lanes find screen survivors in every
+    hot-loop iteration, far more than a chain's queue holds, so the early flush runs many times per ray (second
+    case: scene larger than shared memory, i.e. with tile streaming)."""
+    rng = np.random.default_rng(n_row)
+    mat = S.Material((0.9, 0.5, 0.2), 0.3)
+    xs = [60.0 - 58.0 * i / n_row for i in range(n_row)]          # a cone of nested spheres around the view axis
+    scene = [S.Sphere(mat, (x, 1e-3 * np.sin(i), 1e-3 * np.cos(i)), 0.15 * x * (0.8 + 0.1 * (i % 3))) for i, x in enumerate(xs)]
+    for i in range(n_other):
+        c = rng.uniform((4, -32, -8), (64, 32, 24))
+        scene.append(S.Sphere(S.Material(tuple(rng.uniform(0.1, 1, 3)), float(rng.uniform(0, 0.8))), tuple(c), float(rng.uniform(0.1, 0.6))))
+    scene.append(S.Wall(S.Material((0.2, 0.3, 0.9), 0.4), (70.0, -5.0, -5.0), (-1.0, 0.0, 0.0), 10.0, 10.0))
+    pod = S.default_camera(49, 16.0 / 9.0).pod()                  # odd size: the centre pixel looks exactly along the axis
+    got, st = render(gpu, renderer_mod, scene, pod, 3)
+    check_frame(got, port.render(scene, pod, 3), st)
+    assert (got["object_id"] >= 0).sum() > 8
 
 
 def test_fused_frame_output_places_pixels_globally(gpu, renderer_mod, port, S, syn, pkg):
