@@ -39,6 +39,8 @@ class Oracle:
         f("abi_version", C.c_int)
         f("max_threads", C.c_int)
         f("camera_init", None, C.POINTER(abi.CameraDesc), C.POINTER(abi.CameraPOD))
+        f("camera_walk", None, C.POINTER(abi.CameraDesc), C.c_char_p, C.POINTER(C.c_double), C.c_int32,
+          C.POINTER(C.c_double), C.POINTER(abi.CameraPOD))
         f("render_rows", C.c_double, C.POINTER(abi.ObjectPOD), C.c_int32, C.POINTER(abi.CameraPOD), C.c_int32,
           C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_uint32),
           C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.POINTER(C.c_uint64))
@@ -81,6 +83,18 @@ class Oracle:
         d = cam.desc()
         self._camera_init(C.byref(d), C.byref(out))
         return out
+
+    def camera_walk(self, cam, steps):
+        """Camera::init once, then one Camera method per step (scene.cpp:108-165); steps = [(op, arg), ...] with op in
+        'wsad' (moves), 'y' (rotate_left_right(arg)), 'p' (rotate_up_down(arg)). Returns (states [n][3][3] =
+        position, direction, vup after every step; abi.CameraPOD after the last step)."""
+        ops = "".join(op for op, _ in steps).encode()
+        args = np.ascontiguousarray([float(a) for _, a in steps], dtype=np.float64)
+        states = np.zeros((len(steps), 3, 3), np.float64)
+        out = abi.CameraPOD()
+        d = cam.desc()
+        self._camera_walk(C.byref(d), ops, _ptr(args, C.c_double), len(steps), _ptr(states, C.c_double), C.byref(out))
+        return states, out
 
     def render(self, scene, cam_pod, max_depth=10, rows=None, threads=0, want=("radiance", "rgba8", "object_id",
                                                                                  "hit_mask", "ray_count"),

@@ -280,6 +280,71 @@ void orc_camera_init(const rtx_camera_desc* d, rtx_camera* out)
     out->height = (int32_t)image_height;
 }
 
+/* Camera moves (scene.cpp:108-165). The state the reference's methods read and write is (position, direction, vup);
+ * init() sets direction = normalize(position - lookat) (scene.cpp:93) and is never re-run by a move (main.cpp:154 vs
+ * :262-306), so image_top_left and the pixel deltas stay those of init().
+ *   forward_vec = normalize(direction); right_vec = normalize(cross(direction, vup));
+ *   up_vec = normalize(cross(right_vec, direction))                                             scene.cpp:108-119
+ *   forward/backward/right/left: position +- vec * movement_speed                                scene.cpp:121-135
+ *   rotate_left_right(angle): yaw around z through atan2/cos/sin, then vup = up_vec()            scene.cpp:137-145
+ *   rotate_up_down(angle): pitch through atan2/sin/cos; beyond +pi/2 the pitch is kept, beyond -pi/2 it becomes
+ *   MINUS the old pitch (the reference's own asymmetry, scene.cpp:155-156); then vup = up_vec()  scene.cpp:147-165
+ * ops: 'w' 's' 'a' 'd' as the keys of main.cpp:262-306, 'y' = rotate_left_right(args[k]), 'p' = rotate_up_down(args[k]).
+ * state_out: position, direction, vup after every step (9 doubles each). */
+#define ORC_PI 3.14159265358979323846   /* glibc's M_PI (scene.cpp:155-156); -std=c11 hides the macro */
+static v3 cam_right_vec(v3 direction, v3 vup) { return unit(cross(direction, vup)); }
+static v3 cam_up_vec(v3 direction, v3 vup) { return unit(cross(cam_right_vec(direction, vup), direction)); }
+
+void orc_camera_walk(const rtx_camera_desc* d, const char* ops, const double* args, int32_t n_ops, double* state_out,
+                     rtx_camera* cam_out)
+{
+    const double movement_speed = 0.1;                       /* main.cpp:149 */
+    rtx_camera c;
+    orc_camera_init(d, &c);
+    v3 position = d->position, vup = d->vup;
+    v3 direction = unit(sub(d->position, d->lookat));        /* scene.cpp:93 */
+    for (int32_t k = 0; k < n_ops; k++) {
+        switch (ops[k]) {
+            case 'w': position = add(position, scale(unit(direction), movement_speed)); break;
+            case 's': position = sub(position, scale(unit(direction), movement_speed)); break;
+            case 'd': position = add(position, scale(cam_right_vec(direction, vup), movement_speed)); break;
+            case 'a': position = sub(position, scale(cam_right_vec(direction, vup), movement_speed)); break;
+            case 'y': {
+                double current_angle = atan2(direction.y, direction.x);
+                double new_angle = current_angle + args[k];
+                double base_length = len(mk(direction.x, direction.y, 0));
+                direction = mk(cos(new_angle) * base_length, sin(new_angle) * base_length, direction.z);
+                vup = cam_up_vec(direction, vup);
+                break;
+            }
+            case 'p': {
+                double base_length = len(mk(direction.x, direction.y, 0));
+                double pitch_angle = atan2(direction.z, base_length);
+                double new_pitch_angle = pitch_angle + args[k];
+                new_pitch_angle = new_pitch_angle > ORC_PI / 2 ? pitch_angle : new_pitch_angle;
+                new_pitch_angle = new_pitch_angle < -ORC_PI / 2 ? -pitch_angle : new_pitch_angle;
+                double new_z = sin(new_pitch_angle);
+                double new_base_length = cos(new_pitch_angle);
+                v3 new_base_vector = scale(unit(mk(direction.x, direction.y, 0)), new_base_length);
+                direction = mk(new_base_vector.x, new_base_vector.y, new_z);
+                vup = cam_up_vec(direction, vup);
+                break;
+            }
+            default: break;
+        }
+        const v3 st[3] = {position, direction, vup};
+        for (int i = 0; i < 3; i++) {
+            state_out[9 * k + 3 * i + 0] = st[i].x;
+            state_out[9 * k + 3 * i + 1] = st[i].y;
+            state_out[9 * k + 3 * i + 2] = st[i].z;
+        }
+    }
+    if (cam_out) {
+        *cam_out = c;
+        cam_out->position = position;
+    }
+}
+
 /* The loop body of rt_scene (main.cpp:129-136) over the given global rows, packed [n_rows][width];
  * every output plane is optional. Returns seconds spent in the loop, -1 on bad arguments. */
 double orc_render_rows_params(const rtx_object* objs, int32_t n_objs, const rtx_camera* cam, const rtx_params* p,

@@ -160,6 +160,52 @@ void ref_camera_init(const rtx_camera_desc* d, rtx_camera* out)
 }
 
 /*
+ * Camera moves through the reference class (scene.cpp:108-165): init() once, then one method per step.
+ * ops[k]: 'w' forward, 's' backward, 'a' left, 'd' right (the keys of main.cpp:262-306), 'y' rotate_left_right(args[k]),
+ * 'p' rotate_up_down(args[k]) (the mouse look main.cpp:319-323 leaves commented out). init() is NOT re-run, exactly
+ * like the reference's main loop. state_out receives position, direction, vup (9 doubles) after every step; cam_out
+ * what rt_scene would consume after the last step (image_top_left and the deltas are still those of init()).
+ */
+void ref_camera_walk(const rtx_camera_desc* d, const char* ops, const double* args, int32_t n_ops, double* state_out,
+                     rtx_camera* cam_out)
+{
+    Camera cam;
+    cam.aspect_ratio = d->aspect_ratio;
+    cam.image_width = d->image_width;
+    cam.movement_speed = 0.1;
+    cam.vfov = d->vfov;
+    cam.position = V(d->position);
+    cam.lookat = V(d->lookat);
+    cam.vup = V(d->vup);
+    std::vector<vec3> u = cam.init();
+    for (int32_t k = 0; k < n_ops; k++) {
+        switch (ops[k]) {
+            case 'w': cam.forward(); break;
+            case 's': cam.backward(); break;
+            case 'a': cam.left(); break;
+            case 'd': cam.right(); break;
+            case 'y': cam.rotate_left_right(args[k]); break;
+            case 'p': cam.rotate_up_down(args[k]); break;
+            default: break;
+        }
+        const vec3 st[3] = {cam.position, cam.direction, cam.vup};
+        for (int i = 0; i < 3; i++) {
+            state_out[9 * k + 3 * i + 0] = st[i].x;
+            state_out[9 * k + 3 * i + 1] = st[i].y;
+            state_out[9 * k + 3 * i + 2] = st[i].z;
+        }
+    }
+    if (cam_out) {
+        cam_out->position = P(cam.position);
+        cam_out->image_top_left = P(cam.image_top_left);
+        cam_out->delta_x = P(u[0]);
+        cam_out->delta_y = P(u[1]);
+        cam_out->width = static_cast<int32_t>(cam.image_width);
+        cam_out->height = static_cast<int32_t>(cam.image_height);
+    }
+}
+
+/*
  * Renders the given global rows (rows[k], k < n_rows) of one frame; outputs are packed [n_rows][width].
  * radiance comes from recursive_ray_tracing (main.cpp:89); object_id / hit_mask / ray_count (any may be
  * NULL) come from walking the same chain with find_closest_hit + vec3::reflect. Returns the seconds spent

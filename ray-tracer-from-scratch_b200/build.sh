@@ -31,3 +31,7 @@ g++ -std=c++17 -O2 -ffp-contract=off -Wall -I"$here/../include" -I"$here/host" \
     "$here/examples/headless_main.cpp" -o "$here/rtx_headless" \
     -L"$here" -lrtx_b200 -Wl,-rpath,'$ORIGIN'
 echo "built $here/rtx_headless"
+g++ -std=c++17 -O2 -ffp-contract=off -Wall -I"$here/../include" -I"$here/host" \
+    "$here/examples/camera_walk.cpp" -o "$here/rtx_camera_walk" \
+    -L"$here" -lrtx_b200 -Wl,-rpath,'$ORIGIN'
+echo "built $here/rtx_camera_walk"

@@ -129,6 +129,11 @@ int main(int argc, char* argv[])
                     case 's': cam.backward(); break;
                     case 'a': cam.left(); break;
                     case 'd': cam.right(); break;
+                    // the mouse look of main.cpp:319-323 (commented out there) at full deflection, x_input / y_input = -+1
+                    case 'j': cam.rotate_left_right(0.05); break;
+                    case 'l': cam.rotate_left_right(-0.05); break;
+                    case 'i': cam.rotate_up_down(0.05); break;
+                    case 'k': cam.rotate_up_down(-0.05); break;
                     default: break;
                 }
             }

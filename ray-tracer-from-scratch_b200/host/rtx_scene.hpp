@@ -126,6 +126,7 @@ using Scene = std::vector<std::unique_ptr<SceneGeometry>>;
 class Camera {
     vec3 forward_vec() const { return direction.normalize(); }
     vec3 right_vec() const { return vec3::cross(direction, vup).normalize(); }
+    vec3 up_vec() const { return vec3::cross(right_vec(), direction).normalize(); }             // scene.cpp:116-119
 public:
     vec3 direction, image_top_left;
     double movement_speed = 0.1, aspect_ratio = 1.0, image_width = 640, image_height = 0, focal_length = 0, vfov = 90;
@@ -150,6 +151,30 @@ public:
     void backward() { position = position - forward_vec() * movement_speed; }
     void right() { position = position + right_vec() * movement_speed; }
     void left() { position = position - right_vec() * movement_speed; }
+    // The mouse look the reference implements but leaves commented out in its loop (scene.cpp:137-165,
+    // main.cpp:319-323). They change direction and vup only; init() ignores `direction`, so like the reference a
+    // rotation shows in the image only through later right()/left() moves unless the caller re-aims lookat itself.
+    void rotate_left_right(double angle)
+    {
+        const double current_angle = std::atan2(direction.y, direction.x);
+        const double new_angle = current_angle + angle;
+        const double base_length = vec3(direction.x, direction.y, 0).length();
+        direction = vec3(std::cos(new_angle) * base_length, std::sin(new_angle) * base_length, direction.z);
+        vup = up_vec();
+    }
+    void rotate_up_down(double angle)
+    {
+        const double base_length = vec3(direction.x, direction.y, 0).length();
+        const double pitch_angle = std::atan2(direction.z, base_length);
+        double new_pitch_angle = pitch_angle + angle;
+        new_pitch_angle = new_pitch_angle > M_PI / 2 ? pitch_angle : new_pitch_angle;
+        new_pitch_angle = new_pitch_angle < -M_PI / 2 ? -pitch_angle : new_pitch_angle;     // sic (scene.cpp:156)
+        const double new_z = std::sin(new_pitch_angle);
+        const double new_base_length = std::cos(new_pitch_angle);
+        const vec3 new_base_vector = vec3(direction.x, direction.y, 0).normalize() * new_base_length;
+        direction = vec3(new_base_vector.x, new_base_vector.y, new_z);
+        vup = up_vec();
+    }
 
     rtx_camera pod(const std::vector<vec3>& u) const
     {

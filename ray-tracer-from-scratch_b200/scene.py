@@ -167,6 +167,52 @@ class Camera:
         self.u = [pixel_delta_x, pixel_delta_y]
         return self.u
 
+    # -- moves (scene.cpp:108-165). Like the reference's main loop (main.cpp:154 vs :262-306) they do NOT re-run
+    #    init(): image_top_left and the pixel deltas stay where init() put them, only `position` feeds rt_scene.
+    def forward_vec(self):
+        return _normalize(_v(self.direction))                                        # scene.cpp:108-110
+
+    def right_vec(self):
+        return _normalize(_cross(_v(self.direction), _v(self.vup)))                  # scene.cpp:112-114
+
+    def up_vec(self):
+        return _normalize(_cross(self.right_vec(), _v(self.direction)))              # scene.cpp:116-119
+
+    def forward(self):
+        self.position = _add(_v(self.position), _mul(self.forward_vec(), self.movement_speed))    # scene.cpp:121-123
+
+    def backward(self):
+        self.position = _sub(_v(self.position), _mul(self.forward_vec(), self.movement_speed))    # scene.cpp:125-127
+
+    def right(self):
+        self.position = _add(_v(self.position), _mul(self.right_vec(), self.movement_speed))      # scene.cpp:129-131
+
+    def left(self):
+        self.position = _sub(_v(self.position), _mul(self.right_vec(), self.movement_speed))      # scene.cpp:133-135
+
+    def rotate_left_right(self, angle):
+        """scene.cpp:137-145: yaw about z through atan2 / cos / sin, then vup = up_vec()."""
+        dx, dy, dz = _v(self.direction)
+        new_angle = math.atan2(dy, dx) + angle
+        base_length = _length((dx, dy, 0.0))
+        self.direction = (math.cos(new_angle) * base_length, math.sin(new_angle) * base_length, dz)
+        self.vup = self.up_vec()
+
+    def rotate_up_down(self, angle):
+        """scene.cpp:147-165: pitch through atan2 / sin / cos. Past +pi/2 the old pitch is kept, past -pi/2 it becomes
+        MINUS the old pitch (the reference's own asymmetry, scene.cpp:155-156). Then vup = up_vec()."""
+        dx, dy, dz = _v(self.direction)
+        base_length = _length((dx, dy, 0.0))
+        pitch_angle = math.atan2(dz, base_length)
+        new_pitch_angle = pitch_angle + angle
+        new_pitch_angle = pitch_angle if new_pitch_angle > math.pi / 2 else new_pitch_angle
+        new_pitch_angle = -pitch_angle if new_pitch_angle < -math.pi / 2 else new_pitch_angle
+        new_z = math.sin(new_pitch_angle)
+        new_base_length = math.cos(new_pitch_angle)
+        nb = _mul(_normalize((dx, dy, 0.0)), new_base_length)
+        self.direction = (nb[0], nb[1], new_z)
+        self.vup = self.up_vec()
+
     def pod(self):
         """rtx_camera: what rt_scene consumes (main.cpp:132-134). Runs init() if it has not been run."""
         if self.u is None:

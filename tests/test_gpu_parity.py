@@ -311,6 +311,15 @@ def test_cpp_headless_main_matches_reference_main_loop(tmp_path, port, S, render
     pod2.position = type(pod2.position)(pos_x, 0.1, 0.0)    # right_vec = normalize(cross(direction, vup)) = (0,1,0)
     exp2 = port.render(S.default_scene(), pod2, 10, want=("rgba8",))["rgba8"]
     assert np.array_equal(np.fromfile(raw2, dtype=np.uint32).reshape(200, 200), exp2)
+    # moves interleaved with the mouse-look rotations (scene.cpp:137-165; keys j/l/i/k = rotate_left_right(+-0.05) /
+    # rotate_up_down(+-0.05)): a rotation changes right_vec and so the later a/d moves; expected camera from the oracle's walk
+    raw3 = tmp_path / "h.rgba"
+    subprocess.run([exe, "--width", "160", "--frames", "9", "--keys", "xjjdikkaw", "--raw", str(raw3), "--out", ""], check=True, capture_output=True)
+    steps = [("y", 0.05), ("y", 0.05), ("d", 0), ("p", 0.05), ("p", -0.05), ("p", -0.05), ("a", 0), ("w", 0)]
+    states, pod3 = port.camera_walk(S.default_camera(160, 1.0), steps)
+    assert abs(states[-1][0][1]) > 1e-4                     # the yaw really moved the camera sideways differently
+    exp3 = port.render(S.default_scene(), pod3, 10, want=("rgba8",))["rgba8"]
+    assert np.array_equal(np.fromfile(raw3, dtype=np.uint32).reshape(160, 160), exp3)
 
 
 def test_scene_larger_than_shared_memory_streams_tiles(gpu, renderer_mod, port, S):

@@ -6,6 +6,7 @@ include/rtx_b200.h, answer its host-only entry points, and REFUSE to create a co
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -128,3 +129,76 @@ def test_flythrough_cameras_keep_focal_length_one(S):
 
 def test_status_strings(lib):
     assert lib.rtx_status_string(0) == b"ok" and b"invalid" in lib.rtx_status_string(1)
+
+
+# ---- camera moves (scene.cpp:108-165): golden walks generated from the unmodified reference ---------------------------
+
+def _walks():
+    return load_json("camera_walks.json")["walks"]
+
+
+def _camera_of(S, w):
+    cam = S.Camera()
+    c = w["camera"]
+    cam.position, cam.lookat, cam.vup = fh3(c["position"]), fh3(c["lookat"]), fh3(c["vup"])
+    cam.vfov, cam.aspect_ratio, cam.image_width = c["vfov"], float.fromhex(c["aspect_ratio"]), c["image_width"]
+    return cam
+
+
+def _same(got, exp):
+    got, exp = np.asarray(got, np.float64), np.asarray(exp, np.float64)
+    return np.array_equal(got.view(np.uint64), exp.view(np.uint64)) or np.array_equal(got, exp)   # (-0.0 == 0.0 is fine)
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_camera_walk_python_mirror_matches_reference(S, idx):
+    """scene.Camera.forward/backward/left/right/rotate_*: bit for bit the reference's position / direction / vup after
+    every step of the golden walks; init() is not re-run, so image_top_left stays that of init()."""
+    w = _walks()[idx]
+    cam = _camera_of(S, w)
+    cam.init()
+    top_left = tuple(cam.image_top_left)
+    for (op, arg), state in zip(w["steps"], w["states"]):
+        if op in "wsad":
+            {"w": cam.forward, "s": cam.backward, "a": cam.left, "d": cam.right}[op]()
+        elif op == "y":
+            cam.rotate_left_right(arg)
+        else:
+            cam.rotate_up_down(arg)
+        exp = [fh3(v) for v in state]
+        assert _same([cam.position, cam.direction, cam.vup], exp), (op, arg)
+    pod = cam.pod()
+    assert _same([pod.position.x, pod.position.y, pod.position.z], fh3(w["final_pod"]["position"]))
+    assert tuple(cam.image_top_left) == top_left and _same(top_left, fh3(w["final_pod"]["image_top_left"]))
+    assert (pod.width, pod.height) == (w["final_pod"]["width"], w["final_pod"]["height"])
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_camera_walk_oracle_port_matches_reference(port, S, idx):
+    w = _walks()[idx]
+    states, pod = port.camera_walk(_camera_of(S, w), [(op, arg) for op, arg in w["steps"]])
+    assert _same(states, [[fh3(v) for v in st] for st in w["states"]])
+    assert _same([pod.position.x, pod.position.y, pod.position.z], fh3(w["final_pod"]["position"]))
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_camera_walk_cpp_facade_matches_reference(pkg, idx):
+    """host/rtx_scene.hpp's Camera through examples/camera_walk.cpp (host code only: runs without a GPU)."""
+    exe = os.path.join(os.path.dirname(os.path.abspath(pkg.__file__)), "rtx_camera_walk")
+    if not os.path.exists(exe):
+        subprocess.check_call([os.path.join(os.path.dirname(exe), "build.sh")])
+    w = _walks()[idx]
+    c = w["camera"]
+    argv = [exe] + c["position"] + c["lookat"] + c["vup"] + [repr(float(c["vfov"])), c["aspect_ratio"], repr(float(c["image_width"]))]
+    argv += [op if op in "wsad" else "%s:%s" % (op, float(arg).hex()) for op, arg in w["steps"]]
+    out = subprocess.run(argv, capture_output=True, text=True, check=True).stdout.split("\n")
+    got = [[float.fromhex(x) for x in line.split()] for line in out if line.strip()]
+    exp = [[float.fromhex(x) for vec in st for x in vec] for st in w["states"]]
+    assert _same(got, exp)
+
+
+def test_camera_walk_reference_build_agrees_with_golden(ref, S):
+    """Where oracle/_ref exists: the golden file is what the unmodified reference computes now."""
+    for w in _walks():
+        states, _ = ref.camera_walk(_camera_of(S, w), [(op, arg) for op, arg in w["steps"]])
+        assert _same(states, [[fh3(v) for v in st] for st in w["states"]])
