@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RTX_ABI_VERSION 2
+#define RTX_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------- */
 #define RTX_OK              0
@@ -58,19 +58,24 @@ typedef struct rtx_material {
 
 #define RTX_SPHERE 0   /* Sphere(Material, point3 center, double radius)              scene.h:75-84  */
 #define RTX_WALL   1   /* Wall(Material, point3 position, vec3 normal, length, width) scene.h:62-73  */
+#define RTX_BOX    2   /* EXTENSION (no reference code: README.md:21 names a sprint-2 `Box`, the snapshot has none; parity
+                          unpinned, the specification is oracle/oracle.c::box_intersect). Axis-aligned box = six Wall-like
+                          faces -x,+x,-y,+y,-z,+z, each with Wall::intersect's arithmetic (scene.cpp:7-29), its minimum
+                          corner, its outward normal (never flipped) and the positive unit axes as in-plane basis; nearest
+                          face with t > 0, lowest face on ties; distance = t like Wall. ONE object id for the whole box. */
 
 /* One entry of the reference's std::vector<std::unique_ptr<SceneGeometry>> (main.cpp:156-163).
  * The array index IS the object id (hit_object_index, main.cpp:80) and the tie-break order
  * (strict '<' in main.cpp:77 => lowest index wins equal distances). */
 typedef struct rtx_object {
-    int32_t      kind;     /* RTX_SPHERE | RTX_WALL */
+    int32_t      kind;     /* RTX_SPHERE | RTX_WALL | RTX_BOX */
     int32_t      reserved; /* must be 0 */
     rtx_material mat;
-    rtx_vec3     p;        /* sphere: center            | wall: corner 'position' (scene.h:64) */
-    rtx_vec3     n;        /* sphere: ignored           | wall: normal AS PASSED to the ctor; the library
-                              normalises it exactly as scene.h:71 does (n / sqrt(n.n)) */
-    double       a;        /* sphere: radius            | wall: length */
-    double       b;        /* sphere: ignored           | wall: width  */
+    rtx_vec3     p;        /* sphere: center   | wall: corner 'position' (scene.h:64) | box: minimum corner */
+    rtx_vec3     n;        /* sphere: ignored  | wall: normal AS PASSED to the ctor; the library normalises it exactly
+                              as scene.h:71 does (n / sqrt(n.n))            | box: extents (sx, sy, sz) */
+    double       a;        /* sphere: radius   | wall: length                        | box: ignored */
+    double       b;        /* sphere: ignored  | wall: width                         | box: ignored */
 } rtx_object;
 
 /* Inputs of Camera::init (scene.h:94-99, main.cpp:146-153). image_width/aspect_ratio are doubles
@@ -122,7 +127,26 @@ typedef struct rtx_params {
      * path. Only used to place pixels in rtx_outputs.frame_rgba8. Defaults 0, 1. */
     int32_t  frame_offset;
     int32_t  frame_stride;
+    /* EXTENSIONS — off by default, i.e. the reference's semantics. README.md:13-14 speaks of a sun and of tone
+     * mapping and main.cpp:18-19 defines SUN_COLOR / SUN_DIRECTION, but the snapshot contains no code that uses
+     * them: parity is unpinned, the specification is the CPU restatement in oracle/oracle.c.
+     * sun: every local colour (main.cpp:104) gains  color * sun_color * (max(0, s.n) * diffuse + pow(max(0, h.n),
+     *   exponent) * specular)  with s = normalize(sun_direction), h = normalize(normalize(-d) + s), n the unit normal;
+     *   no shadow ray (the reference's point light has none either), sky unchanged.
+     * tonemap: RTX_TONEMAP_REINHARD applies Reinhard's global photographic operator per frame before the 8-bit
+     *   pack: L = .2126 R + .7152 G + .0722 B, Lavg = exp(mean(log(1e-4 + L))), Ls = key / Lavg * L,
+     *   Ld = Ls * (1 + Ls / white^2) / (1 + Ls) (white <= 0: Ld = Ls / (1 + Ls)), rgb *= Ld / L (0 where L <= 0).
+     *   Needs the whole frame on one GPU (n_ranks must be 1). */
+    int32_t  sun_enabled;
+    int32_t  tonemap;          /* RTX_TONEMAP_* */
+    rtx_vec3 sun_color;        /* SUN_COLOR     (1.64,1.27,.99)     main.cpp:18 */
+    rtx_vec3 sun_direction;    /* SUN_DIRECTION (.7,.4,.7)          main.cpp:19; towards the sun, any length > 0 */
+    double   tonemap_key;      /* Reinhard's a, default .18 */
+    double   tonemap_white;    /* luminance that maps to pure white; <= 0 (default): no burn-out term */
 } rtx_params;
+
+#define RTX_TONEMAP_NONE     0  /* reference: radiance goes straight to the 8-bit pack (main.cpp:338-347) */
+#define RTX_TONEMAP_REINHARD 1  /* extension, see rtx_params */
 
 #define RTX_MAX_DEPTH 254     /* ray_count is a uint8: depth+1 rays per pixel at most */
 
@@ -221,6 +245,15 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cameras, int32_t n_frames,
  * RGB triples (exactly one of radiance_f32 / radiance_f64 non-NULL), memory = RTX_MEM_*. */
 int rtx_quantise(rtx_ctx* ctx, const float* radiance_f32, const double* radiance_f64, int64_t n_pixels,
                  int32_t quantise_mode, uint32_t* rgba8, int32_t memory, rtx_stats* stats);
+
+/* EXTENSION (rtx_params.tonemap; no reference code, specification = oracle/oracle.c::orc_tonemap): Reinhard's global
+ * operator per frame followed by the 8-bit pack (params->quantise_mode), on a caller-supplied radiance buffer of n_frames
+ * frames of pixels_per_frame RGB triples (exactly one of radiance_f32 / radiance_f64 non-NULL), memory = RTX_MEM_*.
+ * params->tonemap must be RTX_TONEMAP_REINHARD. log_avg_luminance (HOST pointer, may be NULL) receives the n_frames
+ * log-average luminances the operator used. The statistic is accumulated in fixed point with integer atomics, so the
+ * output is identical from run to run. */
+int rtx_tonemap(rtx_ctx* ctx, const float* radiance_f32, const double* radiance_f64, int64_t pixels_per_frame, int32_t n_frames,
+                const rtx_params* params, uint32_t* rgba8, int32_t memory, double* log_avg_luminance, rtx_stats* stats);
 
 /* Multi-GPU gather epilogue: scatters a band-major buffer (n_ranks blocks of rows_per_rank rows, block r =
  * rank r's packed rows, as an all-gather delivers them) into a row-major frame. Device pointers,

@@ -66,6 +66,8 @@ class Oracle:
               C.POINTER(C.c_uint64))
             f("quantise_mode", None, C.POINTER(C.c_double), C.c_int64, C.c_int32, C.POINTER(C.c_uint32))
             f("quantise_f32", None, C.POINTER(C.c_float), C.c_int64, C.c_int32, C.POINTER(C.c_uint32))
+            f("tonemap", None, C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_int64, C.c_int32, C.POINTER(abi.Params),
+              C.POINTER(C.c_uint32), C.POINTER(C.c_double))
 
     def _f(self, name, restype, *argtypes):
         fn = getattr(self.lib, self.prefix + name)
@@ -151,6 +153,21 @@ class Oracle:
             rgb = rgb.astype(np.float64)
             self._quantise_mode(_ptr(rgb, C.c_double), len(rgb), int(mode), _ptr(out, C.c_uint32))
         return out
+
+    def tonemap(self, rgb, params):
+        """EXTENSION (port only): Reinhard's global operator + 8-bit pack on [n_frames][pixels][3] radiance (f32 or f64).
+        Returns (rgba8 [n_frames][pixels], log-average luminance per frame)."""
+        rgb = np.ascontiguousarray(rgb)
+        assert rgb.ndim == 3 and rgb.shape[2] == 3
+        n_frames, pixels = rgb.shape[0], rgb.shape[1]
+        out = np.zeros((n_frames, pixels), np.uint32)
+        lavg = np.zeros(n_frames, np.float64)
+        if rgb.dtype == np.float32:
+            self._tonemap(None, _ptr(rgb, C.c_float), pixels, n_frames, C.byref(params), _ptr(out, C.c_uint32), _ptr(lavg, C.c_double))
+        else:
+            rgb = np.ascontiguousarray(rgb, dtype=np.float64)
+            self._tonemap(_ptr(rgb, C.c_double), None, pixels, n_frames, C.byref(params), _ptr(out, C.c_uint32), _ptr(lavg, C.c_double))
+        return out, lavg
 
     def intersect(self, geom, origin, direction):
         obj = scene_mod.flatten([geom])

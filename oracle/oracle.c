@@ -79,7 +79,7 @@ static void prepare(const rtx_object* in, int n, object* out)
         out[k].p = in[k].p;
         out[k].a = in[k].a;
         out[k].b = in[k].b;
-        out[k].n = in[k].kind == RTX_WALL ? unit(in[k].n) : mk(0, 0, 0);
+        out[k].n = in[k].kind == RTX_WALL ? unit(in[k].n) : in[k].kind == RTX_BOX ? in[k].n : mk(0, 0, 0);
     }
 }
 
@@ -128,9 +128,44 @@ static collision sphere_intersect(const object* s, v3 o, v3 d)
     return r;
 }
 
+/* RTX_BOX — NOT in the reference snapshot (README.md:21 mentions a sprint-2 `Box`; no code survives): parity
+ * unpinned, this function IS the specification (include/rtx_b200.h). An axis-aligned box, p = minimum corner,
+ * n = (sx, sy, sz) its extents, behaves as six Wall-like faces in the order -x, +x, -y, +y, -z, +z. Each face runs
+ * Wall::intersect's arithmetic (scene.cpp:7-29) with its own corner c (the face's minimum corner), outward normal
+ * and the positive unit axes spanning it as (right, up) — the reference's own basis derivation (scene.cpp:18-19)
+ * is NaN for normals along z, which is why a box cannot be assembled from six reference Walls. The nearest face with
+ * t > 0 wins, the lowest face index on equal t; distance is t (parametric, like Wall), the normal is the face's
+ * outward normal, never flipped (a ray starting inside hits the far face from behind, like a Wall's back face). */
+static collision box_intersect(const object* g, v3 o, v3 d)
+{
+    static const v3 axis[3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    const double size[3] = {g->n.x, g->n.y, g->n.z};
+    collision best = miss();
+    double best_t = DBL_MAX;
+    for (int f = 0; f < 6; f++) {
+        const int ax = f >> 1, hi = f & 1;
+        const int r_ax = ax == 0 ? 1 : 0, u_ax = ax == 2 ? 1 : 2;     /* x: (y,z)   y: (x,z)   z: (x,y) */
+        const v3 normal = hi ? axis[ax] : neg(axis[ax]);
+        const v3 corner = hi ? add(g->p, scale(axis[ax], size[ax])) : g->p;
+        double denominator = dot(normal, d);
+        double t = dot(sub(corner, o), normal) / denominator;
+        if (t > 0) {
+            v3 rel = sub(add(o, scale(d, t)), corner);
+            double px = dot(rel, axis[r_ax]);
+            double py = dot(rel, axis[u_ax]);
+            if (px >= 0 && px <= size[r_ax] && py >= 0 && py <= size[u_ax] && t < best_t) {
+                best_t = t;
+                collision c = {t, normal, 1, -1};
+                best = c;
+            }
+        }
+    }
+    return best;
+}
+
 static inline collision intersect(const object* g, v3 o, v3 d)
 {
-    return g->kind == RTX_SPHERE ? sphere_intersect(g, o, d) : wall_intersect(g, o, d);
+    return g->kind == RTX_SPHERE ? sphere_intersect(g, o, d) : g->kind == RTX_BOX ? box_intersect(g, o, d) : wall_intersect(g, o, d);
 }
 
 /* find_closest_hit (main.cpp:67-84): strict '<' keeps the lowest index on equal distances. */
@@ -185,6 +220,21 @@ static v3 trace(const object* scene, int n, v3 o, v3 d, int remaining, const rtx
     double di = diffuse_term(add(o, scale(d, col.distance)), col.normal, p->light_pos);
     double si = pow(specular_term(pos, col.normal, p->light_pos, neg(d)), m->specular_exponent);
     v3 local = scale(m->color, di * m->diffuse + si * m->specular + m->ambient);
+    if (p->sun_enabled) {
+        /* EXTENSION, not in the reference (rtx_params.sun_enabled, include/rtx_b200.h): SUN_COLOR / SUN_DIRECTION
+         * (main.cpp:18-19, defined and never used) as a directional light through the same Blinn-Phong terms;
+         * no shadow ray, like the reference's point light. This block IS the specification. */
+        v3 s = unit(p->sun_direction);
+        v3 nn = unit(col.normal);
+        double ls = dot(s, nn);
+        double ds = ls > 0 ? ls : 0;
+        v3 h = unit(add(unit(neg(d)), s));
+        double sps = dot(h, nn);
+        double ss = pow(sps > 0 ? sps : 0, m->specular_exponent);
+        double ks = ds * m->diffuse + ss * m->specular;
+        v3 tint = mk(m->color.x * p->sun_color.x, m->color.y * p->sun_color.y, m->color.z * p->sun_color.z);
+        local = add(local, scale(tint, ks));
+    }
     if (remaining <= 0) return local;
     v3 start = add(pos, scale(col.normal, p->reflect_offset));   /* normal unnormalised: offset = r*1e-4 on spheres */
     v3 rd = reflect(d, col.normal);
@@ -241,6 +291,12 @@ void orc_default_params(rtx_params* p)
     p->rank = 0;
     p->frame_offset = 0;
     p->frame_stride = 1;
+    p->sun_enabled = 0;                           /* extensions off = the reference */
+    p->tonemap = RTX_TONEMAP_NONE;
+    p->sun_color = mk(1.64, 1.27, 0.99);          /* main.cpp:18 */
+    p->sun_direction = mk(.7, .4, .7);            /* main.cpp:19 */
+    p->tonemap_key = 0.18;
+    p->tonemap_white = 0.0;
 }
 
 int orc_abi_version(void) { return RTX_ABI_VERSION; }
@@ -419,6 +475,48 @@ void orc_quantise_f32(const float* rgb, int64_t n, int32_t mode, uint32_t* out)
 {
     for (int64_t k = 0; k < n; k++)
         out[k] = pack_rgba(mk((double)rgb[3 * k], (double)rgb[3 * k + 1], (double)rgb[3 * k + 2]), mode);
+}
+
+/* EXTENSION, not in the reference (rtx_params.tonemap = RTX_TONEMAP_REINHARD, include/rtx_b200.h; README.md:13 only
+ * mentions that tone mapping exists). This function IS the specification the CUDA kernels (csrc/tonemap.cu) follow:
+ * Reinhard's global photographic operator per frame, then the 8-bit pack of main.cpp:345 in the chosen mode.
+ *   L    = .2126 R + .7152 G + .0722 B, negative or NaN -> 0
+ *   sum  = sum over the frame of llrint(log(1e-4 + L) * 2^32)      (32.32 fixed point: order independent)
+ *   Lavg = exp(((double)sum / 2^32) / n);  Ls = key / Lavg * L;  Ld = Ls (1 + Ls / white^2) / (1 + Ls)  [white <= 0: no term]
+ *   rgb *= Ld / L (0 where L <= 0)
+ * Exactly one of rgb64 / rgb32 is non-NULL; log_avg (may be NULL) receives Lavg per frame. */
+static double tm_lum(double r, double g, double b)
+{
+    double l = 0.2126 * r + 0.7152 * g + 0.0722 * b;
+    return l > 0.0 ? l : 0.0;
+}
+void orc_tonemap(const double* rgb64, const float* rgb32, int64_t pixels, int32_t n_frames, const rtx_params* p, uint32_t* out,
+                 double* log_avg)
+{
+    const double fix = 4294967296.0;
+    for (int32_t f = 0; f < n_frames; f++) {
+        const int64_t base = (int64_t)f * pixels;
+        long long sum = 0;
+        for (int64_t k = base; k < base + pixels; k++) {
+            double r = rgb64 ? rgb64[3 * k] : (double)rgb32[3 * k], g = rgb64 ? rgb64[3 * k + 1] : (double)rgb32[3 * k + 1],
+                   b = rgb64 ? rgb64[3 * k + 2] : (double)rgb32[3 * k + 2];
+            sum += llrint(log(1e-4 + tm_lum(r, g, b)) * fix);
+        }
+        const double mean = ((double)sum / fix) / (double)pixels;
+        const double lavg = exp(mean);
+        const double key_over_avg = p->tonemap_key / lavg;
+        const double inv_white2 = p->tonemap_white > 0.0 ? 1.0 / (p->tonemap_white * p->tonemap_white) : 0.0;
+        if (log_avg) log_avg[f] = lavg;
+        for (int64_t k = base; k < base + pixels; k++) {
+            double r = rgb64 ? rgb64[3 * k] : (double)rgb32[3 * k], g = rgb64 ? rgb64[3 * k + 1] : (double)rgb32[3 * k + 1],
+                   b = rgb64 ? rgb64[3 * k + 2] : (double)rgb32[3 * k + 2];
+            double l = tm_lum(r, g, b);
+            double ls = key_over_avg * l;
+            double ld = (ls * (1.0 + ls * inv_white2)) / (1.0 + ls);
+            double s = l > 0.0 ? ld / l : 0.0;
+            out[k] = pack_rgba(mk(r * s, g * s, b * s), p->quantise_mode);
+        }
+    }
 }
 
 /* ---- function-level doors (same signatures as the ref_* ones) ------------------------------------ */

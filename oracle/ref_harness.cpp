@@ -20,6 +20,7 @@
  */
 #include <SDL.h>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -114,8 +115,12 @@ static Scene build_scene(const rtx_object* objs, int n)
         Material m(V(o.mat.color), o.mat.metallic, o.mat.ambient, o.mat.diffuse, o.mat.specular, o.mat.specular_exponent);
         if (o.kind == RTX_SPHERE)
             scene.push_back(std::make_unique<Sphere>(m, V(o.p), o.a));
-        else
+        else if (o.kind == RTX_WALL)
             scene.push_back(std::make_unique<Wall>(m, V(o.p), V(o.n), o.a, o.b));
+        else {   /* RTX_BOX and anything else is an extension of this repo: the reference has no such class */
+            std::fprintf(stderr, "ref_harness: object kind %d does not exist in the reference\n", o.kind);
+            std::abort();
+        }
     }
     return scene;
 }

@@ -5,11 +5,12 @@ the reference code (file:line) every field stands for.
 """
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 RTX_OK, RTX_ERR_INVALID, RTX_ERR_CUDA, RTX_ERR_NO_SCENE, RTX_ERR_NOMEM = 0, 1, 2, 3, 4
-RTX_SPHERE, RTX_WALL = 0, 1
+RTX_SPHERE, RTX_WALL, RTX_BOX = 0, 1, 2        # RTX_BOX: extension, see the header
 RTX_QUANT_WRAP, RTX_QUANT_SATURATE = 0, 1
+RTX_TONEMAP_NONE, RTX_TONEMAP_REINHARD = 0, 1    # extension, see the header
 RTX_MEM_HOST, RTX_MEM_DEVICE = 0, 1
 RTX_MAX_DEPTH = 254
 
@@ -50,7 +51,10 @@ class Params(C.Structure):
                 ("light_pos", Vec3), ("ground_color", Vec3), ("sky_low", Vec3), ("sky_high", Vec3),
                 ("reflect_offset", C.c_double), ("sky_exponent", C.c_double),
                 ("band_rows", C.c_int32), ("n_ranks", C.c_int32), ("rank", C.c_int32), ("reserved2", C.c_int32),
-                ("frame_offset", C.c_int32), ("frame_stride", C.c_int32)]
+                ("frame_offset", C.c_int32), ("frame_stride", C.c_int32),
+                # extensions (off by default): sun and tone-map operator
+                ("sun_enabled", C.c_int32), ("tonemap", C.c_int32), ("sun_color", Vec3), ("sun_direction", Vec3),
+                ("tonemap_key", C.c_double), ("tonemap_white", C.c_double)]
 
 
 class Outputs(C.Structure):
@@ -75,6 +79,6 @@ class Stats(C.Structure):
 EXPORTS = (
     "rtx_abi_version", "rtx_status_string", "rtx_create", "rtx_destroy", "rtx_last_error", "rtx_set_stream",
     "rtx_set_scene", "rtx_camera_init", "rtx_default_params", "rtx_local_rows", "rtx_global_row",
-    "rtx_render", "rtx_quantise", "rtx_unpermute_bands", "rtx_ffma_peak",
+    "rtx_render", "rtx_quantise", "rtx_tonemap", "rtx_unpermute_bands", "rtx_ffma_peak",
     "rtx_buffer_alloc", "rtx_buffer_free", "rtx_buffer_export", "rtx_buffer_import", "rtx_buffer_release",
 )

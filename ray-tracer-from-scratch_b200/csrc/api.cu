@@ -36,6 +36,9 @@ struct rtx_ctx {
     size_t d_out_cap[6] = {};
     double* d_rad_scratch = nullptr;   // radiance buffer for the unfused quantise path
     size_t d_rad_scratch_cap = 0;
+    void* d_tm_sums = nullptr;         // tone-map extension: per-frame fixed-point log-luminance sums
+    size_t d_tm_sums_cap = 0;
+    std::vector<long long> h_tm_sums;
 };
 
 namespace {
@@ -165,6 +168,7 @@ void rtx_destroy(rtx_ctx* ctx)
     for (auto& p : ctx->d_out)
         if (p) cudaFree(p);
     if (ctx->d_rad_scratch) cudaFree(ctx->d_rad_scratch);
+    if (ctx->d_tm_sums) cudaFree(ctx->d_tm_sums);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -185,13 +189,14 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
     RTX_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<float4> sph32, wall32;
     std::vector<SphereExact> sph64;
-    std::vector<int32_t> sph_id, kind(n), slot(n);
+    if (n > (1 << 28) - 1) return fail(ctx, RTX_ERR_INVALID, "rtx_set_scene: more than 2^28 - 1 objects");   // key = id * 8 + face
+    std::vector<int32_t> sph_key, kind(n), slot(n);
     std::vector<WallDev> walls;
     std::vector<MaterialDev> mats(n);
     double bound = 0.0;
     for (int k = 0; k < n; k++) {
         const rtx_object& o = objects[k];
-        if (o.kind != RTX_SPHERE && o.kind != RTX_WALL) return fail(ctx, RTX_ERR_INVALID, "rtx_set_scene: unknown object kind");
+        if (o.kind != RTX_SPHERE && o.kind != RTX_WALL && o.kind != RTX_BOX) return fail(ctx, RTX_ERR_INVALID, "rtx_set_scene: unknown object kind");
         MaterialDev& m = mats[k];
         m.color = d3{o.mat.color.x, o.mat.color.y, o.mat.color.z};
         m.ambient = o.mat.ambient;
@@ -208,8 +213,36 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
             float r32 = std::nextafter(static_cast<float>(std::fabs(o.a)), INFINITY);   // radius enters squared: sign is irrelevant
             if (!std::isfinite(o.a)) r32 = INFINITY;
             sph32.push_back(make_float4(static_cast<float>(o.p.x), static_cast<float>(o.p.y), static_cast<float>(o.p.z), r32));
-            sph_id.push_back(k);
+            sph_key.push_back(k * 8);
             bound = std::fmax(bound, amax3(H(o.p)) + std::fabs(o.a));
+        } else if (o.kind == RTX_BOX) {
+            // EXTENSION (rtx_b200.h, RTX_BOX): six Wall-like faces -x,+x,-y,+y,-z,+z that share the box's id; the trace
+            // kernel sees them as walls (same exact test, same bounding-sphere screen), the face index is the low
+            // part of the tie-break key and selects the normal when shading.
+            slot[k] = static_cast<int32_t>(walls.size());
+            const h3 axis[3] = {h3{1, 0, 0}, h3{0, 1, 0}, h3{0, 0, 1}};
+            const double size[3] = {o.n.x, o.n.y, o.n.z};
+            for (int f = 0; f < 6; f++) {
+                const int ax = f >> 1, hi = f & 1;
+                const int r_ax = ax == 0 ? 1 : 0, u_ax = ax == 2 ? 1 : 2;
+                WallDev w;
+                const h3 corner = hi ? hadd(H(o.p), hmul(axis[ax], size[ax])) : H(o.p);
+                w.p = D(corner);
+                w.n = D(hi ? axis[ax] : hmul(axis[ax], -1.0));
+                w.right = D(axis[r_ax]);
+                w.up = D(axis[u_ax]);
+                w.length = size[r_ax];
+                w.width = size[u_ax];
+                w.key = k * 8 + f;
+                w.pad = 0;
+                walls.push_back(w);
+                const h3 centre = hadd(hadd(corner, hmul(axis[r_ax], size[r_ax] / 2)), hmul(axis[u_ax], size[u_ax] / 2));
+                float r32 = static_cast<float>(0.5 * std::sqrt(size[r_ax] * size[r_ax] + size[u_ax] * size[u_ax]) * (1.0 + 1e-6));
+                r32 = std::nextafter(r32, INFINITY);
+                if (!std::isfinite(size[r_ax]) || !std::isfinite(size[u_ax])) r32 = INFINITY;
+                wall32.push_back(make_float4(static_cast<float>(centre.x), static_cast<float>(centre.y), static_cast<float>(centre.z), r32));
+            }
+            bound = std::fmax(bound, amax3(H(o.p)) + std::fabs(size[0]) + std::fabs(size[1]) + std::fabs(size[2]));
         } else {
             slot[k] = static_cast<int32_t>(walls.size());
             WallDev w;
@@ -222,7 +255,7 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
             w.up = D(up);
             w.length = o.a;
             w.width = o.b;
-            w.id = k;
+            w.key = k * 8;
             w.pad = 0;
             walls.push_back(w);
             // Bounding sphere of the rectangle for the FP32 screen: every point Wall::intersect can accept
@@ -254,7 +287,7 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
     std::vector<unsigned char> blob(off, 0);
     if (ns_pad) std::memcpy(&blob[o_s32], sph32.data(), sizeof(float4) * ns_pad);
     if (ns) std::memcpy(&blob[o_s64], sph64.data(), sizeof(SphereExact) * ns);
-    if (ns) std::memcpy(&blob[o_sid], sph_id.data(), sizeof(int32_t) * ns);
+    if (ns) std::memcpy(&blob[o_sid], sph_key.data(), sizeof(int32_t) * ns);
     if (nw) std::memcpy(&blob[o_wal], walls.data(), sizeof(WallDev) * nw);
     if (n) std::memcpy(&blob[o_mat], mats.data(), sizeof(MaterialDev) * n);
     if (n) std::memcpy(&blob[o_knd], kind.data(), sizeof(int32_t) * n);
@@ -277,7 +310,7 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
     s.n_entries_padded = ns_pad;
     s.ent32 = reinterpret_cast<const float4*>(base + o_s32);
     s.sph64 = reinterpret_cast<const SphereExact*>(base + o_s64);
-    s.sph_id = reinterpret_cast<const int32_t*>(base + o_sid);
+    s.sph_key = reinterpret_cast<const int32_t*>(base + o_sid);
     s.walls = reinterpret_cast<const WallDev*>(base + o_wal);
     s.mats = reinterpret_cast<const MaterialDev*>(base + o_mat);
     s.kind = reinterpret_cast<const int32_t*>(base + o_knd);
@@ -336,6 +369,12 @@ void rtx_default_params(rtx_params* p)
     p->rank = 0;
     p->frame_offset = 0;
     p->frame_stride = 1;
+    p->sun_enabled = 0;                                   // extensions off: the reference's semantics
+    p->tonemap = RTX_TONEMAP_NONE;
+    p->sun_color = rtx_vec3{1.64, 1.27, 0.99};            // SUN_COLOR      main.cpp:18
+    p->sun_direction = rtx_vec3{.7, .4, .7};              // SUN_DIRECTION  main.cpp:19
+    p->tonemap_key = 0.18;
+    p->tonemap_white = 0.0;
 }
 
 int32_t rtx_local_rows(int32_t height, int32_t band_rows, int32_t n_ranks, int32_t rank)
@@ -370,6 +409,11 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
         return fail(ctx, RTX_ERR_INVALID, "rtx_render: unknown quantise_mode");
     if (outs->memory != RTX_MEM_HOST && outs->memory != RTX_MEM_DEVICE)
         return fail(ctx, RTX_ERR_INVALID, "rtx_render: outputs.memory must be RTX_MEM_HOST or RTX_MEM_DEVICE");
+    if (p.tonemap != RTX_TONEMAP_NONE && p.tonemap != RTX_TONEMAP_REINHARD) return fail(ctx, RTX_ERR_INVALID, "rtx_render: unknown tonemap");
+    const bool tonemap = p.tonemap == RTX_TONEMAP_REINHARD && outs->rgba8;
+    if (tonemap && (p.n_ranks != 1 || outs->frame_rgba8))
+        return fail(ctx, RTX_ERR_INVALID, "rtx_render: the tone-map operator needs the whole frame on one GPU (n_ranks = 1, no frame_rgba8)");
+    if (tonemap && !(p.tonemap_key > 0.0)) return fail(ctx, RTX_ERR_INVALID, "rtx_render: tonemap_key must be > 0");
     const int W = cams[0].width, Hh = cams[0].height;
     if (W <= 0 || Hh <= 0) return fail(ctx, RTX_ERR_INVALID, "rtx_render: camera width/height must be positive");
     double cam_bound = 0.0;
@@ -416,7 +460,7 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
     }
     if (outs->frame_rgba8 && (p.frame_stride < 1 || p.frame_offset < 0))
         return fail(ctx, RTX_ERR_INVALID, "rtx_render: frame_offset/frame_stride must be >= 0 / >= 1");
-    const bool unfused = !p.fuse_quantise && user[0] && !outs->frame_rgba8;
+    const bool unfused = (!p.fuse_quantise || tonemap) && user[0] && !outs->frame_rgba8;
     double* rad_for_quant = nullptr;
     if (unfused) {
         if (dev[2]) {
@@ -448,6 +492,9 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
     a.sky_high = D(H(p.sky_high));
     a.reflect_offset = p.reflect_offset;
     a.sky_exponent = p.sky_exponent;
+    a.sun_enabled = p.sun_enabled ? 1 : 0;
+    a.sun_dir = D(hunit(H(p.sun_direction)));             // normalised like every direction of the reference (vec.cpp:21-24)
+    a.sun_color = D(H(p.sun_color));
     // FP32 screen error bound (derivation in DESIGN.md §3.2): with B = scene/camera extent and ray origins
     // within 2B, the line-distance error is below 1.7e-6*B; 8e-6*B leaves a 4x margin. Origins beyond 2B
     // (primary-ray overshoot) fall back to exact tests lane by lane.
@@ -475,9 +522,18 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     if (unfused) {
         RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 2, 0, 2 * sizeof(unsigned long long), st));
-        RTX_CUDA(ctx, launch_quantise_f64(rad_for_quant, static_cast<int64_t>(n_px), p.quantise_mode,
-                                          static_cast<uint32_t*>(dev[0]), ctx->d_counters, ctx->n_sms, st));
-        launches++;
+        if (tonemap) {
+            int rc = grow(ctx, &ctx->d_tm_sums, &ctx->d_tm_sums_cap, sizeof(long long) * std::max(n_frames, 16));
+            if (rc != RTX_OK) return rc;
+            RTX_CUDA(ctx, launch_tonemap_f64(rad_for_quant, static_cast<int64_t>(local_rows) * W, n_frames, p.tonemap_key, p.tonemap_white,
+                                             p.quantise_mode, static_cast<uint32_t*>(dev[0]), static_cast<long long*>(ctx->d_tm_sums),
+                                             ctx->d_counters, ctx->n_sms, st));
+            launches += 2;
+        } else {
+            RTX_CUDA(ctx, launch_quantise_f64(rad_for_quant, static_cast<int64_t>(n_px), p.quantise_mode,
+                                              static_cast<uint32_t*>(dev[0]), ctx->d_counters, ctx->n_sms, st));
+            launches++;
+        }
     }
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     if (host_out) {
@@ -562,6 +618,72 @@ int rtx_quantise(rtx_ctx* ctx, const float* rad32, const double* rad64, int64_t 
         long long bits = static_cast<long long>(ctx->h_counters[3]);
         std::memcpy(&stats->max_luminance, &bits, sizeof bits);
         stats->launches = 1;
+    }
+    ctx->error.clear();
+    return RTX_OK;
+}
+
+int rtx_tonemap(rtx_ctx* ctx, const float* rad32, const double* rad64, int64_t pixels_per_frame, int32_t n_frames,
+                const rtx_params* params, uint32_t* rgba8, int32_t memory, double* log_avg_luminance, rtx_stats* stats)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    if ((rad32 == nullptr) == (rad64 == nullptr)) return fail(ctx, RTX_ERR_INVALID, "rtx_tonemap: pass exactly one radiance buffer");
+    if (pixels_per_frame <= 0 || n_frames <= 0 || !rgba8 || !params) return fail(ctx, RTX_ERR_INVALID, "rtx_tonemap: bad size or null argument");
+    const rtx_params& p = *params;
+    if (p.tonemap != RTX_TONEMAP_REINHARD) return fail(ctx, RTX_ERR_INVALID, "rtx_tonemap: params.tonemap must be RTX_TONEMAP_REINHARD");
+    if (!(p.tonemap_key > 0.0)) return fail(ctx, RTX_ERR_INVALID, "rtx_tonemap: tonemap_key must be > 0");
+    if (p.quantise_mode != RTX_QUANT_WRAP && p.quantise_mode != RTX_QUANT_SATURATE) return fail(ctx, RTX_ERR_INVALID, "rtx_tonemap: unknown quantise_mode");
+    if (memory != RTX_MEM_HOST && memory != RTX_MEM_DEVICE) return fail(ctx, RTX_ERR_INVALID, "rtx_tonemap: bad memory kind");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n_px = static_cast<size_t>(pixels_per_frame) * n_frames;
+    const size_t in_bytes = n_px * (rad32 ? 12 : 24);
+    const void* d_in = rad32 ? static_cast<const void*>(rad32) : static_cast<const void*>(rad64);
+    uint32_t* d_o = rgba8;
+    int rc = grow(ctx, &ctx->d_tm_sums, &ctx->d_tm_sums_cap, sizeof(long long) * std::max(n_frames, 16));
+    if (rc != RTX_OK) return rc;
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    if (memory == RTX_MEM_HOST) {
+        void* pp = ctx->d_rad_scratch;
+        rc = grow(ctx, &pp, &ctx->d_rad_scratch_cap, std::max<size_t>(in_bytes, 16));
+        ctx->d_rad_scratch = static_cast<double*>(pp);
+        if (rc != RTX_OK) return rc;
+        rc = grow(ctx, &ctx->d_out[0], &ctx->d_out_cap[0], std::max<size_t>(n_px * 4, 16));
+        if (rc != RTX_OK) return rc;
+        RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rad_scratch, d_in, in_bytes, cudaMemcpyHostToDevice, st));
+        d_in = ctx->d_rad_scratch;
+        d_o = static_cast<uint32_t*>(ctx->d_out[0]);
+    }
+    RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    long long* sums = static_cast<long long*>(ctx->d_tm_sums);
+    if (rad32)
+        RTX_CUDA(ctx, launch_tonemap_f32(static_cast<const float*>(d_in), pixels_per_frame, n_frames, p.tonemap_key, p.tonemap_white,
+                                         p.quantise_mode, d_o, sums, ctx->d_counters, ctx->n_sms, st));
+    else
+        RTX_CUDA(ctx, launch_tonemap_f64(static_cast<const double*>(d_in), pixels_per_frame, n_frames, p.tonemap_key, p.tonemap_white,
+                                         p.quantise_mode, d_o, sums, ctx->d_counters, ctx->n_sms, st));
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    if (memory == RTX_MEM_HOST) RTX_CUDA(ctx, cudaMemcpyAsync(rgba8, d_o, n_px * 4, cudaMemcpyDeviceToHost, st));
+    ctx->h_tm_sums.resize(n_frames);
+    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->h_tm_sums.data(), sums, sizeof(long long) * n_frames, cudaMemcpyDeviceToHost, st));
+    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    RTX_CUDA(ctx, cudaStreamSynchronize(st));
+    if (log_avg_luminance)   // same expression as the kernel and the oracle: exp((sum / 2^32) / n)
+        for (int f = 0; f < n_frames; f++)
+            log_avg_luminance[f] = std::exp((static_cast<double>(ctx->h_tm_sums[f]) / 4294967296.0) / static_cast<double>(pixels_per_frame));
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); stats->h2d_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); stats->surface_update_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); stats->d2h_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); stats->total_ms = ms;
+        stats->over_range_pixels = ctx->h_counters[2];
+        long long bits = static_cast<long long>(ctx->h_counters[3]);
+        std::memcpy(&stats->max_luminance, &bits, sizeof bits);
+        stats->launches = 2;
     }
     ctx->error.clear();
     return RTX_OK;

@@ -48,9 +48,10 @@ __device__ __forceinline__ d3 lerp(d3 a, d3 b, double t)
 // ---- device copy of the scene (built by rtx_set_scene) --------------------------------------------
 //
 // The virtual SceneGeometry::intersect (scene.h:51-60) is replaced by one flat array of screen entries
-// (warp-uniform scan, no dispatch) plus type-switched exact data for the few survivors; `id` maps back to
-// the index in the reference's scene vector, which is both the object id and the tie-break order
-// (main.cpp:77-80).
+// (warp-uniform scan, no dispatch) plus type-switched exact data for the few survivors. Every exact record carries
+// a KEY = scene id * 8 + face: the scene id is the index in the reference's scene vector, which is both the object
+// id and the tie-break order (main.cpp:77-80); the low three bits order the six faces of an RTX_BOX (extension; 0 for
+// spheres and walls), so comparing keys reproduces the reference's order and key >> 3 is the object id.
 
 struct SphereExact {   // 32 B, read only for filter survivors
     double cx, cy, cz, r;
@@ -62,7 +63,7 @@ struct WallDev {       // everything Wall::intersect needs, with the ray-indepen
     d3 right;          // normalize(cross(n, (0,0,1)))        scene.cpp:18
     d3 up;             // normalize(cross(right, n))          scene.cpp:19
     double length, width;
-    int32_t id;
+    int32_t key;       // tie-break key = scene id * 8 + face (face = 0 for a Wall, 0..5 for the faces of a box)
     int32_t pad;
 };
 
@@ -79,11 +80,11 @@ struct SceneDev {
     // BOUNDING sphere per wall (entry n_spheres + w = wall slot w); padding has r = -1.
     const float4* ent32;               // [n_entries_padded]
     const SphereExact* sph64;          // [n_spheres]
-    const int32_t* sph_id;             // [n_spheres]
-    const WallDev* walls;              // [n_walls]
+    const int32_t* sph_key;            // [n_spheres] scene id * 8
+    const WallDev* walls;              // [n_walls] walls and box faces (six consecutive entries per box)
     const MaterialDev* mats;           // [n_objects]
-    const int32_t* kind;               // [n_objects] RTX_SPHERE | RTX_WALL
-    const int32_t* slot;               // [n_objects] index into sph64 / walls
+    const int32_t* kind;               // [n_objects] RTX_SPHERE | RTX_WALL | RTX_BOX
+    const int32_t* slot;               // [n_objects] index into sph64 / walls (box: its first face)
 };
 
 // Per-launch arguments of the trace kernel.
@@ -96,6 +97,8 @@ struct TraceArgs {
     int32_t max_depth, quantise_mode;
     d3 light, ground, sky_low, sky_high;
     double reflect_offset, sky_exponent;
+    int32_t sun_enabled;               // extension (rtx_params.sun_enabled): directional Blinn-Phong term
+    d3 sun_dir, sun_color;             // unit vector towards the sun; its colour
     float filter_eps;                  // E: bound on the FP32 filter's distance error (see trace.cu)
     float origin_bound;                // rays whose origin exceeds this fall back to exact tests
     // outputs (device pointers, any may be null)
@@ -167,6 +170,10 @@ cudaError_t launch_quantise_f64(const double* rad, int64_t n_pixels, int mode, u
                                 unsigned long long* counters, int n_sms, cudaStream_t stream);
 cudaError_t launch_quantise_f32(const float* rad, int64_t n_pixels, int mode, uint32_t* rgba8,
                                 unsigned long long* counters, int n_sms, cudaStream_t stream);
+cudaError_t launch_tonemap_f32(const float* rad, int64_t pixels_per_frame, int n_frames, double key, double white, int mode,
+                               uint32_t* rgba8, long long* sums, unsigned long long* counters, int n_sms, cudaStream_t stream);
+cudaError_t launch_tonemap_f64(const double* rad, int64_t pixels_per_frame, int n_frames, double key, double white, int mode,
+                               uint32_t* rgba8, long long* sums, unsigned long long* counters, int n_sms, cudaStream_t stream);
 cudaError_t launch_unpermute(const void* band_major, void* row_major, int height, int width, int elem_bytes,
                              int band_rows, int n_ranks, int rows_per_rank, cudaStream_t stream);
 cudaError_t run_ffma_peak(int variant, int n_sms, cudaStream_t stream, double* tflops, double* mhz);

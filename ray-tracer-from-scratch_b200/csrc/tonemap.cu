@@ -1,0 +1,197 @@
+// tonemap.cu — EXTENSION (rtx_params.tonemap = RTX_TONEMAP_REINHARD; off by default, the reference packs radiance
+// straight to 8 bits, main.cpp:338-347). README.md:13 speaks of tone mapping, the snapshot has no operator: parity is
+// unpinned, the specification is oracle/oracle.c::orc_tonemap, which these kernels follow operation for operation.
+//
+//   pass 1  logsum   per frame, sum over pixels of log(1e-4 + L), L = .2126 R + .7152 G + .0722 B (negative / NaN -> 0)
+//   pass 2  map+pack Lavg = exp(sum / n), Ls = key / Lavg * L, Ld = Ls (1 + Ls / white^2) / (1 + Ls), rgb *= Ld / L,
+//                    then the same 8-bit pack as the quantise kernel
+//
+// Both are HBM-bound streaming kernels (pass 1 reads 12 or 24 B per pixel, pass 2 reads the same and writes 4 B):
+// 4 pixels per thread with 128-bit loads and one 128-bit store, grid = 8 CTAs per SM, warp-shuffle reductions and one
+// atomic per warp for the global statistic. The statistic is accumulated in 32.32 FIXED POINT with integer atomics:
+// integer addition is associative, so the frame's log-average — and with it every pixel — is identical from run to
+// run whatever the order in which warps finish (a floating-point atomicAdd would not be).
+#include <algorithm>
+
+#include "rtx_device.cuh"
+
+namespace rtx {
+
+namespace {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr double kFix = 4294967296.0;   // 2^32
+
+// Rec. 709 luminance with every rounding spelled out; negative and NaN luminances count as 0.
+__device__ __forceinline__ double luminance(double r, double g, double b)
+{
+    const double l = ex::add(ex::add(ex::mul(0.2126, r), ex::mul(0.7152, g)), ex::mul(0.0722, b));
+    return l > 0.0 ? l : 0.0;
+}
+
+__device__ __forceinline__ long long log_fixed(double r, double g, double b)
+{
+    return __double2ll_rn(ex::mul(log(ex::add(1e-4, luminance(r, g, b))), kFix));
+}
+
+struct MapConsts {
+    double key_over_avg;   // key / Lavg of this frame
+    double inv_white2;     // 1 / white^2, or 0 when there is no burn-out term
+};
+
+__device__ __forceinline__ MapConsts map_consts(long long sum_fixed, long long pixels, double key, double white)
+{
+    const double mean = ex::div(ex::div(static_cast<double>(sum_fixed), kFix), static_cast<double>(pixels));
+    MapConsts c;
+    c.key_over_avg = ex::div(key, exp(mean));
+    c.inv_white2 = white > 0.0 ? ex::div(1.0, ex::mul(white, white)) : 0.0;
+    return c;
+}
+
+struct PackStats {
+    unsigned long long over;
+    double maxlum;
+};
+
+__device__ __forceinline__ uint32_t map_pixel(PackStats& s, const MapConsts& c, double r, double g, double b, int mode)
+{
+    const double l = luminance(r, g, b);
+    const double ls = ex::mul(c.key_over_avg, l);
+    const double ld = ex::div(ex::mul(ls, ex::add(1.0, ex::mul(ls, c.inv_white2))), ex::add(1.0, ls));
+    const double k = l > 0.0 ? ex::div(ld, l) : 0.0;
+    const double R = ex::mul(r, k), G = ex::mul(g, k), B = ex::mul(b, k);
+    bool over;
+    const uint32_t word = pack_rgba_flag(R, G, B, mode, over);
+    if (over) s.over++;
+    const double lum = (R + G + B) * (1.0 / 3.0);
+    if (lum > s.maxlum) s.maxlum = lum;
+    return word;
+}
+
+// Four pixels (12 channels) of frame-relative quad q. VEC: 128-bit loads (the frame's base is 16-byte aligned).
+template <typename T, bool VEC>
+__device__ __forceinline__ void load_quad(const T* __restrict__ frame, long long q, double (&v)[12])
+{
+    if constexpr (VEC && sizeof(T) == 4) {
+        const float4* in4 = reinterpret_cast<const float4*>(frame);
+        const float4 a = __ldcs(&in4[3 * q]), b = __ldcs(&in4[3 * q + 1]), c = __ldcs(&in4[3 * q + 2]);
+        const float f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int k = 0; k < 12; k++) v[k] = f[k];
+    } else if constexpr (VEC) {
+        const double2* in2 = reinterpret_cast<const double2*>(frame);
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const double2 d = __ldcs(&in2[6 * q + k]);
+            v[2 * k] = d.x;
+            v[2 * k + 1] = d.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; k++) v[k] = static_cast<double>(frame[12 * q + k]);
+    }
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) tonemap_logsum_kernel(const T* __restrict__ rad, long long pixels, long long* __restrict__ sums)
+{
+    const T* __restrict__ frame = rad + 3 * pixels * blockIdx.y;
+    const long long n_quads = pixels >> 2;
+    long long acc = 0;
+    for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < n_quads;
+         q += static_cast<long long>(gridDim.x) * blockDim.x) {
+        double v[12];
+        load_quad<T, VEC>(frame, q, v);
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc += log_fixed(v[3 * k], v[3 * k + 1], v[3 * k + 2]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (pixels & 3)) {   // ragged tail
+        const long long p = (n_quads << 2) + threadIdx.x;
+        acc += log_fixed(frame[3 * p], frame[3 * p + 1], frame[3 * p + 2]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(kFull, acc, off);
+    if ((threadIdx.x & 31) == 0 && acc != 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&sums[blockIdx.y]), static_cast<unsigned long long>(acc));
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) tonemap_pack_kernel(const T* __restrict__ rad, long long pixels, const long long* __restrict__ sums,
+                                                           double key, double white, int mode, uint32_t* __restrict__ out,
+                                                           unsigned long long* counters)
+{
+    const T* __restrict__ frame = rad + 3 * pixels * blockIdx.y;
+    uint32_t* __restrict__ oframe = out + pixels * blockIdx.y;
+    const MapConsts c = map_consts(sums[blockIdx.y], pixels, key, white);
+    PackStats st{0ull, 0.0};
+    const long long n_quads = pixels >> 2;
+    for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < n_quads;
+         q += static_cast<long long>(gridDim.x) * blockDim.x) {
+        double v[12];
+        load_quad<T, VEC>(frame, q, v);
+        uint4 o;
+        o.x = map_pixel(st, c, v[0], v[1], v[2], mode);
+        o.y = map_pixel(st, c, v[3], v[4], v[5], mode);
+        o.z = map_pixel(st, c, v[6], v[7], v[8], mode);
+        o.w = map_pixel(st, c, v[9], v[10], v[11], mode);
+        if constexpr (VEC) {
+            __stcs(reinterpret_cast<uint4*>(oframe) + q, o);
+        } else {
+            oframe[4 * q] = o.x; oframe[4 * q + 1] = o.y; oframe[4 * q + 2] = o.z; oframe[4 * q + 3] = o.w;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (pixels & 3)) {
+        const long long p = (n_quads << 2) + threadIdx.x;
+        oframe[p] = map_pixel(st, c, frame[3 * p], frame[3 * p + 1], frame[3 * p + 2], mode);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        st.over += __shfl_down_sync(kFull, st.over, off);
+        st.maxlum = fmax(st.maxlum, __shfl_down_sync(kFull, st.maxlum, off));
+    }
+    if ((threadIdx.x & 31) == 0 && counters) {
+        if (st.over) atomicAdd(&counters[2], st.over);
+        if (st.maxlum > 0.0) atomicMax(&counters[3], static_cast<unsigned long long>(__double_as_longlong(st.maxlum)));
+    }
+}
+
+template <typename T>
+cudaError_t launch_typed(const T* rad, long long pixels, int n_frames, double key, double white, int mode, uint32_t* rgba8,
+                         long long* sums, unsigned long long* counters, int n_sms, cudaStream_t stream)
+{
+    // whole waves: 8 CTAs of 256 threads per SM, shared between the frames of the call
+    long long per_frame = (pixels / 4 + 255) / 256;
+    const long long cap = std::max<long long>(1, static_cast<long long>(n_sms) * 8 / n_frames);
+    per_frame = std::max<long long>(1, std::min(per_frame, cap));
+    const dim3 grid(static_cast<unsigned>(per_frame), static_cast<unsigned>(n_frames));
+    // vector path: every frame's base must be 16-byte aligned in both buffers
+    const bool vec = (pixels % 4 == 0) && (reinterpret_cast<uintptr_t>(rad) % 16 == 0) && (reinterpret_cast<uintptr_t>(rgba8) % 16 == 0);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(long long) * n_frames, stream);
+    if (e != cudaSuccess) return e;
+    if (vec) {
+        tonemap_logsum_kernel<T, true><<<grid, 256, 0, stream>>>(rad, pixels, sums);
+        tonemap_pack_kernel<T, true><<<grid, 256, 0, stream>>>(rad, pixels, sums, key, white, mode, rgba8, counters);
+    } else {
+        tonemap_logsum_kernel<T, false><<<grid, 256, 0, stream>>>(rad, pixels, sums);
+        tonemap_pack_kernel<T, false><<<grid, 256, 0, stream>>>(rad, pixels, sums, key, white, mode, rgba8, counters);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_tonemap_f32(const float* rad, int64_t pixels_per_frame, int n_frames, double key, double white, int mode,
+                               uint32_t* rgba8, long long* sums, unsigned long long* counters, int n_sms, cudaStream_t stream)
+{
+    if (pixels_per_frame <= 0 || n_frames <= 0) return cudaSuccess;
+    return launch_typed<float>(rad, pixels_per_frame, n_frames, key, white, mode, rgba8, sums, counters, n_sms, stream);
+}
+
+cudaError_t launch_tonemap_f64(const double* rad, int64_t pixels_per_frame, int n_frames, double key, double white, int mode,
+                               uint32_t* rgba8, long long* sums, unsigned long long* counters, int n_sms, cudaStream_t stream)
+{
+    if (pixels_per_frame <= 0 || n_frames <= 0) return cudaSuccess;
+    return launch_typed<double>(rad, pixels_per_frame, n_frames, key, white, mode, rgba8, sums, counters, n_sms, stream);
+}
+
+}  // namespace rtx

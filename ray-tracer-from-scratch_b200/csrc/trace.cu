@@ -116,7 +116,7 @@ struct Chain {
     float fdx, fdy, fdz, fd_o;   // second-screen constants: d^ and d^.o in float
     float inv_dlen_lo;           // float lower bound of 1/|d| (wall distances are parametric)
     float best_hi;               // float upper bound of best_dist
-    int best_id;
+    int best_key;       // scene id * 8 + face of the best hit so far (-1: none)
     int remaining;      // remaining_iterations (main.cpp:89)
     int first_id;       // primary hit id
     int rays;
@@ -140,11 +140,11 @@ struct Packed {
 
 __device__ __forceinline__ float2 dup(float v) { return make_float2(v, v); }
 
-// main.cpp:77 generalised to any evaluation order: accept iff distance > 0 and (distance, id) is
-// lexicographically smaller than the best so far — identical to the in-order strict '<' scan.
-__device__ __forceinline__ bool better(double dist, int id, double best_dist, int best_id)
+// main.cpp:77 generalised to any evaluation order: accept iff distance > 0 and (distance, key) is
+// lexicographically smaller than the best so far — identical to the in-order strict '<' scan (key = id * 8 + face).
+__device__ __forceinline__ bool better(double dist, int key, double best_dist, int best_key)
 {
-    return dist > 0 && (dist < best_dist || (dist == best_dist && id < best_id));
+    return dist > 0 && (dist < best_dist || (dist == best_dist && key < best_key));
 }
 
 // Ray constants for both screens. `origin_bound`: the error bound E assumes |o| <= origin_bound; a ray that
@@ -164,7 +164,7 @@ __device__ __forceinline__ Packed setup_chain(Chain& c, float origin_bound)
     c.a_dd = ex::len2(c.d);
     c.dlen = ex::sqrt(c.a_dd);
     c.best_dist = 1.7976931348623157e308;   // DBL_MAX, main.cpp:70
-    c.best_id = -1;
+    c.best_key = -1;
     c.best_hi = __int_as_float(0x7f800000);
     c.qn = 0;
     const double inv = 1.0 / c.dlen;
@@ -215,19 +215,19 @@ __device__ __noinline__ void drain_queue(Chain& c, const SceneDev sc, const floa
         if (e < sc.n_spheres) {
             if (b32 - rb > c.best_hi) continue;                // sphere distance is in world units (scene.cpp:77)
             const double dist = sphere_exact(c.o, c.d, c.a_dd, c.dlen, sc.sph64[e], nullptr);
-            const int id = sc.sph_id[e];
-            if (better(dist, id, c.best_dist, c.best_id)) {
+            const int key = sc.sph_key[e];
+            if (better(dist, key, c.best_dist, c.best_key)) {
                 c.best_dist = dist;
-                c.best_id = id;
+                c.best_key = key;
                 c.best_hi = __double2float_ru(dist);
             }
         } else {
             if ((b32 - rb) * c.inv_dlen_lo > c.best_hi) continue;   // wall distance is t of the unnormalised d
             const WallDev& w = sc.walls[e - sc.n_spheres];
             const double t = wall_exact(c.o, c.d, w);
-            if (better(t, w.id, c.best_dist, c.best_id)) {
+            if (better(t, w.key, c.best_dist, c.best_key)) {
                 c.best_dist = t;
-                c.best_id = w.id;
+                c.best_key = w.key;
                 c.best_hi = __double2float_ru(t);
             }
         }
@@ -418,9 +418,10 @@ __device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, FrameTo
     using namespace ex;
     const SceneDev& sc = a.scene;
     c.rays++;
-    if (c.rays == 1) c.first_id = c.best_id;
+    const int best_id = c.best_key >> 3;          // object id (-1 stays -1); the low bits are the box face
+    if (c.rays == 1) c.first_id = best_id;
     bool done;
-    if (c.best_id < 0) {
+    if (best_id < 0) {
         // out_color, main.cpp:28-37 (sign test on the unnormalised z)
         d3 col;
         if (c.d.z < 0.0) {
@@ -437,13 +438,13 @@ __device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, FrameTo
         done = true;
     } else {
         d3 normal;
-        const int slot = sc.slot[c.best_id];
-        if (sc.kind[c.best_id] == RTX_SPHERE) {
+        const int slot = sc.slot[best_id];
+        if (sc.kind[best_id] == RTX_SPHERE) {
             sphere_exact(c.o, c.d, c.a_dd, c.dlen, sc.sph64[slot], &normal);
         } else {
-            normal = sc.walls[slot].n;
+            normal = sc.walls[slot + (c.best_key & 7)].n;      // a wall, or the face of a box that was hit
         }
-        const MaterialDev m = sc.mats[c.best_id];
+        const MaterialDev m = sc.mats[best_id];
         const d3 pos = add(c.o, scale(c.d, c.best_dist));                  // main.cpp:99
         const d3 ldir = unit(sub(a.light, pos));                           // main.cpp:44,57
         const d3 nn = unit(normal);                                        // main.cpp:46,56
@@ -454,7 +455,19 @@ __device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, FrameTo
         const double sp = dot(half, nn);                                   // main.cpp:60
         const double si = pow(sp > 0 ? sp : 0, m.exponent);                // main.cpp:103
         const double k = add(add(mul(di, m.diffuse), mul(si, m.specular)), m.ambient);
-        const d3 local = scale(m.color, k);                                // main.cpp:104
+        d3 local = scale(m.color, k);                                      // main.cpp:104
+        if (a.sun_enabled) {
+            // EXTENSION (rtx_params.sun_enabled; no reference code, specification = oracle.c::trace): the unused
+            // SUN_COLOR / SUN_DIRECTION of main.cpp:18-19 as a directional light through the same Blinn-Phong terms
+            const double ls = dot(a.sun_dir, nn);
+            const double ds = ls > 0 ? ls : 0;
+            const d3 hs = unit(add(neg(dhat), a.sun_dir));
+            const double sps = dot(hs, nn);
+            const double ss = pow(sps > 0 ? sps : 0, m.exponent);
+            const double ks = add(mul(ds, m.diffuse), mul(ss, m.specular));
+            const d3 tint = d3{mul(m.color.x, a.sun_color.x), mul(m.color.y, a.sun_color.y), mul(m.color.z, a.sun_color.z)};
+            local = add(local, scale(tint, ks));
+        }
         if (c.remaining <= 0) {                                            // main.cpp:105-108
             c.acc.x += c.weight * local.x;
             c.acc.y += c.weight * local.y;
@@ -554,7 +567,7 @@ __device__ __noinline__ void start_pixel(Chain& c, unsigned long long p, const T
 // This kernel is the same algorithm without the machinery: one chain per lane held in registers, every object tested
 // with the exact double routines, persistent lanes refilled from the same pixel counter. Results are identical by
 // construction (same sphere_exact / wall_exact / better / shade_body).
-constexpr int kSmallScene = 16;       // objects
+constexpr int kSmallScene = 16;       // screen entries (spheres + walls + box faces)
 constexpr int kSmallThreads = 256;
 
 #ifndef RTX_SMALL_MINBLOCKS
@@ -587,16 +600,16 @@ __global__ void __launch_bounds__(kSmallThreads, RTX_SMALL_MINBLOCKS) trace_smal
             c.a_dd = ex::len2(c.d);
             c.dlen = ex::sqrt(c.a_dd);
             c.best_dist = 1.7976931348623157e308;   // DBL_MAX, main.cpp:70
-            c.best_id = -1;
+            c.best_key = -1;
             for (int i = 0; i < sc.n_spheres; i++) {
                 const double dist = sphere_exact(c.o, c.d, c.a_dd, c.dlen, sc.sph64[i], nullptr);
-                const int id = sc.sph_id[i];
-                if (better(dist, id, c.best_dist, c.best_id)) { c.best_dist = dist; c.best_id = id; }
+                const int key = sc.sph_key[i];
+                if (better(dist, key, c.best_dist, c.best_key)) { c.best_dist = dist; c.best_key = key; }
             }
             for (int i = 0; i < sc.n_walls; i++) {
                 const WallDev& w = sc.walls[i];
                 const double t = wall_exact(c.o, c.d, w);
-                if (better(t, w.id, c.best_dist, c.best_id)) { c.best_dist = t; c.best_id = w.id; }
+                if (better(t, w.key, c.best_dist, c.best_key)) { c.best_dist = t; c.best_key = w.key; }
             }
             shade_body(c, a, tot);
         }
@@ -727,8 +740,8 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
                 }
                 if (__any_sync(kFull, overflow)) {   // a mailbox overflowed: redo this segment the ordinary way
                     ch[0].qn = ch[1].qn = 0;
-                    if (ch[0].active) { ch[0].best_dist = 1.7976931348623157e308; ch[0].best_id = -1; ch[0].best_hi = __int_as_float(0x7f800000); }
-                    if (ch[1].active) { ch[1].best_dist = 1.7976931348623157e308; ch[1].best_id = -1; ch[1].best_hi = __int_as_float(0x7f800000); }
+                    if (ch[0].active) { ch[0].best_dist = 1.7976931348623157e308; ch[0].best_key = -1; ch[0].best_hi = __int_as_float(0x7f800000); }
+                    if (ch[1].active) { ch[1].best_dist = 1.7976931348623157e308; ch[1].best_key = -1; ch[1].best_hi = __int_as_float(0x7f800000); }
                     coop = false;
                 }
             }
@@ -775,7 +788,7 @@ cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, 
     const unsigned long long total =
         static_cast<unsigned long long>(args.n_frames) * static_cast<unsigned long long>(args.local_rows) * args.width;
     if (total == 0) return cudaSuccess;
-    if (args.scene.n_objects <= kSmallScene) {
+    if (args.scene.n_entries <= kSmallScene) {
         static int per_sm = 0;
         if (per_sm == 0) {
             cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_small_kernel, kSmallThreads, 0);

@@ -72,6 +72,9 @@ def load_library(path=LIB_PATH):
     lib.rtx_quantise.restype = C.c_int
     lib.rtx_quantise.argtypes = [ctx, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
                                  C.POINTER(abi.Stats)]
+    lib.rtx_tonemap.restype = C.c_int
+    lib.rtx_tonemap.argtypes = [ctx, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(abi.Params), C.c_void_p, C.c_int32,
+                                C.POINTER(C.c_double), C.POINTER(abi.Stats)]
     lib.rtx_unpermute_bands.restype = C.c_int
     lib.rtx_unpermute_bands.argtypes = [ctx, C.c_void_p, C.c_void_p] + [C.c_int32] * 6
     lib.rtx_ffma_peak.restype = C.c_int
@@ -97,7 +100,7 @@ def default_params(**overrides):
     p = abi.Params()
     load_library().rtx_default_params(C.byref(p))
     for k, v in overrides.items():
-        if k in ("light_pos", "ground_color", "sky_low", "sky_high"):
+        if k in ("light_pos", "ground_color", "sky_low", "sky_high", "sun_color", "sun_direction"):
             v = abi.Vec3(*v)
         if not hasattr(p, k):
             raise AttributeError("rtx_params has no field %r" % k)
@@ -230,6 +233,32 @@ class Renderer:
                                           C.byref(st)))
         self.last_stats = st
         return out.reshape(rad.shape[:-1]) if rad.ndim > 1 else out
+
+    def tonemap(self, radiance, params):
+        """EXTENSION (rtx_tonemap): Reinhard's global operator + 8-bit pack on a host float32/float64 array shaped
+        [n_frames][pixels][3] (or [n_frames][H][W][3]). Returns (rgba8 words shaped like the input minus the last axis,
+        log-average luminance per frame)."""
+        rad = np.ascontiguousarray(radiance)
+        if rad.dtype not in (np.float32, np.float64) or rad.ndim < 3 or rad.shape[-1] != 3:
+            raise ValueError("radiance must be float32/float64 shaped [n_frames][...][3]")
+        n_frames = rad.shape[0]
+        pixels = rad.size // 3 // n_frames
+        out = np.empty(rad.shape[:-1], np.uint32)
+        lavg = np.zeros(n_frames, np.float64)
+        st = abi.Stats()
+        p32 = rad.ctypes.data if rad.dtype == np.float32 else None
+        p64 = rad.ctypes.data if rad.dtype == np.float64 else None
+        self._check(self.lib.rtx_tonemap(self._ctx, p32, p64, pixels, n_frames, C.byref(params), out.ctypes.data, abi.RTX_MEM_HOST,
+                                         lavg.ctypes.data_as(C.POINTER(C.c_double)), C.byref(st)))
+        self.last_stats = st
+        return out, lavg
+
+    def tonemap_device(self, rad_ptr, is_f32, pixels_per_frame, n_frames, params, out_ptr):
+        st = abi.Stats()
+        self._check(self.lib.rtx_tonemap(self._ctx, rad_ptr if is_f32 else None, None if is_f32 else rad_ptr, int(pixels_per_frame),
+                                         int(n_frames), C.byref(params), out_ptr, abi.RTX_MEM_DEVICE, None, C.byref(st)))
+        self.last_stats = st
+        return st
 
     def quantise_device(self, rad_ptr, is_f32, n_pixels, out_ptr, mode=abi.RTX_QUANT_WRAP):
         st = abi.Stats()

@@ -110,8 +110,26 @@ class Wall:
         return o
 
 
+class Box:
+    """EXTENSION — not in the reference snapshot (README.md:21 names a sprint-2 `Box`; no code survives). An axis-aligned
+    box: `position` is the minimum corner, `size` the extents. Six Wall-like faces with ONE object id; the exact
+    semantics are the header's (include/rtx_b200.h, RTX_BOX) and oracle/oracle.c::box_intersect."""
+    kind = abi.RTX_BOX
+
+    def __init__(self, mat=None, position=(0, 0, 0), size=(1, 1, 1)):
+        self.mat = mat if mat is not None else default_mat()
+        self.position = _v(position)
+        self.size = _v(size)
+
+    def pod(self):
+        o = abi.ObjectPOD()
+        o.kind, o.mat = self.kind, self.mat.pod()
+        o.p, o.n = abi.Vec3(*self.position), abi.Vec3(*self.size)
+        return o
+
+
 def flatten(scene):
-    """list of Sphere/Wall in scene order (== object ids, main.cpp:80) -> ctypes array of rtx_object."""
+    """list of Sphere/Wall (/Box) in scene order (== object ids, main.cpp:80) -> ctypes array of rtx_object."""
     arr = (abi.ObjectPOD * max(len(scene), 1))()
     for k, g in enumerate(scene):
         arr[k] = g.pod()

@@ -31,14 +31,27 @@ def test_library_exports_every_declared_symbol(lib, pkg):
     assert lib.rtx_abi_version() == pkg.abi.ABI_VERSION
 
 
-def test_struct_sizes_match_header(pkg):
+def test_struct_sizes_match_header(pkg, tmp_path):
+    """ctypes mirror vs the C header itself: sizes and the offset of every field, as gcc lays them out."""
     a = pkg.abi
     assert C.sizeof(a.Vec3) == 24 and C.sizeof(a.MaterialPOD) == 64          # SURVEY.md §8(a) rows A, D
-    assert C.sizeof(a.ObjectPOD) == 8 + 64 + 24 + 24 + 16
-    assert C.sizeof(a.CameraPOD) == 4 * 24 + 8 and C.sizeof(a.CameraDesc) == 3 * 24 + 24
-    assert C.sizeof(a.Params) == 16 + 4 * 24 + 16 + 16 + 8
-    assert C.sizeof(a.Outputs) == 6 * 8 + 8 + 8
-    assert C.sizeof(a.Stats) == 5 * 8 + 4 * 8 + 8 + 8 + 16
+    pairs = [("rtx_vec3", a.Vec3), ("rtx_material", a.MaterialPOD), ("rtx_object", a.ObjectPOD), ("rtx_camera_desc", a.CameraDesc),
+             ("rtx_camera", a.CameraPOD), ("rtx_params", a.Params), ("rtx_outputs", a.Outputs), ("rtx_stats", a.Stats)]
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "rtx_b200.h"', "int main(void) {"]
+    for cname, ct in pairs:
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, ct in pairs:
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
 
 
 def test_no_cpu_fallback(lib, pkg):
