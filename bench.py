@@ -453,6 +453,23 @@ def main():
                                                    "unit": "GB/s", "frac": npx * bpp / (ms_q * 1e-3) / 1e9 / hbm_peak, "ms": ms_q,
                                                    "bytes_per_pixel": bpp, "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)"}
                 del rad
+            # extension: the Reinhard tone-map operator (two launches: luminance statistic, then map + pack) on the same
+            # frame; algorithmic bytes = the radiance read TWICE + 4 B written per pixel.
+            line["roofline_tonemap"] = {}
+            ptm = R.default_params(tonemap=abi.RTX_TONEMAP_REINHARD, quantise_mode=abi.RTX_QUANT_SATURATE)
+            for name, dt, bpp in (("f32", torch.float32, 28), ("f64", torch.float64, 52)):
+                rad = torch.rand(npx * 3, dtype=dt, device=dev) * 1.3
+                ts = []
+                for _ in range(7):
+                    flush.add_(1)
+                    torch.cuda.synchronize()
+                    ts.append(r.tonemap_device(rad.data_ptr(), dt == torch.float32, npx, 1, ptm, qout.data_ptr()).surface_update_ms)
+                ms_q = sorted(ts[2:])[len(ts[2:]) // 2]
+                line["roofline_tonemap"][name] = {"bound": "hbm", "achieved": npx * bpp / (ms_q * 1e-3) / 1e9, "peak": hbm_peak,
+                                                  "unit": "GB/s", "frac": npx * bpp / (ms_q * 1e-3) / 1e9 / hbm_peak, "ms": ms_q,
+                                                  "bytes_per_pixel": bpp, "launches": 2,
+                                                  "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)"}
+                del rad
         if world == 1 and args.workload == "auto" and not args.no_also:
             # BASELINE.json configs[1] (1080p default scene, depth 8) in the same run: device-resident and end to end
             spec2 = workload_spec("c2", 1)

@@ -23,7 +23,7 @@ for flag in RTX_MBOX_CAP=1 RTX_QUEUE_CAP=1; do
         -o "$here/test_builds/librtx_b200_$flag.so" &
 done
 wait
-cat "$here/csrc/api.cu" "$here/csrc/trace.cu" "$here/csrc/aux_kernels.cu" "$here/csrc/tonemap.cu" "$here/csrc/rtx_device.cuh" "$here/../include/rtx_b200.h" \
+cat $(ls "$here"/csrc/*.cu | LC_ALL=C sort) "$here/csrc/rtx_device.cuh" "$here/../include/rtx_b200.h" \
     | sha256sum | cut -d' ' -f1 > "$here/test_builds/SOURCES.sha256"
 echo "built $here/test_builds/"
 # C++ host facade example: the reference's main loop, headless (writes PPM). Links the C ABI only.

@@ -75,6 +75,15 @@ inline h3 hmul(h3 a, double s) { return h3{a.x * s, a.y * s, a.z * s}; }
 inline d3 D(h3 a) { return d3{a.x, a.y, a.z}; }
 inline double amax3(h3 a) { return std::fmax(std::fabs(a.x), std::fmax(std::fabs(a.y), std::fabs(a.z))); }
 
+// Bounding-sphere entry of a rectangle for the FP32 screen. An unbounded rectangle (non-finite extent) gets r = +inf,
+// which passes the screen for every ray — provided the centre is finite: half an infinite extent times a basis vector
+// with zero components is NaN, and a NaN test result would REJECT the entry. The centre is irrelevant then: use 0.
+inline float4 screen_entry(h3 centre, float r32)
+{
+    if (std::isinf(r32)) return make_float4(0.f, 0.f, 0.f, r32);
+    return make_float4(static_cast<float>(centre.x), static_cast<float>(centre.y), static_cast<float>(centre.z), r32);
+}
+
 int grow(rtx_ctx* ctx, void** p, size_t* cap, size_t need)
 {
     if (need <= *cap) return RTX_OK;
@@ -194,6 +203,10 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
     std::vector<WallDev> walls;
     std::vector<MaterialDev> mats(n);
     double bound = 0.0;
+    // Extent of the scene for the screen's error bound. Objects with non-finite geometry do not widen it (the bound
+    // would become infinite and send every entry of every ray to the exact test): they either have r = +inf in the
+    // screen (always pass) or NaN results there (rejected, and the reference's NaN comparisons never hit them either).
+    auto extend = [&bound](double x) { if (std::isfinite(x)) bound = std::fmax(bound, x); };
     for (int k = 0; k < n; k++) {
         const rtx_object& o = objects[k];
         if (o.kind != RTX_SPHERE && o.kind != RTX_WALL && o.kind != RTX_BOX) return fail(ctx, RTX_ERR_INVALID, "rtx_set_scene: unknown object kind");
@@ -214,7 +227,7 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
             if (!std::isfinite(o.a)) r32 = INFINITY;
             sph32.push_back(make_float4(static_cast<float>(o.p.x), static_cast<float>(o.p.y), static_cast<float>(o.p.z), r32));
             sph_key.push_back(k * 8);
-            bound = std::fmax(bound, amax3(H(o.p)) + std::fabs(o.a));
+            extend(amax3(H(o.p)) + std::fabs(o.a));
         } else if (o.kind == RTX_BOX) {
             // EXTENSION (rtx_b200.h, RTX_BOX): six Wall-like faces -x,+x,-y,+y,-z,+z that share the box's id; the trace
             // kernel sees them as walls (same exact test, same bounding-sphere screen), the face index is the low
@@ -240,9 +253,9 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
                 float r32 = static_cast<float>(0.5 * std::sqrt(size[r_ax] * size[r_ax] + size[u_ax] * size[u_ax]) * (1.0 + 1e-6));
                 r32 = std::nextafter(r32, INFINITY);
                 if (!std::isfinite(size[r_ax]) || !std::isfinite(size[u_ax])) r32 = INFINITY;
-                wall32.push_back(make_float4(static_cast<float>(centre.x), static_cast<float>(centre.y), static_cast<float>(centre.z), r32));
+                wall32.push_back(screen_entry(centre, r32));
             }
-            bound = std::fmax(bound, amax3(H(o.p)) + std::fabs(size[0]) + std::fabs(size[1]) + std::fabs(size[2]));
+            extend(amax3(H(o.p)) + std::fabs(size[0]) + std::fabs(size[1]) + std::fabs(size[2]));
         } else {
             slot[k] = static_cast<int32_t>(walls.size());
             WallDev w;
@@ -264,8 +277,8 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
             float r32 = static_cast<float>(0.5 * std::sqrt(o.a * o.a + o.b * o.b) * (1.0 + 1e-6));
             r32 = std::nextafter(r32, INFINITY);
             if (!std::isfinite(o.a) || !std::isfinite(o.b)) r32 = INFINITY;
-            wall32.push_back(make_float4(static_cast<float>(centre.x), static_cast<float>(centre.y), static_cast<float>(centre.z), r32));
-            bound = std::fmax(bound, amax3(H(o.p)) + std::fabs(o.a) + std::fabs(o.b));
+            wall32.push_back(screen_entry(centre, r32));
+            extend(amax3(H(o.p)) + std::fabs(o.a) + std::fabs(o.b));
         }
     }
     const int ns = static_cast<int>(sph64.size()), nw = static_cast<int>(walls.size());

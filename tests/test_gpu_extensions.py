@@ -68,9 +68,12 @@ def test_degenerate_boxes(gpu, renderer_mod, port, S):
     scene = S.default_scene() + [S.Box(mat, (2.0, -0.5, -0.5), (0.0, 1.0, 1.0)), S.Box(mat, (2.2, 0.2, 0.2), (-1.0, 1.0, 1.0)),
                                  S.Box(mat, (2.0, 0.0, 0.0), (float("inf"), 1.0, 1.0)), S.Box(mat, (float("nan"), 0.0, 0.0), (1.0, 1.0, 1.0))]
     scene += S.synthetic_scene(20, 2, seed=5)
+    scene.append(S.Wall(mat, (6.0, -3.0, -1.0), (-1, 0, 0), float("inf"), 2.0))      # a half-infinite strip: CAN be hit
     pod = S.default_camera(96, 1.0).pod()
     got, st = render(gpu, renderer_mod, scene, pod, 4)
-    check_frame(got, port.render(scene, pod, 4), st)
+    exp = port.render(scene, pod, 4)
+    check_frame(got, exp, st)
+    assert (exp["object_id"] == len(scene) - 1).sum() > 0 and (exp["object_id"] == 5).sum() > 0   # the strip and the unbounded box are visible
 
 
 @pytest.mark.parametrize("which", ["default", "synthetic"])

@@ -5,6 +5,7 @@ identical — the kernel takes every hit decision in the reference's own double 
 <= 1e-4 with denominator max(|ref|, 1e-3) — asserted here at the much tighter 1e-12, the only divergence being
 libm-vs-CUDA pow (<= 2 ulp) and the front-to-back accumulation order of the reflection lerp.
 """
+import glob
 import hashlib
 import sys
 
@@ -342,7 +343,7 @@ def test_overflow_paths_of_the_trace_kernel(tmp_path, renderer_mod, port, S, fla
     import subprocess
     pkg_dir = os.path.dirname(os.path.abspath(renderer_mod.__file__))
     root = os.path.dirname(pkg_dir)
-    sources = [os.path.join(pkg_dir, "csrc", f) for f in ("api.cu", "trace.cu", "aux_kernels.cu")]
+    sources = sorted(glob.glob(os.path.join(pkg_dir, "csrc", "*.cu")))      # the same list, in the same order, as build.sh
     lib = os.path.join(pkg_dir, "test_builds", "librtx_b200_%s.so" % flag[2:])      # prebuilt by build.sh
     headers = [os.path.join(pkg_dir, "csrc", "rtx_device.cuh"), os.path.join(root, "include", "rtx_b200.h")]
     digest = hashlib.sha256(b"".join(open(f, "rb").read() for f in sources + headers)).hexdigest()
