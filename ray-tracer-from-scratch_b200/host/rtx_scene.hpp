@@ -120,6 +120,24 @@ public:
     }
 };
 
+// EXTENSION — no reference class (README.md:21 names a sprint-2 `Box`; no code survives): an axis-aligned box given by
+// its minimum corner and extents; six Wall-like faces, ONE object id (include/rtx_b200.h, RTX_BOX).
+class Box : public SceneGeometry {
+    point3 position;   // minimum corner
+    vec3 size;         // extents along x, y, z
+public:
+    Box(Material m = default_mat(), point3 position = point3(0, 0, 0), vec3 size = vec3(1, 1, 1)) : SceneGeometry{m}, position{position}, size{size} {}
+    rtx_object describe() const override
+    {
+        rtx_object o{};
+        o.kind = RTX_BOX;
+        o.mat = get_material().pod();
+        o.p = position.pod();
+        o.n = size.pod();
+        return o;
+    }
+};
+
 using Scene = std::vector<std::unique_ptr<SceneGeometry>>;
 
 // ---- Camera (scene.h:86-112, scene.cpp:80-165) ---------------------------------------------------------------------

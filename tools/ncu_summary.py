@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Turns ncu captures brought back in gpurun_out/ into the small text summaries committed under profiles/.
 
-    python tools/ncu_summary.py <full.ncu-rep> <launches.csv> <out.md> [title]
+    python tools/ncu_summary.py <full.ncu-rep> <launches.csv | -> <out.md> [title]
+
+With "-" instead of a launch list only the per-kernel tables are written, and repeated launches of one kernel are
+collapsed into the first one plus the range of durations.
 """
 import csv
 import io
@@ -38,6 +41,18 @@ def main():
     title = sys.argv[4] if len(sys.argv) > 4 else rep
     hdr, units, kernels = raw(rep)
     lines = ["# " + title, "", "Source: `%s` (ncu --set full --clock-control none --import-source on), `%s` (launch list)." % (rep, launches), ""]
+    if launches == "-":   # collapse repeated launches of the same kernel
+        seen, kept = {}, []
+        for vals in kernels:
+            d = dict(zip(hdr, vals))
+            name = d.get("Kernel Name", "?")
+            dur = float(d.get("gpu__time_duration.sum", "0").replace(",", ""))
+            if name not in seen:
+                seen[name] = [dur, dur, 1]
+                kept.append(vals)
+            else:
+                seen[name] = [min(seen[name][0], dur), max(seen[name][1], dur), seen[name][2] + 1]
+        kernels = kept
     for vals in kernels:
         d = dict(zip(hdr, vals))
         u = dict(zip(hdr, units))
@@ -50,7 +65,14 @@ def main():
                      if h.startswith(STALL) and h.endswith("_per_issue_active.ratio") and d[h] not in ("", "n/a")), reverse=True)
         for v, name in st[:9]:
             lines.append("| %s | %.3f |" % (name, v))
+        if launches == "-":
+            lo, hi, n = seen[d.get("Kernel Name", "?")]
+            lines.append("%d launches captured, gpu__time_duration %.3f - %.3f %s." % (n, lo, hi, u.get("gpu__time_duration.sum", "")))
         lines.append("")
+    if launches == "-":
+        open(dst, "w").write("\n".join(lines) + "\n")
+        print("wrote", dst)
+        return
     # launch list
     rows = [r for r in csv.reader(open(launches)) if r and not r[0].startswith("==")]
     h = rows[0]
