@@ -2,7 +2,8 @@
 """Randomized parity soak (GPU box): random scenes, cameras, depths, frame sizes and parameters, CUDA path vs the C
 oracle. Ids, hit masks, ray counts and RGBA8 must be identical, radiance within 1e-12 relative.
 
-    python tools/fuzz_parity.py [seconds=120] [seed=1]          (FUZZ_BIG=1: larger scenes and frames)
+    python tools/fuzz_parity.py [seconds=120] [seed=1]          (FUZZ_BIG=1: larger scenes and frames;
+                                                                 FUZZ_EXT=1: also the extensions — boxes and the sun)
 """
 import importlib
 import os
@@ -40,6 +41,11 @@ def random_scene(rng):
         if abs(n[0]) + abs(n[1]) < 1e-3:
             n = (1.0, 0.0, n[2])
         scene.append(S.Wall(mat(), p, n, rng.uniform(0.2, 8) * scale, rng.uniform(0.2, 8) * scale))
+    if os.environ.get("FUZZ_EXT") == "1":
+        for _ in range(rng.choice([0, 1, 2, 5, 12, 40])):
+            p = (rng.uniform(-6, 12) * scale, rng.uniform(-8, 8) * scale, rng.uniform(-6, 6) * scale)
+            size = tuple(rng.choice([0.1, 0.5, 2.0, 6.0, 30.0]) * scale * rng.uniform(0.5, 1.5) for _ in range(3))
+            scene.append(S.Box(mat(), p, size))
     rng.shuffle(scene)                      # spheres and walls interleaved in scene order
     if scene and rng.random() < 0.3:        # exact duplicates: ties must go to the lower index
         scene.insert(rng.randrange(len(scene)), scene[rng.randrange(len(scene))])
@@ -81,6 +87,12 @@ def main():
                       reflect_offset=rng.choice([1e-4, 1e-3, 1e-6]), sky_exponent=rng.choice([0.25, 0.5, 1.0, 2.2]))
             for k, v in kw.items():
                 setattr(p, k, type(getattr(p, k))(*v) if isinstance(v, tuple) else v)
+        if os.environ.get("FUZZ_EXT") == "1" and rng.random() < 0.5:
+            ext = dict(sun_enabled=1, sun_color=(rng.uniform(0, 2), rng.uniform(0, 2), rng.uniform(0, 2)),
+                       sun_direction=(rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-1, 1) or 0.5))
+            for k, v in ext.items():
+                setattr(p, k, type(getattr(p, k))(*v) if isinstance(v, tuple) else v)
+            kw.update(ext)
         r.set_scene(scene)
         got, st = r.render([pod], R.default_params(max_depth=depth, **kw), want=want)
         exp = oracle.render(scene, pod, params=p)
