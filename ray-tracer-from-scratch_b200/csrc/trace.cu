@@ -413,10 +413,9 @@ struct FrameTotals {
 
 // Shade one finished segment of a chain (recursive_ray_tracing, main.cpp:89-119) and either set up the
 // reflected ray or write the pixel.
-__device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, FrameTotals& tot)
+__device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, const SceneDev& sc, FrameTotals& tot)
 {
     using namespace ex;
-    const SceneDev& sc = a.scene;
     c.rays++;
     const int best_id = c.best_key >> 3;          // object id (-1 stays -1); the low bits are the box face
     if (c.rays == 1) c.first_id = best_id;
@@ -557,7 +556,7 @@ __device__ __forceinline__ void start_pixel_body(Chain& c, unsigned long long p,
 }
 
 // Out-of-line wrappers for the big kernel (its chains live in local memory; the hot loop should stay small).
-__device__ __noinline__ void shade_chain(Chain& c, const TraceArgs& a, FrameTotals& tot) { shade_body(c, a, tot); }
+__device__ __noinline__ void shade_chain(Chain& c, const TraceArgs& a, FrameTotals& tot) { shade_body(c, a, a.scene, tot); }
 __device__ __noinline__ void start_pixel(Chain& c, unsigned long long p, const TraceArgs& a) { start_pixel_body(c, p, a); }
 
 // ---- small scenes ---------------------------------------------------------------------------------------------------
@@ -575,7 +574,28 @@ constexpr int kSmallThreads = 256;
 #endif
 __global__ void __launch_bounds__(kSmallThreads, RTX_SMALL_MINBLOCKS) trace_small_kernel(const TraceArgs a)
 {
-    const SceneDev& sc = a.scene;
+    // The whole scene (<= 16 entries, < 4 KB) is staged in shared memory once per CTA: every lane reads the same
+    // object at the same time, so these are broadcast LDS instead of L1/L2 round trips in front of every exact test
+    // and every shading step (ncu: long_scoreboard 1.4 warps per issue with the scene in global memory).
+    __shared__ SphereExact s_sph[kSmallScene];
+    __shared__ int32_t s_sph_key[kSmallScene];
+    __shared__ WallDev s_wall[kSmallScene];
+    __shared__ MaterialDev s_mat[kSmallScene];
+    __shared__ int32_t s_kind[kSmallScene], s_slot[kSmallScene];
+    {
+        const SceneDev& g = a.scene;
+        for (int i = threadIdx.x; i < g.n_spheres; i += kSmallThreads) { s_sph[i] = g.sph64[i]; s_sph_key[i] = g.sph_key[i]; }
+        for (int i = threadIdx.x; i < g.n_walls; i += kSmallThreads) s_wall[i] = g.walls[i];
+        for (int i = threadIdx.x; i < g.n_objects; i += kSmallThreads) { s_mat[i] = g.mats[i]; s_kind[i] = g.kind[i]; s_slot[i] = g.slot[i]; }
+        __syncthreads();
+    }
+    SceneDev sc = a.scene;
+    sc.sph64 = s_sph;
+    sc.sph_key = s_sph_key;
+    sc.walls = s_wall;
+    sc.mats = s_mat;
+    sc.kind = s_kind;
+    sc.slot = s_slot;
     const unsigned lane_id = threadIdx.x & 31u;
     const unsigned long long total_pixels =
         static_cast<unsigned long long>(a.n_frames) * static_cast<unsigned long long>(a.local_rows) * a.width;
@@ -611,7 +631,7 @@ __global__ void __launch_bounds__(kSmallThreads, RTX_SMALL_MINBLOCKS) trace_smal
                 const double t = wall_exact(c.o, c.d, w);
                 if (better(t, w.key, c.best_dist, c.best_key)) { c.best_dist = t; c.best_key = w.key; }
             }
-            shade_body(c, a, tot);
+            shade_body(c, a, sc, tot);
         }
     }
     __syncwarp();
