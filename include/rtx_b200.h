@@ -136,7 +136,8 @@ typedef struct rtx_params {
      * tonemap: RTX_TONEMAP_REINHARD applies Reinhard's global photographic operator per frame before the 8-bit
      *   pack: L = .2126 R + .7152 G + .0722 B, Lavg = exp(mean(log(1e-4 + L))), Ls = key / Lavg * L,
      *   Ld = Ls * (1 + Ls / white^2) / (1 + Ls) (white <= 0: Ld = Ls / (1 + Ls)), rgb *= Ld / L (0 where L <= 0).
-     *   Needs the whole frame on one GPU (n_ranks must be 1). */
+     *   Inside rtx_render it needs the whole frame on one GPU (n_ranks must be 1); row-sharded frames use the two-step
+     *   rtx_tonemap_sums / rtx_tonemap_apply with one integer all-reduce in between. */
     int32_t  sun_enabled;
     int32_t  tonemap;          /* RTX_TONEMAP_* */
     rtx_vec3 sun_color;        /* SUN_COLOR     (1.64,1.27,.99)     main.cpp:18 */
@@ -254,6 +255,18 @@ int rtx_quantise(rtx_ctx* ctx, const float* radiance_f32, const double* radiance
  * output is identical from run to run. */
 int rtx_tonemap(rtx_ctx* ctx, const float* radiance_f32, const double* radiance_f64, int64_t pixels_per_frame, int32_t n_frames,
                 const rtx_params* params, uint32_t* rgba8, int32_t memory, double* log_avg_luminance, rtx_stats* stats);
+
+/* The same operator in two steps, for frames whose rows are spread over several GPUs (DEVICE pointers only):
+ *   1. every rank: rtx_tonemap_sums ADDS the fixed-point log-luminance sums of its own pixels to sums[n_frames]
+ *      (int64, zeroed by the caller beforehand);
+ *   2. the caller all-reduces sums over the ranks with an integer SUM (NCCL over NVLink; sharding.py::tonemap_sharded) —
+ *      integer addition is associative, so the result does not depend on the number of ranks or the reduction order;
+ *   3. every rank: rtx_tonemap_apply maps and packs its own pixels with the global sums and the GLOBAL number of
+ *      pixels per frame. The assembled frame is bit for bit the one rtx_tonemap produces on a single GPU. */
+int rtx_tonemap_sums(rtx_ctx* ctx, const float* radiance_f32, const double* radiance_f64, int64_t pixels_per_frame, int32_t n_frames,
+                     int64_t* sums);
+int rtx_tonemap_apply(rtx_ctx* ctx, const float* radiance_f32, const double* radiance_f64, int64_t pixels_per_frame, int32_t n_frames,
+                      const int64_t* sums, int64_t pixels_per_frame_global, const rtx_params* params, uint32_t* rgba8, rtx_stats* stats);
 
 /* Multi-GPU gather epilogue: scatters a band-major buffer (n_ranks blocks of rows_per_rank rows, block r =
  * rank r's packed rows, as an all-gather delivers them) into a row-major frame. Device pointers,

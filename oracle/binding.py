@@ -68,6 +68,9 @@ class Oracle:
             f("quantise_f32", None, C.POINTER(C.c_float), C.c_int64, C.c_int32, C.POINTER(C.c_uint32))
             f("tonemap", None, C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_int64, C.c_int32, C.POINTER(abi.Params),
               C.POINTER(C.c_uint32), C.POINTER(C.c_double))
+            f("tonemap_sums", None, C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_int64, C.c_int32, C.POINTER(C.c_int64))
+            f("tonemap_apply", None, C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.c_int64,
+              C.POINTER(abi.Params), C.POINTER(C.c_uint32), C.POINTER(C.c_double))
 
     def _f(self, name, restype, *argtypes):
         fn = getattr(self.lib, self.prefix + name)
@@ -168,6 +171,21 @@ class Oracle:
             rgb = np.ascontiguousarray(rgb, dtype=np.float64)
             self._tonemap(_ptr(rgb, C.c_double), None, pixels, n_frames, C.byref(params), _ptr(out, C.c_uint32), _ptr(lavg, C.c_double))
         return out, lavg
+
+    def tonemap_sums(self, rgb, sums):
+        """Step 1 of the sharded tone map: ADDS the per-frame fixed-point sums of rgb [n_frames][pixels][3] (float64) to
+        the int64 array `sums`."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.float64)
+        self._tonemap_sums(_ptr(rgb, C.c_double), None, rgb.shape[1], rgb.shape[0], _ptr(sums, C.c_int64))
+        return sums
+
+    def tonemap_apply(self, rgb, sums, pixels_global, params):
+        """Step 2: maps and packs rgb [n_frames][pixels][3] with sums taken over pixels_global pixels per frame."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.float64)
+        out = np.zeros(rgb.shape[:2], np.uint32)
+        self._tonemap_apply(_ptr(rgb, C.c_double), None, rgb.shape[1], rgb.shape[0], _ptr(np.ascontiguousarray(sums, dtype=np.int64), C.c_int64),
+                            int(pixels_global), C.byref(params), _ptr(out, C.c_uint32), None)
+        return out
 
     def intersect(self, geom, origin, direction):
         obj = scene_mod.flatten([geom])

@@ -490,8 +490,8 @@ static double tm_lum(double r, double g, double b)
     double l = 0.2126 * r + 0.7152 * g + 0.0722 * b;
     return l > 0.0 ? l : 0.0;
 }
-void orc_tonemap(const double* rgb64, const float* rgb32, int64_t pixels, int32_t n_frames, const rtx_params* p, uint32_t* out,
-                 double* log_avg)
+/* Step 1: ADDS the fixed-point sums of this buffer's frames to sums[n_frames]. */
+void orc_tonemap_sums(const double* rgb64, const float* rgb32, int64_t pixels, int32_t n_frames, int64_t* sums)
 {
     const double fix = 4294967296.0;
     for (int32_t f = 0; f < n_frames; f++) {
@@ -502,7 +502,18 @@ void orc_tonemap(const double* rgb64, const float* rgb32, int64_t pixels, int32_
                    b = rgb64 ? rgb64[3 * k + 2] : (double)rgb32[3 * k + 2];
             sum += llrint(log(1e-4 + tm_lum(r, g, b)) * fix);
         }
-        const double mean = ((double)sum / fix) / (double)pixels;
+        sums[f] += sum;
+    }
+}
+/* Step 2: maps and packs this buffer's pixels with sums taken over pixels_global pixels per frame (>= pixels when the
+ * frame's rows are spread over several ranks and the sums were added up over them). */
+void orc_tonemap_apply(const double* rgb64, const float* rgb32, int64_t pixels, int32_t n_frames, const int64_t* sums,
+                       int64_t pixels_global, const rtx_params* p, uint32_t* out, double* log_avg)
+{
+    const double fix = 4294967296.0;
+    for (int32_t f = 0; f < n_frames; f++) {
+        const int64_t base = (int64_t)f * pixels;
+        const double mean = ((double)sums[f] / fix) / (double)pixels_global;
         const double lavg = exp(mean);
         const double key_over_avg = p->tonemap_key / lavg;
         const double inv_white2 = p->tonemap_white > 0.0 ? 1.0 / (p->tonemap_white * p->tonemap_white) : 0.0;
@@ -517,6 +528,14 @@ void orc_tonemap(const double* rgb64, const float* rgb32, int64_t pixels, int32_
             out[k] = pack_rgba(mk(r * s, g * s, b * s), p->quantise_mode);
         }
     }
+}
+void orc_tonemap(const double* rgb64, const float* rgb32, int64_t pixels, int32_t n_frames, const rtx_params* p, uint32_t* out,
+                 double* log_avg)
+{
+    int64_t* sums = (int64_t*)calloc((size_t)n_frames, sizeof(int64_t));
+    orc_tonemap_sums(rgb64, rgb32, pixels, n_frames, sums);
+    orc_tonemap_apply(rgb64, rgb32, pixels, n_frames, sums, pixels, p, out, log_avg);
+    free(sums);
 }
 
 /* ---- function-level doors (same signatures as the ref_* ones) ------------------------------------ */

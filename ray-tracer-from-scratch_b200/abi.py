@@ -79,6 +79,6 @@ class Stats(C.Structure):
 EXPORTS = (
     "rtx_abi_version", "rtx_status_string", "rtx_create", "rtx_destroy", "rtx_last_error", "rtx_set_stream",
     "rtx_set_scene", "rtx_camera_init", "rtx_default_params", "rtx_local_rows", "rtx_global_row",
-    "rtx_render", "rtx_quantise", "rtx_tonemap", "rtx_unpermute_bands", "rtx_ffma_peak",
+    "rtx_render", "rtx_quantise", "rtx_tonemap", "rtx_tonemap_sums", "rtx_tonemap_apply", "rtx_unpermute_bands", "rtx_ffma_peak",
     "rtx_buffer_alloc", "rtx_buffer_free", "rtx_buffer_export", "rtx_buffer_import", "rtx_buffer_release",
 )

@@ -538,9 +538,12 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
         if (tonemap) {
             int rc = grow(ctx, &ctx->d_tm_sums, &ctx->d_tm_sums_cap, sizeof(long long) * std::max(n_frames, 16));
             if (rc != RTX_OK) return rc;
-            RTX_CUDA(ctx, launch_tonemap_f64(rad_for_quant, static_cast<int64_t>(local_rows) * W, n_frames, p.tonemap_key, p.tonemap_white,
-                                             p.quantise_mode, static_cast<uint32_t*>(dev[0]), static_cast<long long*>(ctx->d_tm_sums),
-                                             ctx->d_counters, ctx->n_sms, st));
+            const int64_t ppf = static_cast<int64_t>(local_rows) * W;
+            long long* sums = static_cast<long long*>(ctx->d_tm_sums);
+            RTX_CUDA(ctx, cudaMemsetAsync(sums, 0, sizeof(long long) * n_frames, st));
+            RTX_CUDA(ctx, launch_tonemap_sums(nullptr, rad_for_quant, ppf, n_frames, sums, ctx->n_sms, st));
+            RTX_CUDA(ctx, launch_tonemap_apply(nullptr, rad_for_quant, ppf, n_frames, sums, ppf, p.tonemap_key, p.tonemap_white,
+                                               p.quantise_mode, static_cast<uint32_t*>(dev[0]), ctx->d_counters, ctx->n_sms, st));
             launches += 2;
         } else {
             RTX_CUDA(ctx, launch_quantise_f64(rad_for_quant, static_cast<int64_t>(n_px), p.quantise_mode,
@@ -670,12 +673,12 @@ int rtx_tonemap(rtx_ctx* ctx, const float* rad32, const double* rad64, int64_t p
     RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     long long* sums = static_cast<long long*>(ctx->d_tm_sums);
-    if (rad32)
-        RTX_CUDA(ctx, launch_tonemap_f32(static_cast<const float*>(d_in), pixels_per_frame, n_frames, p.tonemap_key, p.tonemap_white,
-                                         p.quantise_mode, d_o, sums, ctx->d_counters, ctx->n_sms, st));
-    else
-        RTX_CUDA(ctx, launch_tonemap_f64(static_cast<const double*>(d_in), pixels_per_frame, n_frames, p.tonemap_key, p.tonemap_white,
-                                         p.quantise_mode, d_o, sums, ctx->d_counters, ctx->n_sms, st));
+    const float* in32 = rad32 ? static_cast<const float*>(d_in) : nullptr;
+    const double* in64 = rad32 ? nullptr : static_cast<const double*>(d_in);
+    RTX_CUDA(ctx, cudaMemsetAsync(sums, 0, sizeof(long long) * n_frames, st));
+    RTX_CUDA(ctx, launch_tonemap_sums(in32, in64, pixels_per_frame, n_frames, sums, ctx->n_sms, st));
+    RTX_CUDA(ctx, launch_tonemap_apply(in32, in64, pixels_per_frame, n_frames, sums, pixels_per_frame, p.tonemap_key, p.tonemap_white,
+                                       p.quantise_mode, d_o, ctx->d_counters, ctx->n_sms, st));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     if (memory == RTX_MEM_HOST) RTX_CUDA(ctx, cudaMemcpyAsync(rgba8, d_o, n_px * 4, cudaMemcpyDeviceToHost, st));
     ctx->h_tm_sums.resize(n_frames);
@@ -697,6 +700,53 @@ int rtx_tonemap(rtx_ctx* ctx, const float* rad32, const double* rad64, int64_t p
         long long bits = static_cast<long long>(ctx->h_counters[3]);
         std::memcpy(&stats->max_luminance, &bits, sizeof bits);
         stats->launches = 2;
+    }
+    ctx->error.clear();
+    return RTX_OK;
+}
+
+int rtx_tonemap_sums(rtx_ctx* ctx, const float* rad32, const double* rad64, int64_t pixels_per_frame, int32_t n_frames, int64_t* sums)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    if ((rad32 == nullptr) == (rad64 == nullptr)) return fail(ctx, RTX_ERR_INVALID, "rtx_tonemap_sums: pass exactly one radiance buffer");
+    if (pixels_per_frame < 0 || n_frames <= 0 || !sums) return fail(ctx, RTX_ERR_INVALID, "rtx_tonemap_sums: bad size or null argument");
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64_t");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    RTX_CUDA(ctx, launch_tonemap_sums(rad32, rad64, pixels_per_frame, n_frames, reinterpret_cast<long long*>(sums), ctx->n_sms, ctx->stream));
+    RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->error.clear();
+    return RTX_OK;
+}
+
+int rtx_tonemap_apply(rtx_ctx* ctx, const float* rad32, const double* rad64, int64_t pixels_per_frame, int32_t n_frames, const int64_t* sums,
+                      int64_t pixels_per_frame_global, const rtx_params* params, uint32_t* rgba8, rtx_stats* stats)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    if ((rad32 == nullptr) == (rad64 == nullptr)) return fail(ctx, RTX_ERR_INVALID, "rtx_tonemap_apply: pass exactly one radiance buffer");
+    if (pixels_per_frame < 0 || n_frames <= 0 || !sums || !rgba8 || !params || pixels_per_frame_global < pixels_per_frame || pixels_per_frame_global <= 0)
+        return fail(ctx, RTX_ERR_INVALID, "rtx_tonemap_apply: bad size or null argument");
+    const rtx_params& p = *params;
+    if (p.tonemap != RTX_TONEMAP_REINHARD) return fail(ctx, RTX_ERR_INVALID, "rtx_tonemap_apply: params.tonemap must be RTX_TONEMAP_REINHARD");
+    if (!(p.tonemap_key > 0.0)) return fail(ctx, RTX_ERR_INVALID, "rtx_tonemap_apply: tonemap_key must be > 0");
+    if (p.quantise_mode != RTX_QUANT_WRAP && p.quantise_mode != RTX_QUANT_SATURATE) return fail(ctx, RTX_ERR_INVALID, "rtx_tonemap_apply: unknown quantise_mode");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    RTX_CUDA(ctx, launch_tonemap_apply(rad32, rad64, pixels_per_frame, n_frames, reinterpret_cast<const long long*>(sums), pixels_per_frame_global,
+                                       p.tonemap_key, p.tonemap_white, p.quantise_mode, rgba8, ctx->d_counters, ctx->n_sms, st));
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    RTX_CUDA(ctx, cudaStreamSynchronize(st));
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        stats->surface_update_ms = stats->total_ms = ms;
+        stats->over_range_pixels = ctx->h_counters[2];
+        long long bits = static_cast<long long>(ctx->h_counters[3]);
+        std::memcpy(&stats->max_luminance, &bits, sizeof bits);
+        stats->launches = 1;
     }
     ctx->error.clear();
     return RTX_OK;

@@ -170,10 +170,11 @@ cudaError_t launch_quantise_f64(const double* rad, int64_t n_pixels, int mode, u
                                 unsigned long long* counters, int n_sms, cudaStream_t stream);
 cudaError_t launch_quantise_f32(const float* rad, int64_t n_pixels, int mode, uint32_t* rgba8,
                                 unsigned long long* counters, int n_sms, cudaStream_t stream);
-cudaError_t launch_tonemap_f32(const float* rad, int64_t pixels_per_frame, int n_frames, double key, double white, int mode,
-                               uint32_t* rgba8, long long* sums, unsigned long long* counters, int n_sms, cudaStream_t stream);
-cudaError_t launch_tonemap_f64(const double* rad, int64_t pixels_per_frame, int n_frames, double key, double white, int mode,
-                               uint32_t* rgba8, long long* sums, unsigned long long* counters, int n_sms, cudaStream_t stream);
+cudaError_t launch_tonemap_sums(const float* rad32, const double* rad64, int64_t pixels_per_frame, int n_frames, long long* sums,
+                                int n_sms, cudaStream_t stream);
+cudaError_t launch_tonemap_apply(const float* rad32, const double* rad64, int64_t pixels_per_frame, int n_frames, const long long* sums,
+                                 int64_t pixels_global, double key, double white, int mode, uint32_t* rgba8, unsigned long long* counters,
+                                 int n_sms, cudaStream_t stream);
 cudaError_t launch_unpermute(const void* band_major, void* row_major, int height, int width, int elem_bytes,
                              int band_rows, int n_ranks, int rows_per_rank, cudaStream_t stream);
 cudaError_t run_ffma_peak(int variant, int n_sms, cudaStream_t stream, double* tflops, double* mhz);

@@ -117,12 +117,14 @@ __global__ void __launch_bounds__(256) tonemap_logsum_kernel(const T* __restrict
 
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) tonemap_pack_kernel(const T* __restrict__ rad, long long pixels, const long long* __restrict__ sums,
-                                                           double key, double white, int mode, uint32_t* __restrict__ out,
-                                                           unsigned long long* counters)
+                                                           long long pixels_global, double key, double white, int mode,
+                                                           uint32_t* __restrict__ out, unsigned long long* counters)
 {
+    // `pixels` = this buffer's pixels per frame; `pixels_global` = the pixels per frame the sums were taken over (more
+    // than `pixels` when the frame's rows are spread over several GPUs and the sums were all-reduced)
     const T* __restrict__ frame = rad + 3 * pixels * blockIdx.y;
     uint32_t* __restrict__ oframe = out + pixels * blockIdx.y;
-    const MapConsts c = map_consts(sums[blockIdx.y], pixels, key, white);
+    const MapConsts c = map_consts(sums[blockIdx.y], pixels_global, key, white);
     PackStats st{0ull, 0.0};
     const long long n_quads = pixels >> 2;
     for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < n_quads;
@@ -156,42 +158,60 @@ __global__ void __launch_bounds__(256) tonemap_pack_kernel(const T* __restrict__
 }
 
 template <typename T>
-cudaError_t launch_typed(const T* rad, long long pixels, int n_frames, double key, double white, int mode, uint32_t* rgba8,
-                         long long* sums, unsigned long long* counters, int n_sms, cudaStream_t stream)
+dim3 stream_grid2(long long pixels, int n_frames, int n_sms)
 {
     // whole waves: 8 CTAs of 256 threads per SM, shared between the frames of the call
     long long per_frame = (pixels / 4 + 255) / 256;
     const long long cap = std::max<long long>(1, static_cast<long long>(n_sms) * 8 / n_frames);
     per_frame = std::max<long long>(1, std::min(per_frame, cap));
-    const dim3 grid(static_cast<unsigned>(per_frame), static_cast<unsigned>(n_frames));
-    // vector path: every frame's base must be 16-byte aligned in both buffers
-    const bool vec = (pixels % 4 == 0) && (reinterpret_cast<uintptr_t>(rad) % 16 == 0) && (reinterpret_cast<uintptr_t>(rgba8) % 16 == 0);
-    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(long long) * n_frames, stream);
-    if (e != cudaSuccess) return e;
-    if (vec) {
+    return dim3(static_cast<unsigned>(per_frame), static_cast<unsigned>(n_frames));
+}
+
+// vector path: every frame's base must be 16-byte aligned
+inline bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
+
+template <typename T>
+cudaError_t launch_sums_typed(const T* rad, long long pixels, int n_frames, long long* sums, int n_sms, cudaStream_t stream)
+{
+    const dim3 grid = stream_grid2<T>(pixels, n_frames, n_sms);
+    if ((pixels % 4 == 0) && aligned16(rad))
         tonemap_logsum_kernel<T, true><<<grid, 256, 0, stream>>>(rad, pixels, sums);
-        tonemap_pack_kernel<T, true><<<grid, 256, 0, stream>>>(rad, pixels, sums, key, white, mode, rgba8, counters);
-    } else {
+    else
         tonemap_logsum_kernel<T, false><<<grid, 256, 0, stream>>>(rad, pixels, sums);
-        tonemap_pack_kernel<T, false><<<grid, 256, 0, stream>>>(rad, pixels, sums, key, white, mode, rgba8, counters);
-    }
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_apply_typed(const T* rad, long long pixels, int n_frames, const long long* sums, long long pixels_global, double key,
+                               double white, int mode, uint32_t* rgba8, unsigned long long* counters, int n_sms, cudaStream_t stream)
+{
+    const dim3 grid = stream_grid2<T>(pixels, n_frames, n_sms);
+    if ((pixels % 4 == 0) && aligned16(rad) && aligned16(rgba8))
+        tonemap_pack_kernel<T, true><<<grid, 256, 0, stream>>>(rad, pixels, sums, pixels_global, key, white, mode, rgba8, counters);
+    else
+        tonemap_pack_kernel<T, false><<<grid, 256, 0, stream>>>(rad, pixels, sums, pixels_global, key, white, mode, rgba8, counters);
     return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t launch_tonemap_f32(const float* rad, int64_t pixels_per_frame, int n_frames, double key, double white, int mode,
-                               uint32_t* rgba8, long long* sums, unsigned long long* counters, int n_sms, cudaStream_t stream)
+// Pass 1: ADDS this buffer's per-frame fixed-point sums to sums[n_frames] (the caller zeroes them first).
+cudaError_t launch_tonemap_sums(const float* rad32, const double* rad64, int64_t pixels_per_frame, int n_frames, long long* sums,
+                                int n_sms, cudaStream_t stream)
 {
     if (pixels_per_frame <= 0 || n_frames <= 0) return cudaSuccess;
-    return launch_typed<float>(rad, pixels_per_frame, n_frames, key, white, mode, rgba8, sums, counters, n_sms, stream);
+    return rad32 ? launch_sums_typed<float>(rad32, pixels_per_frame, n_frames, sums, n_sms, stream)
+                 : launch_sums_typed<double>(rad64, pixels_per_frame, n_frames, sums, n_sms, stream);
 }
 
-cudaError_t launch_tonemap_f64(const double* rad, int64_t pixels_per_frame, int n_frames, double key, double white, int mode,
-                               uint32_t* rgba8, long long* sums, unsigned long long* counters, int n_sms, cudaStream_t stream)
+// Pass 2: maps and packs with the given sums, taken over pixels_global pixels per frame.
+cudaError_t launch_tonemap_apply(const float* rad32, const double* rad64, int64_t pixels_per_frame, int n_frames, const long long* sums,
+                                 int64_t pixels_global, double key, double white, int mode, uint32_t* rgba8, unsigned long long* counters,
+                                 int n_sms, cudaStream_t stream)
 {
     if (pixels_per_frame <= 0 || n_frames <= 0) return cudaSuccess;
-    return launch_typed<double>(rad, pixels_per_frame, n_frames, key, white, mode, rgba8, sums, counters, n_sms, stream);
+    return rad32 ? launch_apply_typed<float>(rad32, pixels_per_frame, n_frames, sums, pixels_global, key, white, mode, rgba8, counters, n_sms, stream)
+                 : launch_apply_typed<double>(rad64, pixels_per_frame, n_frames, sums, pixels_global, key, white, mode, rgba8, counters, n_sms, stream);
 }
 
 }  // namespace rtx

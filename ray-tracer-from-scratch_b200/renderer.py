@@ -75,6 +75,11 @@ def load_library(path=LIB_PATH):
     lib.rtx_tonemap.restype = C.c_int
     lib.rtx_tonemap.argtypes = [ctx, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(abi.Params), C.c_void_p, C.c_int32,
                                 C.POINTER(C.c_double), C.POINTER(abi.Stats)]
+    lib.rtx_tonemap_sums.restype = C.c_int
+    lib.rtx_tonemap_sums.argtypes = [ctx, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    lib.rtx_tonemap_apply.restype = C.c_int
+    lib.rtx_tonemap_apply.argtypes = [ctx, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(abi.Params),
+                                      C.c_void_p, C.POINTER(abi.Stats)]
     lib.rtx_unpermute_bands.restype = C.c_int
     lib.rtx_unpermute_bands.argtypes = [ctx, C.c_void_p, C.c_void_p] + [C.c_int32] * 6
     lib.rtx_ffma_peak.restype = C.c_int
@@ -257,6 +262,19 @@ class Renderer:
         st = abi.Stats()
         self._check(self.lib.rtx_tonemap(self._ctx, rad_ptr if is_f32 else None, None if is_f32 else rad_ptr, int(pixels_per_frame),
                                          int(n_frames), C.byref(params), out_ptr, abi.RTX_MEM_DEVICE, None, C.byref(st)))
+        self.last_stats = st
+        return st
+
+    def tonemap_sums_device(self, rad_ptr, is_f32, pixels_per_frame, n_frames, sums_ptr):
+        """Step 1 of the sharded tone map: adds this buffer's per-frame fixed-point sums to the int64 device array."""
+        self._check(self.lib.rtx_tonemap_sums(self._ctx, rad_ptr if is_f32 else None, None if is_f32 else rad_ptr, int(pixels_per_frame),
+                                              int(n_frames), sums_ptr))
+
+    def tonemap_apply_device(self, rad_ptr, is_f32, pixels_per_frame, n_frames, sums_ptr, pixels_per_frame_global, params, out_ptr):
+        """Step 3 of the sharded tone map: maps and packs with the (all-reduced) sums over pixels_per_frame_global pixels."""
+        st = abi.Stats()
+        self._check(self.lib.rtx_tonemap_apply(self._ctx, rad_ptr if is_f32 else None, None if is_f32 else rad_ptr, int(pixels_per_frame),
+                                               int(n_frames), sums_ptr, int(pixels_per_frame_global), C.byref(params), out_ptr, C.byref(st)))
         self.last_stats = st
         return st
 

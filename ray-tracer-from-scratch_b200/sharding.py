@@ -46,6 +46,32 @@ def all_gather_blocks(local, world, group=None):
     return out
 
 
+def allreduce_tonemap_sums(sums, world, group=None):
+    """Step 2 of the row-sharded tone map (extension, rtx_tonemap_sums / rtx_tonemap_apply): the per-frame log-luminance
+    statistic is a 32.32 fixed-point INTEGER sum, so the all-reduce (SUM, int64; NCCL over NVLink on the GPUs) gives the
+    same value whatever the number of ranks and the reduction order — the assembled frame equals the single-GPU one bit
+    for bit. This is the one exchange the path has besides the final gather."""
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    return sums
+
+
+def tonemap_sharded(renderer, rad, pixels_per_frame_global, params, world, group=None):
+    """rad: this rank's radiance rows, a contiguous CUDA tensor [n_frames][rows][W][3] (float32 or float64).
+    Returns (int32 CUDA tensor [n_frames][rows][W] of RGBA8888 words for this rank's rows, the global int64 sums)."""
+    n_frames = rad.shape[0]
+    ppf = rad[0].numel() // 3
+    sums = torch.zeros(n_frames, dtype=torch.int64, device=rad.device)
+    out = torch.empty(tuple(rad.shape[:-1]), dtype=torch.int32, device=rad.device)
+    torch.cuda.current_stream(rad.device).synchronize()          # the zero fill is done before the kernel adds to it
+    renderer.tonemap_sums_device(rad.data_ptr(), rad.dtype == torch.float32, ppf, n_frames, sums.data_ptr())   # returns when complete
+    allreduce_tonemap_sums(sums, world, group)
+    torch.cuda.current_stream(rad.device).synchronize()          # ... and the all-reduce before the second pass reads it
+    renderer.tonemap_apply_device(rad.data_ptr(), rad.dtype == torch.float32, ppf, n_frames, sums.data_ptr(), pixels_per_frame_global,
+                                  params, out.data_ptr())
+    return out, sums
+
+
 def frame_owner(n_frames, world):
     """Frame f is rendered by rank f % world; returns the frames of each rank."""
     return [list(range(r, n_frames, world)) for r in range(world)]

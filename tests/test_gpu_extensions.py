@@ -137,6 +137,42 @@ def test_render_with_tonemap_equals_trace_then_operator(gpu, renderer_mod, port,
     assert not np.array_equal(plain["rgba8"], planes["rgba8"])
 
 
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("H,W,ranks,band", [(54, 96, 4, 4), (50, 37, 3, 3)])
+def test_row_sharded_tonemap_equals_single_gpu_bit_for_bit(gpu, renderer_mod, pkg, dtype, H, W, ranks, band):
+    """rtx_tonemap_sums on every rank's rows, the integer sums added up (what the all-reduce does), rtx_tonemap_apply on
+    every rank's rows: the assembled frames are identical to rtx_tonemap on the whole frames — the statistic is an
+    integer sum, so neither the split nor the order matters. Ranks are emulated on one GPU; the second geometry has
+    ragged bands and a pixel count that is not a multiple of four (scalar path)."""
+    import torch
+    SH = __import__("importlib").import_module("ray-tracer-from-scratch_b200.sharding")
+    dev = torch.device("cuda", 0)
+    F = 2
+    g = torch.Generator(device="cpu").manual_seed(H * W)
+    rad = torch.exp(torch.randn((F, H, W, 3), generator=g, dtype=torch.float64) * 1.5 - 1.0).to(getattr(torch, dtype)).to(dev)
+    params = renderer_mod.default_params(tonemap=pkg.abi.RTX_TONEMAP_REINHARD, quantise_mode=pkg.abi.RTX_QUANT_SATURATE, tonemap_white=2.0)
+    whole = torch.empty((F, H, W), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    gpu.tonemap_device(rad.data_ptr(), dtype == "float32", H * W, F, params, whole.data_ptr())
+    # pass 1 on every rank's rows into ONE accumulator = local sums + integer all-reduce
+    rows = [torch.as_tensor(renderer_mod.global_rows(H, band, ranks, r).astype("int64"), device=dev) for r in range(ranks)]
+    local = [rad[:, rows[r]].contiguous() for r in range(ranks)]
+    sums = torch.zeros(F, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    for r in range(ranks):
+        gpu.tonemap_sums_device(local[r].data_ptr(), dtype == "float32", local[r][0].numel() // 3, F, sums.data_ptr())
+    assembled = torch.zeros((F, H, W), dtype=torch.int32, device=dev)
+    for r in range(ranks):
+        out = torch.empty(tuple(local[r].shape[:-1]), dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        gpu.tonemap_apply_device(local[r].data_ptr(), dtype == "float32", local[r][0].numel() // 3, F, sums.data_ptr(), H * W, params, out.data_ptr())
+        assembled[:, rows[r]] = out
+    assert torch.equal(assembled, whole)
+    # the one-process form of the product helper (world = 1) gives the same frames
+    out1, sums1 = SH.tonemap_sharded(gpu, rad, H * W, params, 1)
+    assert torch.equal(out1, whole) and torch.equal(sums1, sums)
+
+
 def test_tonemap_error_paths(gpu, renderer_mod, pkg, S):
     gpu.set_scene(S.default_scene())
     pod = S.default_camera(32, 1.0).pod()

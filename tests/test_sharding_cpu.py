@@ -58,6 +58,25 @@ def _worker(rank, world, port, H, W, band, result_path):
             frame[g] = gathered[r][: len(g)].numpy().view(np.uint32)
         ok = ok and np.array_equal(frame, full["rgba8"]) and int(total_rays.item()) == full["total_rays"]
 
+    # ---- extension: row-sharded tone map = local sums, ONE integer all-reduce, local apply (sharding.allreduce_tonemap_sums) ----
+    p = oracle.default_params()
+    p.tonemap, p.quantise_mode, p.tonemap_white = pkg.abi.RTX_TONEMAP_REINHARD, pkg.abi.RTX_QUANT_SATURATE, 3.0
+    rad_mine = oracle.render(scene, pod, 6, rows=rows, want=("radiance",))["radiance"].reshape(1, -1, 3)
+    sums = torch.zeros(1, dtype=torch.int64)
+    oracle.tonemap_sums(rad_mine, sums.numpy())
+    SH.allreduce_tonemap_sums(sums, world)
+    tm_local = torch.zeros((rpr, W), dtype=torch.int32)
+    tm_local[: len(rows)] = torch.from_numpy(oracle.tonemap_apply(rad_mine, sums.numpy(), H * W, p).reshape(len(rows), W).view(np.int32))
+    tm_gathered = SH.all_gather_blocks(tm_local, world)
+    if rank == 0:
+        rad_full = oracle.render(scene, pod, 6, want=("radiance",))["radiance"].reshape(1, -1, 3)
+        exp_tm, _ = oracle.tonemap(rad_full, p)
+        tm = np.zeros((H, W), np.uint32)
+        for r in range(world):
+            g = R.global_rows(H, band, world, r)
+            tm[g] = tm_gathered[r][: len(g)].numpy().view(np.uint32)
+        ok = ok and np.array_equal(tm, exp_tm.reshape(H, W))          # bit for bit: the integer statistic does not depend on the split
+
     # ---- camera path, frames sharded (config C5's shape) ----
     cams = [c.pod() for c in S.flythrough_cameras(256, 32, 16.0 / 9.0)[::51]]     # 6 frames, ragged over 2 ranks? 6/2 = 3 each
     cams = cams[:5]                                                               # 5 frames: ragged
