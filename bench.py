@@ -8,9 +8,13 @@
 A "step" renders one batch of the workload through the C ABI (include/rtx_b200.h):
 
     c2  1920x1080, default scene (main.cpp:160-163), depth 8                      BASELINE.json configs[1]
-    c3  3840x2160, synthetic 10 000 spheres + 64 walls, depth 10                  configs[2]  (auto, N = 1)
-    c4  7680x4320, same scene, cyclic 4-row bands over N ranks + all-gather       configs[3]  (auto, N > 1)
+    c3  3840x2160, synthetic 10 000 spheres + 64 walls, depth 10                  configs[2]
+    c4  7680x4320, same scene, cyclic 4-row bands over the N ranks                configs[3]  (auto, every N)
     c5  256 x 1080p camera orbit of the default scene, frames sharded over ranks  configs[4]
+
+The default workload is c4 at every N: BASELINE.json quotes its metric "at 1080p/8K, 1/2/4/8 B200", the 8K frame fits one
+GPU (0.2 s per frame), and one workload for the whole N = 1, 2, 4, 8 series makes it a literal strong-scaling run. The
+default N = 1 run additionally measures c2 (1080p) and c3 (4K) and reports them under `also`.
 
 Metric (BASELINE.json): Mrays/s = rays traced (primary + reflections, equal to the reference's count) / time.
 `value`  : device-resident — scene and cameras already in HBM, outputs stay in HBM (CUDA events, max over ranks).
@@ -57,11 +61,11 @@ def parse_args():
 
 def workload_spec(name, n_gpus, scale=1.0):
     if name == "auto":
-        name = "c3" if n_gpus == 1 else "c4"
+        name = "c4"
     spec = {
         "c2": dict(width=1920, depth=8, scene="default", frames=1, label="c2: 1920x1080 default scene (1 sphere + 2 walls), depth 8"),
         "c3": dict(width=3840, depth=10, scene="synthetic", frames=1, label="c3: 3840x2160 synthetic 10000 spheres + 64 walls, depth 10, brute force"),
-        "c4": dict(width=7680, depth=10, scene="synthetic", frames=1, label="c4: 7680x4320 synthetic 10000 spheres + 64 walls, depth 10, cyclic row bands + all-gather"),
+        "c4": dict(width=7680, depth=10, scene="synthetic", frames=1, label="c4: 7680x4320 synthetic 10000 spheres + 64 walls, depth 10, brute force (cyclic row bands over the ranks when N > 1)"),
         "c5": dict(width=1920, depth=10, scene="default", frames=256, label="c5: 256-frame 1080p orbit of the default scene, frames sharded over ranks"),
     }[name]
     spec = dict(spec, name=name)
@@ -511,6 +515,24 @@ def main():
                 except Exception as e:
                     line["also"]["c2"]["cpu_baseline"] = {"unavailable": repr(e)}
             r.set_scene(objs)
+            # BASELINE.json configs[2] (4K, the same 10 064-object scene): device-resident kernel time and roofline
+            spec3 = workload_spec("c3", 1)
+            pod3 = S.default_camera(spec3["width"], 16.0 / 9.0).pod()
+            dev3 = torch.empty((pod3.height, pod3.width), dtype=torch.int32, device=dev)
+            o3 = abi.Outputs()
+            o3.memory, o3.rgba8 = abi.RTX_MEM_DEVICE, dev3.data_ptr()
+            p3 = R.default_params(max_depth=spec3["depth"])
+            ks = []
+            for _ in range(8):
+                flush.add_(1)
+                torch.cuda.synchronize()
+                st3 = r.render_raw([pod3], p3, o3)
+                ks.append(st3.raytracing_ms)
+            k3 = sorted(ks[3:])[len(ks[3:]) // 2]
+            fl3 = st3.total_rays * (n_spheres * FLOP_SPHERE + n_walls * FLOP_WALL)
+            line["also"]["c3"] = {"workload": spec3["label"], "rays_per_frame": st3.total_rays,
+                                  "device": {"kernel_ms": k3, "mrays_s": st3.total_rays / (k3 * 1e-3) / 1e6,
+                                             "tflops_algorithmic": fl3 / (k3 * 1e-3) / 1e12, "frac_of_fp32_peak": fl3 / (k3 * 1e-3) / 1e12 / peak}}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(args, spec, S, scene, pods)
