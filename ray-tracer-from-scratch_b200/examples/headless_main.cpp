@@ -8,7 +8,11 @@
 // CUDA-event times. The window/renderer/texture calls are replaced by a binary PPM (or raw RGBA8888) file.
 //
 //   rtx_headless [--width 640] [--aspect 1] [--depth 10] [--frames 3] [--keys wwad] [--out frame.ppm] [--raw frame.rgba]
-//                [--png frame.png]
+//                [--png frame.png] [--sun 1] [--tonemap 1] [--box 1]
+// --keys: one key event per frame — w s a d as in the reference (main.cpp:262-306); j l i k = the mouse look the reference
+// leaves commented out (rotate_left_right(+-0.05), rotate_up_down(+-0.05), main.cpp:319-323); anything else = no event.
+// --sun / --tonemap / --box switch on this repo's EXTENSIONS (default-off; include/rtx_b200.h): the sun of main.cpp:18-19
+// as a directional light, Reinhard's operator (saturating pack) in the surface update, a red box added to the scene.
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -85,6 +89,7 @@ int main(int argc, char* argv[])
     int width = 640, depth = 10, frames = 3;
     double aspect = 1.0;   // ASPECT_RATIO = 4/3 is integer division = 1 in the reference (main.cpp:25)
     std::string keys, out_ppm = "frame.ppm", out_raw, out_png;
+    bool ext_sun = false, ext_tonemap = false, ext_box = false;
     for (int k = 1; k + 1 < argc; k += 2) {
         const std::string a = argv[k];
         if (a == "--width") width = std::atoi(argv[k + 1]);
@@ -95,6 +100,9 @@ int main(int argc, char* argv[])
         else if (a == "--out") out_ppm = argv[k + 1];
         else if (a == "--raw") out_raw = argv[k + 1];
         else if (a == "--png") out_png = argv[k + 1];
+        else if (a == "--sun") ext_sun = std::atoi(argv[k + 1]) != 0;
+        else if (a == "--tonemap") ext_tonemap = std::atoi(argv[k + 1]) != 0;
+        else if (a == "--box") ext_box = std::atoi(argv[k + 1]) != 0;
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     try {
@@ -118,8 +126,15 @@ int main(int argc, char* argv[])
         const int pitch = W * 4;
         std::vector<std::vector<RGB>> frame_buffer(H, std::vector<RGB>(W, RGB(0, 0, 0)));   // [row][column]
 
+        if (ext_box) scene.push_back(std::make_unique<Box>(Material(RGB(0.9, 0.2, 0.2), 0.6), point3(2.5, -1.0, -0.8), vec3(1.0, 1.2, 0.9)));
+
         Renderer renderer(0);
         renderer.params.max_depth = depth;
+        if (ext_sun) renderer.params.sun_enabled = 1;
+        if (ext_tonemap) {
+            renderer.params.tonemap = RTX_TONEMAP_REINHARD;
+            renderer.params.quantise_mode = RTX_QUANT_SATURATE;
+        }
         std::vector<int64_t> total_times, rt_times, surface_update_times;
         std::vector<double> device_rt_ms, device_surface_ms;
         for (int frame = 0; frame < frames; frame++) {

@@ -281,7 +281,8 @@ public:
         }
     }
 
-    // The quantise loop (main.cpp:338-347) on a frame buffer the caller already holds.
+    // The quantise loop (main.cpp:338-347) on a frame buffer the caller already holds (with params.tonemap set: the
+    // tone-map extension followed by the same pack).
     void update_surface(const std::vector<std::vector<RGB>>& frame_buffer, size_t H, size_t W, uint32_t* pixels, int pitch)
     {
         radiance.resize(W * H * 3);
@@ -292,8 +293,12 @@ public:
                 dst[0] = v.x; dst[1] = v.y; dst[2] = v.z;
             }
         surface.resize(W * H);
-        check(rtx_quantise(ctx, nullptr, radiance.data(), static_cast<int64_t>(W * H), params.quantise_mode, surface.data(), RTX_MEM_HOST, &stats),
-              "rtx_quantise");
+        if (params.tonemap == RTX_TONEMAP_REINHARD)   // extension: global operator before the pack (off by default)
+            check(rtx_tonemap(ctx, nullptr, radiance.data(), static_cast<int64_t>(W * H), 1, &params, surface.data(), RTX_MEM_HOST, nullptr, &stats),
+                  "rtx_tonemap");
+        else
+            check(rtx_quantise(ctx, nullptr, radiance.data(), static_cast<int64_t>(W * H), params.quantise_mode, surface.data(), RTX_MEM_HOST, &stats),
+                  "rtx_quantise");
         for (size_t i = 0; i < H; i++)
             for (size_t j = 0; j < W; j++) pixels[i * (pitch / 4) + j] = surface[i * W + j];
     }

@@ -173,6 +173,29 @@ def test_row_sharded_tonemap_equals_single_gpu_bit_for_bit(gpu, renderer_mod, pk
     assert torch.equal(out1, whole) and torch.equal(sums1, sums)
 
 
+def test_cpp_headless_main_with_extensions(tmp_path, renderer_mod, port, pkg, S):
+    """The C++ facade end to end with the extensions on: Box in the scene, sun in the shading, and the tone map in the
+    surface update (Renderer::update_surface -> rtx_tonemap), against the oracle's specification of the same pipeline."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(renderer_mod.__file__)), "rtx_headless")
+    raw = tmp_path / "e.rgba"
+    subprocess.run([exe, "--width", "192", "--aspect", "1.5", "--depth", "6", "--frames", "2", "--keys", "xd", "--sun", "1", "--tonemap", "1",
+                    "--box", "1", "--raw", str(raw), "--out", ""], check=True, capture_output=True)
+    scene = S.default_scene() + [S.Box(S.Material((0.9, 0.2, 0.2), 0.6), (2.5, -1.0, -0.8), (1.0, 1.2, 0.9))]
+    cam = S.default_camera(192, 1.5)
+    _, pod = port.camera_walk(cam, [("d", 0)])                       # frame 1: after one step to the right
+    p = port.default_params()
+    p.max_depth, p.sun_enabled = 6, 1
+    p.tonemap, p.quantise_mode = pkg.abi.RTX_TONEMAP_REINHARD, pkg.abi.RTX_QUANT_SATURATE
+    rad = port.render(scene, pod, params=p)["radiance"]
+    exp, _ = port.tonemap(rad.reshape(1, -1, 3), p)
+    got = np.fromfile(raw, dtype=np.uint32).reshape(pod.height, pod.width)
+    d = _lsb(got.reshape(1, -1), exp)
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+    assert (port.render(scene, pod, params=p)["object_id"] == 3).sum() > 50     # the box is in view
+
+
 def test_tonemap_error_paths(gpu, renderer_mod, pkg, S):
     gpu.set_scene(S.default_scene())
     pod = S.default_camera(32, 1.0).pod()
