@@ -562,7 +562,7 @@ __device__ __noinline__ void start_pixel(Chain& c, unsigned long long p, const T
 // ---- small scenes ---------------------------------------------------------------------------------------------------
 // A handful of objects (the reference's own scene has three) needs no screen: the frame is bound by the double
 // shading and, in the big kernel, by instruction-cache misses and local-memory round trips of the chain state
-// (ncu on config C2: no_instruction 3.5, long_scoreboard 3.8 warps per issue; profiles/r1_trace_c2_ncu.md).
+// (ncu on config C2: no_instruction 3.5, long_scoreboard 3.8 warps per issue; profiles/r1_trace_c2_bigkernel_ncu.md).
 // This kernel is the same algorithm without the machinery: one chain per lane held in registers, every object tested
 // with the exact double routines, persistent lanes refilled from the same pixel counter. Results are identical by
 // construction (same sphere_exact / wall_exact / better / shade_body).
