@@ -365,24 +365,21 @@ void orc_camera_walk(const rtx_camera_desc* d, const char* ops, const double* ar
             case 's': position = sub(position, scale(unit(direction), movement_speed)); break;
             case 'd': position = add(position, scale(cam_right_vec(direction, vup), movement_speed)); break;
             case 'a': position = sub(position, scale(cam_right_vec(direction, vup), movement_speed)); break;
-            case 'y': {
-                double current_angle = atan2(direction.y, direction.x);
-                double new_angle = current_angle + args[k];
-                double base_length = len(mk(direction.x, direction.y, 0));
-                direction = mk(cos(new_angle) * base_length, sin(new_angle) * base_length, direction.z);
+            case 'y': {   /* rotate_left_right: yaw about z, the planar length and z are kept */
+                double planar = len(mk(direction.x, direction.y, 0));
+                double yaw = atan2(direction.y, direction.x) + args[k];
+                direction = mk(cos(yaw) * planar, sin(yaw) * planar, direction.z);
                 vup = cam_up_vec(direction, vup);
                 break;
             }
-            case 'p': {
-                double base_length = len(mk(direction.x, direction.y, 0));
-                double pitch_angle = atan2(direction.z, base_length);
-                double new_pitch_angle = pitch_angle + args[k];
-                new_pitch_angle = new_pitch_angle > ORC_PI / 2 ? pitch_angle : new_pitch_angle;
-                new_pitch_angle = new_pitch_angle < -ORC_PI / 2 ? -pitch_angle : new_pitch_angle;
-                double new_z = sin(new_pitch_angle);
-                double new_base_length = cos(new_pitch_angle);
-                v3 new_base_vector = scale(unit(mk(direction.x, direction.y, 0)), new_base_length);
-                direction = mk(new_base_vector.x, new_base_vector.y, new_z);
+            case 'p': {   /* rotate_up_down: unit vector over the old heading; the two clamps are the reference's, sign flip included */
+                v3 flat = mk(direction.x, direction.y, 0);
+                double pitch = atan2(direction.z, len(flat));
+                double target = pitch + args[k];
+                if (target > ORC_PI / 2) target = pitch;
+                if (target < -ORC_PI / 2) target = -pitch;
+                v3 heading = scale(unit(flat), cos(target));
+                direction = mk(heading.x, heading.y, sin(target));
                 vup = cam_up_vec(direction, vup);
                 break;
             }

@@ -174,23 +174,23 @@ public:
     // rotation shows in the image only through later right()/left() moves unless the caller re-aims lookat itself.
     void rotate_left_right(double angle)
     {
-        const double current_angle = std::atan2(direction.y, direction.x);
-        const double new_angle = current_angle + angle;
-        const double base_length = vec3(direction.x, direction.y, 0).length();
-        direction = vec3(std::cos(new_angle) * base_length, std::sin(new_angle) * base_length, direction.z);
+        // yaw about z (scene.cpp:137-145): the planar part of `direction` keeps its length and turns by `angle`, z stays
+        const double planar = vec3(direction.x, direction.y, 0).length();
+        const double yaw = std::atan2(direction.y, direction.x) + angle;
+        direction = vec3(std::cos(yaw) * planar, std::sin(yaw) * planar, direction.z);
         vup = up_vec();
     }
     void rotate_up_down(double angle)
     {
-        const double base_length = vec3(direction.x, direction.y, 0).length();
-        const double pitch_angle = std::atan2(direction.z, base_length);
-        double new_pitch_angle = pitch_angle + angle;
-        new_pitch_angle = new_pitch_angle > M_PI / 2 ? pitch_angle : new_pitch_angle;
-        new_pitch_angle = new_pitch_angle < -M_PI / 2 ? -pitch_angle : new_pitch_angle;     // sic (scene.cpp:156)
-        const double new_z = std::sin(new_pitch_angle);
-        const double new_base_length = std::cos(new_pitch_angle);
-        const vec3 new_base_vector = vec3(direction.x, direction.y, 0).normalize() * new_base_length;
-        direction = vec3(new_base_vector.x, new_base_vector.y, new_z);
+        // pitch (scene.cpp:147-165): the result is a UNIT vector over the old heading. Past the zenith the pitch stays
+        // what it was; past the nadir the reference takes MINUS the old pitch (scene.cpp:156) — kept as is.
+        const vec3 flat(direction.x, direction.y, 0);
+        const double pitch = std::atan2(direction.z, flat.length());
+        double target = pitch + angle;
+        if (target > M_PI / 2) target = pitch;
+        if (target < -M_PI / 2) target = -pitch;
+        const vec3 heading = flat.normalize() * std::cos(target);
+        direction = vec3(heading.x, heading.y, std::sin(target));
         vup = up_vec();
     }
 

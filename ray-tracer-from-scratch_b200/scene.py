@@ -209,26 +209,27 @@ class Camera:
         self.position = _sub(_v(self.position), _mul(self.right_vec(), self.movement_speed))      # scene.cpp:133-135
 
     def rotate_left_right(self, angle):
-        """scene.cpp:137-145: yaw about z through atan2 / cos / sin, then vup = up_vec()."""
+        """scene.cpp:137-145: yaw about z — the planar part of `direction` keeps its length and turns by `angle`;
+        then vup = up_vec()."""
         dx, dy, dz = _v(self.direction)
-        new_angle = math.atan2(dy, dx) + angle
-        base_length = _length((dx, dy, 0.0))
-        self.direction = (math.cos(new_angle) * base_length, math.sin(new_angle) * base_length, dz)
+        planar = _length((dx, dy, 0.0))
+        yaw = math.atan2(dy, dx) + angle
+        self.direction = (math.cos(yaw) * planar, math.sin(yaw) * planar, dz)
         self.vup = self.up_vec()
 
     def rotate_up_down(self, angle):
-        """scene.cpp:147-165: pitch through atan2 / sin / cos. Past +pi/2 the old pitch is kept, past -pi/2 it becomes
-        MINUS the old pitch (the reference's own asymmetry, scene.cpp:155-156). Then vup = up_vec()."""
+        """scene.cpp:147-165: pitch; the result is a unit vector over the old heading. Past the zenith the pitch stays,
+        past the nadir it becomes MINUS the old pitch (the reference's own asymmetry, scene.cpp:156). Then vup = up_vec()."""
         dx, dy, dz = _v(self.direction)
-        base_length = _length((dx, dy, 0.0))
-        pitch_angle = math.atan2(dz, base_length)
-        new_pitch_angle = pitch_angle + angle
-        new_pitch_angle = pitch_angle if new_pitch_angle > math.pi / 2 else new_pitch_angle
-        new_pitch_angle = -pitch_angle if new_pitch_angle < -math.pi / 2 else new_pitch_angle
-        new_z = math.sin(new_pitch_angle)
-        new_base_length = math.cos(new_pitch_angle)
-        nb = _mul(_normalize((dx, dy, 0.0)), new_base_length)
-        self.direction = (nb[0], nb[1], new_z)
+        flat = (dx, dy, 0.0)
+        pitch = math.atan2(dz, _length(flat))
+        target = pitch + angle
+        if target > math.pi / 2:
+            target = pitch
+        if target < -math.pi / 2:
+            target = -pitch
+        heading = _mul(_normalize(flat), math.cos(target))
+        self.direction = (heading[0], heading[1], math.sin(target))
         self.vup = self.up_vec()
 
     def pod(self):
