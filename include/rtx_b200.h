@@ -184,7 +184,7 @@ typedef struct rtx_stats {
     double   total_ms;           /* first event to last event */
     uint64_t total_rays;         /* sum of ray_count over all pixels rendered by this call */
     uint64_t sphere_tests;       /* total_rays * n_spheres */
-    uint64_t wall_tests;         /* total_rays * n_walls   */
+    uint64_t wall_tests;         /* total_rays * (n_walls + 6 per RTX_BOX: a box is six wall-like faces) */
     uint64_t over_range_pixels;  /* pixels with a channel outside [0, 256/255): quantise wraps there */
     double   max_luminance;      /* max over pixels of (R+G+B)/3; diagnostic only, never alters pixels */
     int32_t  launches;           /* kernels launched by the call */
