@@ -288,7 +288,8 @@ int rtx_buffer_release(rtx_ctx* ctx, void* imported_ptr);
  * returns achieved TFLOP/s of a dependent-chain-free FFMA loop over the whole chip. variant 0 = scalar
  * FFMA, 1 = packed fma.rn.f32x2 with two operands shared by all instructions, 2..4 = packed with three /
  * two-plus-one-shared / two distinct register pairs per instruction (register-file bandwidth probes), 5..6 =
- * packed and scalar FMAs interleaved (is there a second FP32 pipe? no: 66-68 vs 74 TFLOP/s). */
+ * packed and scalar FMAs interleaved (is there a second FP32 pipe? no: 66-68 vs 74 TFLOP/s), 7 = packed HALF FMAs
+ * (fma.rn.f16x2; reported in half-precision TFLOP/s; not used by any kernel, a data point only). */
 int rtx_ffma_peak(rtx_ctx* ctx, int32_t variant, double* tflops, double* sm_clock_mhz_estimate);
 
 #ifdef __cplusplus

@@ -817,7 +817,7 @@ int rtx_buffer_release(rtx_ctx* ctx, void* imported_ptr)
 int rtx_ffma_peak(rtx_ctx* ctx, int32_t variant, double* tflops, double* mhz)
 {
     if (!ctx) return RTX_ERR_INVALID;
-    if (variant < 0 || variant > 6) return fail(ctx, RTX_ERR_INVALID, "rtx_ffma_peak: variant must be 0..6");
+    if (variant < 0 || variant > 7) return fail(ctx, RTX_ERR_INVALID, "rtx_ffma_peak: variant must be 0..7");
     RTX_CUDA(ctx, cudaSetDevice(ctx->device));
     RTX_CUDA(ctx, run_ffma_peak(variant, ctx->n_sms, ctx->stream, tflops, mhz));
     ctx->error.clear();

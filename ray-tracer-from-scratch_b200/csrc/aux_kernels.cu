@@ -300,6 +300,31 @@ __global__ void __launch_bounds__(512) ffma_peak_mixed(float* sink, float a, flo
     if (blockIdx.x == 0 && threadIdx.x == 0) clocks[0] = t1 - t0;
 }
 
+// variant 7: packed HALF FMAs (fma.rn.f16x2: two half FMAs per 32-bit register and instruction), 16 independent
+// chains, two operands shared by all instructions — does the CUDA-core half path run at twice the FP32 rate on this
+// chip? (The data point a half-precision pre-screen would stand on; the trace kernel does not use it.)
+__global__ void __launch_bounds__(512) hfma2_peak(float* sink, float a, float b, long long* clocks)
+{
+    unsigned acc[kPeakChains], av, bv;
+    asm("{ .reg .f16 h; cvt.rn.f16.f32 h, %1; mov.b32 %0, {h, h}; }" : "=r"(av) : "f"(a));
+    asm("{ .reg .f16 h; cvt.rn.f16.f32 h, %1; mov.b32 %0, {h, h}; }" : "=r"(bv) : "f"(b));
+#pragma unroll
+    for (int k = 0; k < kPeakChains; k++)
+        asm("{ .reg .f16 h; cvt.rn.f16.f32 h, %1; mov.b32 %0, {h, h}; }" : "=r"(acc[k]) : "f"(threadIdx.x * 1e-3f + k));
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kPeakIters; it++) {
+#pragma unroll
+        for (int k = 0; k < kPeakChains; k++) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(acc[k]) : "r"(av), "r"(bv));
+    }
+    const long long t1 = clock64();
+    unsigned s = 0u;
+#pragma unroll
+    for (int k = 0; k < kPeakChains; k++) s ^= acc[k];
+    if (s == 0x12345678u) sink[0] = 1.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) clocks[0] = t1 - t0;
+}
+
 cudaError_t run_ffma_peak(int variant, int n_sms, cudaStream_t stream, double* tflops, double* mhz)
 {
     float* sink = nullptr;
@@ -327,6 +352,8 @@ cudaError_t run_ffma_peak(int variant, int n_sms, cudaStream_t stream, double* t
             ffma_peak_mixed<4><<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
         else if (variant == 6)
             ffma_peak_mixed<8><<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
+        else if (variant == 7)
+            hfma2_peak<<<blocks, threads, 0, stream>>>(sink, 0.999f, 1e-3f, clocks);
         else
             ffma_peak_scalar<<<blocks, threads, 0, stream>>>(sink, 1.0000001f, 1e-7f, clocks);
         cudaEventRecord(e1, stream);
@@ -338,7 +365,7 @@ cudaError_t run_ffma_peak(int variant, int n_sms, cudaStream_t stream, double* t
     }
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err == cudaSuccess) {
-        const double per_iter = variant == 5 ? 2.0 * (16 + 4) : variant == 6 ? 2.0 * (16 + 8) : 2.0 * kPeakChains;
+        const double per_iter = variant == 5 ? 2.0 * (16 + 4) : variant == 6 ? 2.0 * (16 + 8) : variant == 7 ? 4.0 * kPeakChains : 2.0 * kPeakChains;
         const double flops = per_iter * kPeakIters * static_cast<double>(blocks) * threads;
         if (tflops) *tflops = flops / (best_ms * 1e-3) / 1e12;
         long long h_clocks = 0;

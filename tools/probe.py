@@ -15,7 +15,7 @@ S = pkg.scene
 def main():
     out = {}
     r = R.Renderer(0)
-    for v, name in ((0, "ffma_scalar"), (1, "ffma_packed_f32x2"), (2, "ffma2_3distinct"), (3, "ffma2_shared_b"), (4, "ffma2_2distinct"), (5, "mixed_8ffma2_4ffma"), (6, "mixed_8ffma2_8ffma")):
+    for v, name in ((0, "ffma_scalar"), (1, "ffma_packed_f32x2"), (2, "ffma2_3distinct"), (3, "ffma2_shared_b"), (4, "ffma2_2distinct"), (5, "mixed_8ffma2_4ffma"), (6, "mixed_8ffma2_8ffma"), (7, "hfma2_f16x2")):
         t, mhz = r.ffma_peak(v)
         out[name] = {"tflops": t, "sm_mhz_est": mhz}
         print(name, "%.2f TFLOP/s" % t, "~%.0f MHz" % mhz, flush=True)
