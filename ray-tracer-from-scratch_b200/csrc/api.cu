@@ -12,12 +12,17 @@
 
 using namespace rtx;
 
+constexpr int kRanges = 4;                        // pixel ranges of a small-scene frame rendered into host memory
+constexpr size_t kRangedMinPixels = 1u << 17;     // below this a frame is one launch and one copy
+
 struct rtx_ctx {
     int device = 0;
     int n_sms = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
+    cudaStream_t copy_stream = nullptr;           // read-back of finished pixel ranges while the next range is traced
+    cudaEvent_t ev_range[kRanges + 1] = {};       // range k traced (0..kRanges-1); all copies done (kRanges)
     std::string error;
 
     // scene
@@ -147,9 +152,11 @@ int rtx_create(rtx_ctx** out, int device)
     ctx->n_sms = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (auto& ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& ev : ctx->ev_range) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaHostAlloc(&ctx->h_counters, 16 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
-    if (ok) {   // [0..7] read-back area, [8..15] reset template
+    ok = ok && cudaHostAlloc(&ctx->h_counters, 24 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
+    if (ok) {   // [0..7] read-back area, [8..15] reset template, [16..23] first pixel of each range
         for (int k = 0; k < 8; k++) ctx->h_counters[8 + k] = (k >= 4 && k <= 6) ? ~0ull : 0ull;
     }
     if (!ok) {
@@ -169,6 +176,9 @@ void rtx_destroy(rtx_ctx* ctx)
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_range)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->d_scene_blob) cudaFree(ctx->d_scene_blob);
     if (ctx->d_cameras) cudaFree(ctx->d_cameras);
     if (ctx->h_cameras) cudaFreeHost(ctx->h_cameras);
@@ -531,7 +541,36 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
     // counters: [0..3] = 0, [4..6] = ~0 (atomicMin slots), [7] = 0 — one copy from a pinned template
     RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_counters, ctx->h_counters + 8, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-    RTX_CUDA(ctx, launch_trace(a, ctx->n_sms, st, &launches));
+    // A small scene rendered into HOST memory is bound by the PCIe read-back, not by the kernel (1080p: 0.08 ms of
+    // tracing, 0.15 ms of copy): trace the frame as kRanges consecutive pixel ranges and copy each finished range on a
+    // second stream while the next one is traced. (Not for the big kernel: every launch of it has its own drain tail.)
+    const bool ranged = host_out && !unfused && ctx->scene.n_entries <= kSmallSceneEntries && n_px >= kRangedMinPixels;
+    if (ranged) {
+        for (int c = 0; c < kRanges; c++) {
+            const size_t p0 = (n_px * c / kRanges) & ~static_cast<size_t>(3), p1 = c + 1 == kRanges ? n_px : (n_px * (c + 1) / kRanges) & ~static_cast<size_t>(3);
+            a.pixel_begin = p0;
+            a.pixel_end = p1;
+            if (c > 0) {   // the pixel pool of this launch starts at p0 (range 0 starts at the template's 0)
+                ctx->h_counters[16 + c] = p0;
+                RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_counters, ctx->h_counters + 16 + c, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+            }
+            RTX_CUDA(ctx, launch_trace(a, ctx->n_sms, st, &launches));
+            RTX_CUDA(ctx, cudaEventRecord(ctx->ev_range[c], st));
+        }
+        // all launches are queued before the first copy: a copy into PAGEABLE host memory blocks this thread, and the
+        // kernels behind it should already be running then
+        for (int c = 0; c < kRanges; c++) {
+            const size_t p0 = (n_px * c / kRanges) & ~static_cast<size_t>(3), p1 = c + 1 == kRanges ? n_px : (n_px * (c + 1) / kRanges) & ~static_cast<size_t>(3);
+            RTX_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_range[c], 0));
+            for (int k = 0; k < 6; k++)
+                if (user[k])
+                    RTX_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(user[k]) + p0 * elem[k], static_cast<char*>(dev[k]) + p0 * elem[k],
+                                                  (p1 - p0) * elem[k], cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        RTX_CUDA(ctx, cudaEventRecord(ctx->ev_range[kRanges], ctx->copy_stream));
+    } else {
+        RTX_CUDA(ctx, launch_trace(a, ctx->n_sms, st, &launches));
+    }
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     if (unfused) {
         RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 2, 0, 2 * sizeof(unsigned long long), st));
@@ -552,7 +591,9 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
         }
     }
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-    if (host_out) {
+    if (ranged) {
+        RTX_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_range[kRanges], 0));     // the last range's copies
+    } else if (host_out) {
         for (int k = 0; k < 6; k++)
             if (user[k]) RTX_CUDA(ctx, cudaMemcpyAsync(user[k], dev[k], n_px * elem[k], cudaMemcpyDeviceToHost, st));
     }

@@ -110,6 +110,10 @@ struct TraceArgs {
     uint8_t* ray_count;
     uint32_t* frame_rgba8;             // whole row-major frame set, possibly peer memory (fused gather); may be null
     int32_t frame_offset, frame_stride;
+    // Pixel range of this launch in the packed pixel space [n_frames][local_rows][width]; pixel_end = 0 means all.
+    // rtx_render launches a small scene as a few consecutive ranges so that the read-back of one range overlaps the
+    // tracing of the next (counters[0] is preset to pixel_begin by the host).
+    unsigned long long pixel_begin, pixel_end;
     // counters: [0] next pixel, [1] total rays, [2] over-range pixels, [3] max luminance (double bits),
     // [4] kernel start, [5] pixel pool empty, [6] first warp exit, [7] last warp exit (globaltimer ns; [4..6] start at ~0)
     unsigned long long* counters;
@@ -163,6 +167,8 @@ __device__ __forceinline__ bool over_range(double r, double g, double b)
     const double R = ex::mul(r, 255.0), G = ex::mul(g, 255.0), B = ex::mul(b, 255.0);
     return !(R >= 0.0 && R < 256.0 && G >= 0.0 && G < 256.0 && B >= 0.0 && B < 256.0);
 }
+
+constexpr int kSmallSceneEntries = 16;   // scenes of at most this many screen entries run trace_small_kernel
 
 // Launch wrappers implemented in the .cu files, called by api.cu.
 cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, int* launches);

@@ -566,7 +566,7 @@ __device__ __noinline__ void start_pixel(Chain& c, unsigned long long p, const T
 // This kernel is the same algorithm without the machinery: one chain per lane held in registers, every object tested
 // with the exact double routines, persistent lanes refilled from the same pixel counter. Results are identical by
 // construction (same sphere_exact / wall_exact / better / shade_body).
-constexpr int kSmallScene = 16;       // screen entries (spheres + walls + box faces)
+constexpr int kSmallScene = kSmallSceneEntries;   // screen entries (spheres + walls + box faces)
 constexpr int kSmallThreads = 256;
 
 #ifndef RTX_SMALL_MINBLOCKS
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(kSmallThreads, RTX_SMALL_MINBLOCKS) trace_smal
     sc.kind = s_kind;
     sc.slot = s_slot;
     const unsigned lane_id = threadIdx.x & 31u;
-    const unsigned long long total_pixels =
+    const unsigned long long total_pixels = a.pixel_end ? a.pixel_end :
         static_cast<unsigned long long>(a.n_frames) * static_cast<unsigned long long>(a.local_rows) * a.width;
     Chain c;
     c.active = 0;
@@ -805,10 +805,11 @@ cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, 
     const size_t tile_bytes = stream_tiles ? (static_cast<size_t>(kMaxSmemBytes) - mbox_bytes) / iter_bytes * iter_bytes : (need ? need : iter_bytes);
     const int tile_pairs = static_cast<int>(tile_bytes / 32);
     const size_t smem = tile_bytes + mbox_bytes;
-    const unsigned long long total =
+    unsigned long long total =
         static_cast<unsigned long long>(args.n_frames) * static_cast<unsigned long long>(args.local_rows) * args.width;
     if (total == 0) return cudaSuccess;
     if (args.scene.n_entries <= kSmallScene) {
+        if (args.pixel_end) total = args.pixel_end - args.pixel_begin;      // a range of the frame (see TraceArgs)
         static int per_sm = 0;
         if (per_sm == 0) {
             cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_small_kernel, kSmallThreads, 0);

@@ -490,6 +490,31 @@ def test_small_scene_kernel_boundary(gpu, renderer_mod, port, S):
         assert exp["hit_mask"].any(), (n_s, n_w)
 
 
+def test_small_scene_host_frames_are_traced_in_ranges(gpu, renderer_mod, port, S):
+    """A small scene rendered into HOST memory is traced as four consecutive pixel ranges whose read-back overlaps the next
+    range's kernel (rtx_render, `ranged`): same pixels as one launch. Cases: one frame, a pixel count that is not a
+    multiple of four, a batch of frames (ranges cut across frame boundaries), and the device-memory path (one launch)."""
+    scene = S.default_scene()
+    gpu.set_scene(scene)
+    for width, aspect, depth in ((640, 4.0 / 3.0, 6), (643, 2.0, 3)):
+        pod = S.default_camera(width, aspect).pod()
+        assert pod.width * pod.height >= 1 << 17
+        planes, st = gpu.render([pod], renderer_mod.default_params(max_depth=depth), want=WANT)
+        check_frame({k: v[0] for k, v in planes.items()}, port.render(scene, pod, depth), st)
+        assert st.launches == 4
+    pods = [c.pod() for c in S.flythrough_cameras(3, 321, 4.0 / 3.0)]
+    planes, st = gpu.render(pods, renderer_mod.default_params(max_depth=5), want=WANT)
+    assert st.launches == 4
+    total = 0
+    for f, pod in enumerate(pods):
+        exp = port.render(scene, pod, 5)
+        check_frame({k: v[f] for k, v in planes.items()}, exp)
+        total += exp["total_rays"]
+    assert st.total_rays == total
+    small, st1 = gpu.render([S.default_camera(160, 1.0).pod()], renderer_mod.default_params(max_depth=5), want=("rgba8",))
+    assert st1.launches == 1                                    # below the threshold: one launch, one copy
+
+
 def test_grazing_spheres_never_lose_a_hit(gpu, renderer_mod, port, S):
     """Adversarial input for the conservative FP32 screen: spheres TANGENT to camera rays (distance from the centre
     to the ray = r * (1 + delta), |delta| from 1e-9 to 1e-5, both signs), far from the origin, so that hit / miss is
