@@ -29,6 +29,7 @@ struct rtx_ctx {
     bool have_scene = false;
     SceneDev scene = {};
     void* d_scene_blob = nullptr;
+    size_t scene_blob_cap = 0;
     double scene_bound = 0.0;          // max over objects of |coordinate| + extent
 
     // per-call scratch (grown on demand, reused across calls)
@@ -316,12 +317,16 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
     if (n) std::memcpy(&blob[o_knd], kind.data(), sizeof(int32_t) * n);
     if (n) std::memcpy(&blob[o_slt], slot.data(), sizeof(int32_t) * n);
 
-    RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->d_scene_blob) cudaFree(ctx->d_scene_blob);
-    ctx->d_scene_blob = nullptr;
+    RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // no kernel of an earlier call still reads the old scene
     ctx->have_scene = false;
-    cudaError_t e = cudaMalloc(&ctx->d_scene_blob, off);
-    if (e != cudaSuccess) return fail(ctx, RTX_ERR_NOMEM, std::string("cudaMalloc(scene): ") + cudaGetErrorString(e));
+    if (off > ctx->scene_blob_cap) {                         // the allocation is kept and reused while the new scene fits
+        if (ctx->d_scene_blob) cudaFree(ctx->d_scene_blob);
+        ctx->d_scene_blob = nullptr;
+        ctx->scene_blob_cap = 0;
+        cudaError_t e = cudaMalloc(&ctx->d_scene_blob, off);
+        if (e != cudaSuccess) return fail(ctx, RTX_ERR_NOMEM, std::string("cudaMalloc(scene): ") + cudaGetErrorString(e));
+        ctx->scene_blob_cap = off;
+    }
     RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_scene_blob, blob.data(), off, cudaMemcpyHostToDevice, ctx->stream));
     RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     unsigned char* base = static_cast<unsigned char*>(ctx->d_scene_blob);
