@@ -55,6 +55,10 @@ def parse_args():
                     help="N > 1: peer-memory stores from the trace kernel (fused) or all-gather + unpermute")
     ap.add_argument("--verify", action="store_true",
                     help="N > 1: rank 0 re-renders the frame(s) alone and compares them bit for bit with the gathered result")
+    ap.add_argument("--e2e-mode", default="auto", choices=["auto", "store", "copy"],
+                    help="how pixels reach host memory in the e2e leg: store = the trace kernel writes the pinned mapped host frame itself "
+                         "(zero copy), copy = device staging + copy-engine transfers; auto = store for the 10k-object scene, copy for the small one")
+    ap.add_argument("--chunks", type=int, default=4, help="c5: chunks per rank of the render/copy pipeline")
     ap.add_argument("--scale", type=float, default=1.0, help="developer knob: shrink the frame (not a valid bench)")
     return ap.parse_args()
 
@@ -181,23 +185,41 @@ def reference_oracle():
     return ob.load_port(), "port"
 
 
+def host_threads():
+    """Hardware threads this process may run on. Passed to the harness EXPLICITLY (num_threads clause):
+    torch.distributed.run exports OMP_NUM_THREADS=1 to every rank, which must not throttle the CPU arm."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+CPU_CHUNK = 64          # pixels per OpenMP work item of the harness (oracle/ref_harness.cpp kChunk)
+
+
 class CpuSample:
     """A bounded sample of the workload for the CPU arm: a cyclic subset of 4-row bands of one or two frames,
-    sized from a short calibration so that one pass costs about `seconds` of wall time on all host threads."""
+    sized from a short calibration so that one pass costs about `seconds` of wall time on all host threads.
+    The harness hands out (row, 64-pixel chunk) work items dynamically; the sample always holds at least
+    4 items per thread, so every core is busy whatever the core count."""
 
     def __init__(self, oracle, objs, pods, depth, seconds):
         import numpy as np
         self.oracle, self.objs, self.depth = oracle, objs, depth
-        self.threads = oracle.max_threads()
+        self.threads = host_threads()
         self.pods = pods[:: max(1, len(pods) // 2)][:2]
         H, self.W = self.pods[0].height, self.pods[0].width
-        probe = np.array(sample_rows(H, max(1, H // 4 // 2)), dtype=np.int32)[:8]
+        chunks_per_row = (self.W + CPU_CHUNK - 1) // CPU_CHUNK
+        min_rows = -(-4 * self.threads // (chunks_per_row * len(self.pods)))          # >= 4 work items per thread
+        min_rows = min(H, (min_rows + 3) // 4 * 4)
+        probe = np.array(sample_rows(H, max(1, H // 4 // 2)), dtype=np.int32)[:max(8, min_rows)]
         t = sum(self._render(p, probe, ("radiance",))["seconds"] for p in self.pods)
         sec_per_row = max(t / (len(probe) * len(self.pods)), 1e-9)
-        rows_budget = max(4, min(H, int(seconds / (sec_per_row * len(self.pods))) // 4 * 4))
+        rows_budget = max(4, min_rows, min(H, int(seconds / (sec_per_row * len(self.pods))) // 4 * 4))
         self.every = max(1, (H // 4) // max(1, rows_budget // 4))
         self.rows = np.array(sample_rows(H, self.every), dtype=np.int32)
         self.height = H
+        self.items = len(self.rows) * chunks_per_row * len(self.pods)
         # exact ray count of the sample: an untimed chain walk over the same rows
         self.rays = sum(self._render(p, self.rows, ("ray_count",))["total_rays"] for p in self.pods)
 
@@ -205,16 +227,25 @@ class CpuSample:
         return self.oracle.render(self.objs, pod, self.depth, rows=rows, threads=self.threads, want=want)
 
     def time_once(self):
-        """recursive_ray_tracing over the sample rows, timed inside the harness around the row loop only
+        """recursive_ray_tracing over the sample rows, timed inside the harness around the pixel loop only
         (std::chrono, as main.cpp:326-330)."""
         return sum(self._render(p, self.rows, ("radiance",))["seconds"] for p in self.pods)
 
     def describe(self):
-        return "every %d-th 4-row band of %d frame(s): %d rows x %d px = %d rays" % (
-            self.every, len(self.pods), len(self.rows), self.W, self.rays)
+        return "every %d-th 4-row band of %d frame(s): %d rows x %d px = %d rays, %d work items of %d px over %d threads" % (
+            self.every, len(self.pods), len(self.rows), self.W, self.rays, self.items, CPU_CHUNK, self.threads)
 
 
-def run_reference_arm(args, spec, S):
+def structural_config(spec, S, pods, scene, world, band_rows):
+    """The keys of `config` that name the workload — identical in both arms (ours and --impl reference)."""
+    abi = importlib.import_module("ray-tracer-from-scratch_b200").abi
+    n_spheres = sum(1 for g in scene if g.kind == abi.RTX_SPHERE)
+    return {"workload": spec["label"], "width": pods[0].width, "height": pods[0].height, "frames_per_step": len(pods),
+            "depth": spec["depth"], "n_spheres": n_spheres, "n_walls": len(scene) - n_spheres,
+            "band_rows": band_rows if world > 1 and spec["name"] != "c5" else None}
+
+
+def run_reference_arm(args, spec, S, world):
     """`--impl reference`: the reference's own CPU implementation, all host threads, one bounded sample per step."""
     oracle, kind = reference_oracle()
     scene = build_scene(S, spec["scene"])
@@ -230,12 +261,14 @@ def run_reference_arm(args, spec, S):
     ms = total / args.steps * 1e3
     value = cs.rays / (ms * 1e-3) / 1e6
     sample = cs.describe() + " per step"
+    config = structural_config(spec, S, pods, scene, world, args.band_rows)
+    config.update({"parallelism": "OpenMP, %d host threads, (row, 64-pixel chunk) work items, rank 0 only" % cs.threads,
+                   "sample": sample, "ms_per_frame_extrapolated": ms / (len(cs.rows) * len(cs.pods)) * cs.height})
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "n/a (CPU, rank 0 only)", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": spec["label"], "sample": sample,
-                   "ms_per_frame_extrapolated": ms / (len(cs.rows) * len(cs.pods)) * cs.height},
+        "config": config,
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cs.threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -254,7 +287,205 @@ def cpu_baseline(args, spec, S, scene, pods):
             "ms_per_frame_extrapolated": secs / (len(cs.rows) * len(cs.pods)) * cs.height * 1e3}
 
 
+# ---- parity of what was just timed ---------------------------------------------------------------------------
+def parity_check(spec, planes):
+    """Per-row CRC32 of the RGBA8 words of the frame(s) the timed region produced against tests/golden/fullsize_*.json —
+    statistics the UNMODIFIED reference produced on the CPU (tests/golden/make_fullsize.py): every row of c2 / c3, every
+    16th 4-row band of c4 (272 rows), frames 48 / 128 / 224 of c5. `planes`: {label: array [frames][H][W]} (device and
+    host results). Returns the `parity` block of the JSON line."""
+    import zlib
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "fullsize_%s.json" % spec["name"])
+    if not os.path.exists(path):
+        return {"rows_checked": 0, "rows_bad": None, "source": None, "note": "no golden file for this workload"}
+    g = json.load(open(path))
+    groups = [(int(k), v) for k, v in g["frames"].items()] if "frames" in g else [(0, g)]
+    checked = bad = 0
+    bad_list = []
+    for label, arr in planes.items():
+        a = np.asarray(arr)
+        if a.ndim == 2:
+            a = a[None]
+        if a.shape[1:] != (g["height"], g["width"]):
+            return {"rows_checked": 0, "rows_bad": None, "source": os.path.basename(path), "note": "frame size differs from the golden file (scaled run)"}
+        for frame, gf in groups:
+            rows = np.asarray(gf["rows"])
+            sub = np.ascontiguousarray(a[frame][rows]).view(np.uint32)
+            for r, row, want in zip(rows, sub, gf["rgba8_crc"]):
+                checked += 1
+                if zlib.crc32(row.tobytes()) != want:
+                    bad += 1
+                    if len(bad_list) < 8:
+                        bad_list.append([label, frame, int(r)])
+    out = {"rows_checked": checked, "rows_bad": bad, "source": os.path.basename(path) + " (unmodified reference, tests/golden/make_fullsize.py)",
+           "checked": sorted(planes)}
+    if bad_list:
+        out["first_bad"] = bad_list
+    return out
+
+
 # ---- our arm -----------------------------------------------------------------------------------------------------
+class Arm:
+    """One process (= one GPU) of our arm: the renderer, the sharding layer and the timing loop for any workload."""
+
+    def __init__(self, args, rank, local_rank, world):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.args, self.rank, self.local_rank, self.world = args, rank, local_rank, world
+        self.pkg = importlib.import_module("ray-tracer-from-scratch_b200")
+        self.S, self.abi = self.pkg.scene, self.pkg.abi
+        self.R = importlib.import_module("ray-tracer-from-scratch_b200.renderer")
+        self.SH = importlib.import_module("ray-tracer-from-scratch_b200.sharding")
+        self.dev = torch.device("cuda", local_rank)
+        self.r = self.R.Renderer(local_rank)
+        self.sh = self.SH.ShardedRenderer(self.r, rank, world, band_rows=args.band_rows, fused=args.gather == "fused", n_chunks=args.chunks)
+        self.flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=self.dev)
+        self.host_single = None       # N = 1: pinned + mapped host frame (ptr, numpy view, key)
+
+    def close(self):
+        if self.host_single is not None:
+            self.r.host_free(self.host_single[0])
+            self.host_single = None
+        self.sh.close()
+        self.r.close()
+
+    def _single_host(self, n_frames, H, W):
+        import ctypes
+        import numpy as np
+        key = (n_frames, H, W)
+        if self.host_single is None or self.host_single[2] != key:
+            if self.host_single is not None:
+                self.r.host_free(self.host_single[0])
+            ptr = self.r.host_alloc(n_frames * H * W * 4)
+            view = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint32)), shape=key)
+            self.host_single = (ptr, view, key)
+        return self.host_single[0], self.host_single[1]
+
+    def measure(self, spec, steps, warmup, e2e_steps, sampler=None):
+        """Times `steps` device-resident steps and `e2e_steps` end-to-end steps of one workload; returns a dict on rank 0
+        (None elsewhere). Every rank must call this with the same arguments."""
+        import ctypes
+        torch, dist, abi, S, R, r, sh, args = self.torch, self.dist, self.abi, self.S, self.R, self.r, self.sh, self.args
+        world, rank, dev = self.world, self.rank, self.dev
+        scene = build_scene(S, spec["scene"])
+        objs = S.flatten(scene)
+        if spec["name"] == "c5":
+            pods = [c.pod() for c in S.flythrough_cameras(spec["frames"], spec["width"], 16.0 / 9.0)]
+        else:
+            pods = [S.default_camera(spec["width"], 16.0 / 9.0).pod()]
+        H, W, F = pods[0].height, pods[0].width, len(pods)
+        r.set_scene(objs)
+        single = world == 1 and spec["name"] != "c5"
+        e2e_store = args.e2e_mode == "store" or (args.e2e_mode == "auto" and spec["scene"] == "synthetic")
+        params = R.default_params(max_depth=spec["depth"])
+        outs = {}
+        if single:
+            dev_frame = torch.empty((F, H, W), dtype=torch.int32, device=dev)
+            hptr, hview = self._single_host(F, H, W)
+            o_dev, o_host = abi.Outputs(), abi.Outputs()
+            o_dev.memory, o_dev.rgba8 = abi.RTX_MEM_DEVICE, dev_frame.data_ptr()
+            o_host.memory, o_host.rgba8 = (abi.RTX_MEM_HOST_MAPPED if e2e_store else abi.RTX_MEM_HOST), hptr
+            outs = {False: o_dev, True: o_host}
+        result = {}
+        drain = []
+        frame_mode = abi.RTX_FRAME_STORE if e2e_store else abi.RTX_FRAME_COPY
+
+        def step(e2e):
+            """One step. Returns (rays on this rank, kernel ms, launches)."""
+            if e2e:
+                r.set_scene(objs)                                  # host -> device: the scene (main.cpp:156-163 equivalent)
+            if spec["name"] == "c5":
+                frames, st, launches = sh.render_frames(pods, max_depth=spec["depth"], to_host=e2e)
+                result["host" if e2e else "device"] = frames
+            elif world > 1:
+                frame, st, launches = sh.render_frame(pods[0], max_depth=spec["depth"], to_host=e2e,
+                                                      frame_mode=frame_mode if e2e else abi.RTX_FRAME_STORE)
+                result["host" if e2e else "device"] = frame
+            else:
+                st = r.render_raw(pods, params, outs[e2e])
+                launches = st.launches
+                result["host" if e2e else "device"] = hview if e2e else dev_frame
+            if st:
+                drain.append(st.drain_ms)
+            return (st.total_rays if st else 0), (st.raytracing_ms if st else 0.0), launches
+
+        def timed_region(e2e, n_steps, n_warm, smp=None):
+            for _ in range(n_warm):
+                step(e2e)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            if smp:
+                smp.start()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+            rays = kernel_ms = launches = 0
+            for k in range(n_steps):
+                self.flush.add_(1)                                 # L2 flush, outside the step's events
+                ev[k][0].record()
+                a, b, c = step(e2e)
+                ev[k][1].record()
+                rays += a
+                kernel_ms += b
+                launches += c
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            clocks = smp.stop() if smp else None
+            ms = sum(s.elapsed_time(e) for s, e in ev)
+            t = torch.tensor([ms, float(rays), kernel_ms, float(launches)], dtype=torch.float64, device=dev)
+            per_rank_kernel = [kernel_ms / n_steps]
+            if world > 1:
+                tmax = t.clone()
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                allk = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+                dist.all_gather(allk, t[2:3].clone())
+                per_rank_kernel = [x.item() / n_steps for x in allk]
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                ms, kernel_max = tmax[0].item(), tmax[2].item()
+                rays, launches = t[1].item(), t[3].item()
+            else:
+                kernel_max = kernel_ms
+            return ms, rays, kernel_max, int(launches), clocks, per_rank_kernel
+
+        ms, rays, kernel_ms, launches, clocks, per_rank_kernel = timed_region(False, steps, warmup, sampler)
+        ms_e, rays_e, _, launches_e, _, _ = timed_region(True, e2e_steps, max(1, min(warmup, 2)))
+        verified = None
+        if args.verify and world > 1:
+            torch.cuda.synchronize()
+            if rank == 0:
+                got = result["device"].clone().reshape(F, H, W)
+                ok = True
+                for f0 in range(0, F, 16):
+                    part = pods[f0:f0 + 16]
+                    alone = torch.empty((len(part), H, W), dtype=torch.int32, device=dev)
+                    o = abi.Outputs()
+                    o.memory, o.rgba8 = abi.RTX_MEM_DEVICE, alone.data_ptr()
+                    r.render_raw(part, R.default_params(max_depth=spec["depth"]), o)
+                    ok = ok and bool(torch.equal(alone, got[f0:f0 + len(part)]))
+                verified = ok
+            dist.barrier()
+        if rank != 0:
+            return None
+        import numpy as np
+        torch.cuda.synchronize()
+        planes = {"device frame (value)": result["device"].reshape(F, H, W).cpu().numpy().view(np.uint32),
+                  "host frame (e2e)": np.asarray(result["host"]).reshape(F, H, W).view(np.uint32)}
+        parity = parity_check(spec, planes)
+        if planes["device frame (value)"].shape == planes["host frame (e2e)"].shape:
+            parity["device_equals_host_frame"] = bool(np.array_equal(planes["device frame (value)"], planes["host frame (e2e)"]))
+        n_spheres = sum(1 for g in scene if g.kind == abi.RTX_SPHERE)
+        return dict(spec=spec, scene=scene, pods=pods, H=H, W=W, F=F, n_spheres=n_spheres, n_walls=len(scene) - n_spheres,
+                    ms=ms, rays=rays, kernel_ms=kernel_ms, launches=launches, clocks=clocks, per_rank_kernel=per_rank_kernel,
+                    ms_e=ms_e, rays_e=rays_e, launches_e=launches_e, steps=steps, e2e_steps=e2e_steps, drain=drain, parity=parity,
+                    verified=verified, scene_bytes=len(scene) * ctypes.sizeof(abi.ObjectPOD), frame_bytes=H * W * 4 * F,
+                    camera_bytes=ctypes.sizeof(abi.CameraPOD) * F,
+                    e2e_path=("the trace kernel stores pixels straight into the pinned, mapped host frame (zero copy, RTX_FRAME_STORE / RTX_MEM_HOST_MAPPED)"
+                              if e2e_store and spec["name"] != "c5" else
+                              "device staging + copy-engine read-back on the copy stream, overlapped with tracing (RTX_FRAME_COPY / RTX_MEM_HOST)") +
+                             ("; every rank writes its own rows of ONE shared pinned host frame over its own PCIe link" if world > 1 else ""))
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -266,14 +497,12 @@ def main():
 
     if args.impl == "reference":
         if rank == 0:
-            run_reference_arm(args, spec, S)
+            run_reference_arm(args, spec, S, max(args.gpus, world))
         return
 
-    import numpy as np
     import torch
     import torch.distributed as dist
     R = importlib.import_module("ray-tracer-from-scratch_b200.renderer")
-    SH = importlib.import_module("ray-tracer-from-scratch_b200.sharding")
     abi = pkg.abi
 
     if not torch.cuda.is_available():
@@ -282,121 +511,33 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-
-    scene = build_scene(S, spec["scene"])
-    objs = S.flatten(scene)
-    n_spheres = sum(1 for g in scene if g.kind == abi.RTX_SPHERE)
-    n_walls = len(scene) - n_spheres
-    if spec["name"] == "c5":
-        pods = [c.pod() for c in S.flythrough_cameras(spec["frames"], spec["width"], 16.0 / 9.0)]
-    else:
-        pods = [S.default_camera(spec["width"], 16.0 / 9.0).pod()]
-    H, W = pods[0].height, pods[0].width
-
-    r = R.Renderer(local_rank)
-    r.set_stream(torch.cuda.current_stream().cuda_stream)     # torch events then bracket our kernels
-    r.set_scene(objs)
-    sh = SH.ShardedRenderer(r, rank, world, band_rows=args.band_rows, fused=args.gather == "fused")
-    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=dev)
-
-    import ctypes
-    scene_bytes = len(scene) * ctypes.sizeof(abi.ObjectPOD)
-    frame_bytes = H * W * 4 * len(pods)
-    host_frame = torch.empty((len(pods), H, W), dtype=torch.int32, pin_memory=True) if rank == 0 else None
-
-    drain = []
-
-    def step(e2e):
-        """One step. Returns (rays on this rank, kernel ms, launches)."""
-        if e2e:
-            r.set_scene(objs)                                  # host -> device: the scene (main.cpp:156-163 equivalent)
-        if spec["name"] == "c5":
-            frames, st, launches = sh.render_frames(pods, max_depth=spec["depth"])
-            if e2e and rank == 0:
-                host_frame.copy_(frames, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-        elif world > 1:
-            frame, st, launches = sh.render_frame(pods[0], max_depth=spec["depth"])
-            if e2e and rank == 0:
-                host_frame[0].copy_(frame, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-        else:
-            st = r.render_raw(pods, single_params, single_out[1 if e2e else 0])
-            launches = st.launches
-        if st:
-            drain.append(st.drain_ms)
-        return (st.total_rays if st else 0), (st.raytracing_ms if st else 0.0), launches
-
-    dev_frame = torch.empty((len(pods), H, W), dtype=torch.int32, device=dev) if world == 1 and spec["name"] != "c5" else None
-
-    # single-GPU call arguments are built once, outside the timed region (as a caller rendering frame after frame would)
-    single_params = R.default_params(max_depth=spec["depth"])
-    single_out = [abi.Outputs(), abi.Outputs()]
-    if dev_frame is not None:
-        single_out[0].memory, single_out[0].rgba8 = abi.RTX_MEM_DEVICE, dev_frame.data_ptr()
-        single_out[1].memory, single_out[1].rgba8 = abi.RTX_MEM_HOST, host_frame.data_ptr()
-
-    def timed_region(e2e, steps, warmup, sampler=None):
-        for _ in range(warmup):
-            step(e2e)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        if sampler:
-            sampler.start()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        rays = kernel_ms = launches = 0
-        for k in range(steps):
-            flush.add_(1)                                      # L2 flush, outside the step's events
-            ev[k][0].record()
-            a, b, c = step(e2e)
-            ev[k][1].record()
-            rays += a
-            kernel_ms += b
-            launches += c
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        clocks = sampler.stop() if sampler else None
-        ms = sum(s.elapsed_time(e) for s, e in ev)
-        t = torch.tensor([ms, float(rays), kernel_ms, float(launches)], dtype=torch.float64, device=dev)
-        if world > 1:
-            tmax = t.clone()
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            ms, kernel_max = tmax[0].item(), tmax[2].item()
-            rays, launches = t[1].item(), t[3].item()
-        else:
-            kernel_max = kernel_ms
-        return ms, rays, kernel_max, int(launches), clocks
-
-    verified = None
-    if args.verify and world > 1:
-        # every rank takes part in the sharded render; rank 0 then renders everything alone for comparison
-        if spec["name"] == "c5":
-            got, _, _ = sh.render_frames(pods, max_depth=spec["depth"])
-        else:
-            got, _, _ = sh.render_frame(pods[0], max_depth=spec["depth"])
-        torch.cuda.synchronize()
-        if rank == 0:
-            got = got.clone().reshape(len(pods), H, W)
-            ok = True
-            for f0 in range(0, len(pods), 16):
-                part = pods[f0:f0 + 16]
-                alone = torch.empty((len(part), H, W), dtype=torch.int32, device=dev)
-                o = abi.Outputs()
-                o.memory, o.rgba8 = abi.RTX_MEM_DEVICE, alone.data_ptr()
-                r.render_raw(part, R.default_params(max_depth=spec["depth"]), o)
-                ok = ok and bool(torch.equal(alone, got[f0:f0 + len(part)]))
-            verified = ok
-        dist.barrier()
+    arm = Arm(args, rank, local_rank, world)
+    r = arm.r
+    flush = arm.flush
 
     sampler = ClockSampler(visible_index(local_rank)) if rank == 0 else None
-    ms, rays, kernel_ms, launches, clocks = timed_region(False, args.steps, args.warmup, sampler)
-    ms_e, rays_e, _, _, _ = timed_region(True, max(2, min(args.steps, 5)), 1)
     e2e_steps = max(2, min(args.steps, 5))
+    m = arm.measure(spec, args.steps, args.warmup, e2e_steps, sampler)
+    also = {}
+    if args.workload == "auto" and not args.no_also:
+        # BASELINE.json configs[4] (the 256-frame 1080p orbit, frames sharded over the ranks) in the same run, at every N
+        m5 = arm.measure(workload_spec("c5", world), 5, 3, 3)
+        if rank == 0:
+            also["c5"] = {
+                "workload": m5["spec"]["label"], "frames_per_step": m5["F"], "rays_per_step": m5["rays"] / m5["steps"],
+                "device": {"ms_per_step": m5["ms"] / m5["steps"], "frames_per_s": m5["F"] / (m5["ms"] / m5["steps"] * 1e-3),
+                           "mrays_s": m5["rays"] / (m5["ms"] * 1e-3) / 1e6, "kernel_ms_per_rank": m5["per_rank_kernel"],
+                           "bytes_into_rank0_over_nvlink": m5["frame_bytes"] * (world - 1) // world},
+                "e2e": {"ms_per_step": m5["ms_e"] / m5["e2e_steps"], "frames_per_s": m5["F"] / (m5["ms_e"] / m5["e2e_steps"] * 1e-3),
+                        "mrays_s": m5["rays_e"] / (m5["ms_e"] * 1e-3) / 1e6, "d2h_bytes_per_step": m5["frame_bytes"],
+                        "h2d_bytes_per_step": world * (m5["scene_bytes"] + m5["camera_bytes"] // world), "path": m5["e2e_path"]},
+                "parity": m5["parity"], "gpu_launches": m5["launches"]}
 
+    rc = 0
     if rank == 0:
+        H, W, pods, scene = m["H"], m["W"], m["pods"], m["scene"]
+        n_spheres, n_walls = m["n_spheres"], m["n_walls"]
+        ms, rays, kernel_ms, launches = m["ms"], m["rays"], m["kernel_ms"], m["launches"]
         value = rays / (ms * 1e-3) / 1e6
         rays_per_step = rays / args.steps
         # roofline of the trace kernel: slowest rank's kernel time, that rank's share of the algorithmic work
@@ -411,33 +552,45 @@ def main():
             t = json.load(open(tp)).get(spec["name"])
             if t:
                 traffic, traffic_note = t["dram_bytes_per_launch"], t.get("note")
+        config = structural_config(spec, S, pods, scene, world, args.band_rows)
+        config.update({
+            "parallelism": ("1 process per GPU; " + ("cyclic row bands" if spec["name"] != "c5" else "frames sharded over ranks") +
+                            (("; pixels stored into rank 0's frame over NVLink peer memory by the trace kernel + 1 barrier" if spec["name"] != "c5"
+                              else "; finished frame chunks bulk-copied into rank 0's frame set over NVLink, overlapped with rendering")
+                             if args.gather == "fused" else "; NCCL all-gather to rank 0 + unpermute")) if world > 1 else "single GPU",
+            "rays_per_step": rays_per_step, "ms_per_frame": ms / args.steps / len(pods),
+            "mpixel_per_s": H * W * len(pods) / (ms / args.steps * 1e-3) / 1e6,
+            "l2": "256 MiB written between steps (L2 flush), outside the per-step CUDA events"})
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 screen + f64 decisions/shading", "data": "synthetic",
-            "config": {"workload": spec["label"], "width": W, "height": H, "frames_per_step": len(pods), "depth": spec["depth"],
-                       "n_spheres": n_spheres, "n_walls": n_walls, "band_rows": args.band_rows if world > 1 else None,
-                       "parallelism": ("1 process per GPU; " + ("cyclic row bands" if spec["name"] != "c5" else "frames sharded over ranks") +
-                                       (("; pixels stored into rank 0's frame over NVLink peer memory by the trace kernel + 1 barrier" if spec["name"] != "c5"
-                                         else "; finished frame chunks bulk-copied into rank 0's frame set over NVLink, overlapped with rendering")
-                                        if args.gather == "fused" else "; NCCL all-gather to rank 0 + unpermute")) if world > 1 else "single GPU",
-                       "rays_per_step": rays_per_step, "ms_per_frame": ms / args.steps / len(pods),
-                       "mpixel_per_s": H * W * len(pods) / (ms / args.steps * 1e-3) / 1e6,
-                       "l2": "256 MiB written between steps (L2 flush), outside the per-step CUDA events"},
+            "config": config,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_note": traffic_note, "kernel": "rtx::trace_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
+                         "kernel_ms_per_rank": m["per_rank_kernel"],
                          "algorithmic_flop_per_step": flops_per_step, "peak_source": peak_src,
-                         "drain_ms_per_step_rank0": sum(drain) / max(1, len(drain)),
+                         "executed_flop_per_test": 14, "frac_executed": achieved / peak * 14.0 / 20.0 if n_walls * 33 < n_spheres else None,
+                         "drain_ms_per_step_rank0": sum(m["drain"]) / max(1, len(m["drain"])),
                          "peak_measured_ffma2_tflops": ffma2, "peak_measured_ffma_scalar_tflops": ffma1,
                          "frac_of_measured_ffma2": achieved / ffma2 if ffma2 else None,
-                         "hbm_write_gbs": frame_bytes / world / (kernel_ms / args.steps * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak_gbs()[0]},
-            "e2e": {"value": rays_e / (ms_e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
-                    "h2d_bytes_per_step": scene_bytes + ctypes.sizeof(abi.CameraPOD) * len(pods), "d2h_bytes_per_step": frame_bytes},
+                         "hbm_write_gbs": m["frame_bytes"] / world / (kernel_ms / args.steps * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak_gbs()[0]},
+            "e2e": {"value": m["rays_e"] / (m["ms_e"] * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": m["ms_e"] / e2e_steps, "steps": e2e_steps,
+                    "h2d_bytes_per_step": world * m["scene_bytes"] + m["camera_bytes"] * (world if spec["name"] != "c5" else 1),
+                    "d2h_bytes_per_step": m["frame_bytes"], "path": m["e2e_path"]},
+            "parity": m["parity"],
             "gpu_launches": launches,
-            "clocks": clocks,
+            "clocks": m["clocks"],
         }
-        if verified is not None:
-            line["verified_against_single_gpu"] = verified
+        if m["verified"] is not None:
+            line["verified_against_single_gpu"] = m["verified"]
+        if also:
+            line["also"] = also
+        bad = [p for p in ([m["parity"]] + [v["parity"] for v in also.values() if "parity" in v]) if p.get("rows_bad")]
+        if bad:
+            rc = 1
+        objs = S.flatten(scene)
+        r.set_scene(objs)
         if world == 1:
             # HBM side: the standalone quantise kernel (main.cpp:338-347) on a device-resident radiance frame of the
             # same size; algorithmic bytes = 12 (f32) or 24 (f64) read + 4 written per pixel; L2 flushed before each launch.
@@ -487,6 +640,7 @@ def main():
             o_dev.memory, o_dev.rgba8 = abi.RTX_MEM_DEVICE, dev2.data_ptr()
             o_host.memory, o_host.rgba8 = abi.RTX_MEM_HOST, host2.data_ptr()
             res = {}
+            objs2 = S.flatten(scene2)
             for key, out_desc in (("device", o_dev), ("e2e", o_host)):
                 for _ in range(3):
                     st2 = r.render_raw([pod2], p2, out_desc)
@@ -496,14 +650,39 @@ def main():
                     flush.add_(1)
                     e0.record()
                     if key == "e2e":
-                        r.set_scene(S.flatten(scene2))
+                        r.set_scene(objs2)
                     st2 = r.render_raw([pod2], p2, out_desc)
                     e1.record()
                     e1.synchronize()
                     tot_ms += e0.elapsed_time(e1)
                     kern += st2.raytracing_ms
                 res[key] = {"ms_per_frame": tot_ms / 20, "mrays_s": st2.total_rays / (tot_ms / 20 * 1e-3) / 1e6, "kernel_ms": kern / 20}
-            line["also"] = {"c2": {"workload": spec2["label"], "rays_per_frame": st2.total_rays, **res}}
+            # the same end-to-end work as a stream of frames: rtx_render_async keeps two frames in flight, so the read-back
+            # of frame k (copy stream) overlaps the scene upload + kernel of frame k+1 (each frame has its own host buffer)
+            host2b = torch.empty((pod2.height, pod2.width), dtype=torch.int32, pin_memory=True)
+            o_hostb = abi.Outputs()
+            o_hostb.memory, o_hostb.rgba8 = abi.RTX_MEM_HOST, host2b.data_ptr()
+            n_stream = 64
+            for rep in range(2):                                  # first pass warms up
+                flush.add_(1)
+                e0.record()
+                for k in range(n_stream):
+                    r.set_scene(objs2)
+                    r.render_async([pod2], p2, o_host if k % 2 == 0 else o_hostb)
+                    if k >= 1:
+                        st2 = r.wait()
+                st2 = r.wait()
+                e1.record()
+                e1.synchronize()
+            ms_stream = e0.elapsed_time(e1) / n_stream
+            res["e2e_stream"] = {"ms_per_frame": ms_stream, "mrays_s": st2.total_rays / (ms_stream * 1e-3) / 1e6, "frames": n_stream,
+                                 "frames_in_flight": 2, "api": "rtx_render_async + rtx_wait"}
+            import numpy as np
+            par2 = parity_check(spec2, {"device frame": dev2.cpu().numpy().view(np.uint32), "host frame (e2e)": host2.numpy().view(np.uint32),
+                                        "host frame (e2e_stream)": host2b.numpy().view(np.uint32)})
+            line.setdefault("also", {})["c2"] = {"workload": spec2["label"], "rays_per_frame": st2.total_rays, **res, "parity": par2}
+            if par2.get("rows_bad"):
+                rc = 1
             if not args.no_cpu_baseline:
                 try:
                     oracle2, kind2 = reference_oracle()
@@ -530,19 +709,25 @@ def main():
                 ks.append(st3.raytracing_ms)
             k3 = sorted(ks[3:])[len(ks[3:]) // 2]
             fl3 = st3.total_rays * (n_spheres * FLOP_SPHERE + n_walls * FLOP_WALL)
+            par3 = parity_check(spec3, {"device frame": dev3.cpu().numpy().view(np.uint32)})
             line["also"]["c3"] = {"workload": spec3["label"], "rays_per_frame": st3.total_rays,
                                   "device": {"kernel_ms": k3, "mrays_s": st3.total_rays / (k3 * 1e-3) / 1e6,
-                                             "tflops_algorithmic": fl3 / (k3 * 1e-3) / 1e12, "frac_of_fp32_peak": fl3 / (k3 * 1e-3) / 1e12 / peak}}
+                                             "tflops_algorithmic": fl3 / (k3 * 1e-3) / 1e12, "frac_of_fp32_peak": fl3 / (k3 * 1e-3) / 1e12 / peak},
+                                  "parity": par3}
+            if par3.get("rows_bad"):
+                rc = 1
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(args, spec, S, scene, pods)
             except Exception as e:  # the oracle is optional equipment; say why it is missing
                 line["cpu_baseline"] = {"unavailable": repr(e)}
         print(json.dumps(line), flush=True)
-    sh.close()
-    r.close()
+        if rc:
+            print("bench.py: PARITY FAILURE — rows of the timed frame differ from the reference's golden CRCs", file=sys.stderr, flush=True)
+    arm.close()
     if world > 1:
         dist.destroy_process_group()
+    sys.exit(rc)
 
 
 if __name__ == "__main__":

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RTX_ABI_VERSION 3
+#define RTX_ABI_VERSION 4
 
 /* ---- status codes ------------------------------------------------------- */
 #define RTX_OK              0
@@ -99,6 +99,13 @@ typedef struct rtx_camera {
     int32_t  height;         /* rows i,    image_height = int(image_width / aspect_ratio), scene.cpp:82 */
 } rtx_camera;
 
+/* ray (scene.h:5-25): the reference's ctor takes (direction, origin) in that order (scene.h:14); the direction is
+ * NOT normalised by it and the hot path depends on its length. */
+typedef struct rtx_ray {
+    rtx_vec3 origin;
+    rtx_vec3 direction;
+} rtx_ray;
+
 #define RTX_QUANT_WRAP     0  /* reference: implicit double->Uint8, truncation, wraps mod 256 (main.cpp:345) */
 #define RTX_QUANT_SATURATE 1  /* labelled non-parity option: clamp to [0,255] */
 
@@ -151,8 +158,15 @@ typedef struct rtx_params {
 
 #define RTX_MAX_DEPTH 254     /* ray_count is a uint8: depth+1 rays per pixel at most */
 
-#define RTX_MEM_HOST   0
-#define RTX_MEM_DEVICE 1
+#define RTX_FRAME_STORE 0
+#define RTX_FRAME_COPY  1
+
+#define RTX_MEM_HOST        0   /* plain host pointers: device staging + copies (pinned or pageable memory) */
+#define RTX_MEM_DEVICE      1   /* device pointers: outputs stay in HBM */
+#define RTX_MEM_HOST_MAPPED 2   /* host pointers into PINNED, MAPPED memory (rtx_host_alloc / rtx_host_register /
+                                   rtx_host_shared_open): zero copy — the kernel stores every finished pixel straight into
+                                   the caller's surface over PCIe, the way the reference writes into SDL's surface->pixels
+                                   (main.cpp:193,344); no staging buffer, no copy after the kernel */
 
 /* Output planes, each optional (NULL = not wanted), caller-allocated, all of them either host or
  * device pointers (memory). Shapes are [n_frames][rows][width] where rows = height when n_ranks = 1,
@@ -164,14 +178,28 @@ typedef struct rtx_outputs {
     int32_t*  object_id;     /* primary-ray hit_object_index (main.cpp:80), -1 = miss */
     uint8_t*  hit_mask;      /* 1 iff the primary ray hit anything */
     uint8_t*  ray_count;     /* rays traced for the pixel (primary + reflections), 1..max_depth+1 */
-    int32_t   memory;        /* RTX_MEM_HOST | RTX_MEM_DEVICE */
-    int32_t   reserved;
+    int32_t   memory;        /* RTX_MEM_* : where the planes above live */
+    int32_t   frame_mode;    /* RTX_FRAME_* : how pixels reach frame_rgba8 */
     /* Fused multi-GPU gather: a DEVICE pointer (regardless of `memory`) to a whole row-major frame set
      * [total_frames][height][width] of RGBA8888 words, typically rank 0's buffer mapped into this process with
      * rtx_buffer_import (peer memory over NVLink). The trace kernel stores every finished pixel at its GLOBAL
      * position (global row from the band map, global frame from frame_offset/frame_stride), so no all-gather and
-     * no unpermute pass is needed: a barrier after the call completes the frame. NULL = not wanted. */
+     * no unpermute pass is needed: a barrier after the call completes the frame. NULL = not wanted.
+     * The pointer may also be the device alias of a pinned HOST frame (rtx_host_device_pointer): the ranks of one box then
+     * assemble the frame in shared host memory, each over its own PCIe link.
+     * frame_mode = RTX_FRAME_STORE (default): the trace kernel stores each finished pixel itself (4-byte stores; right
+     *   when pixels are expensive, i.e. large scenes: the stores hide entirely under the kernel).
+     * frame_mode = RTX_FRAME_COPY: the call renders into context staging and then moves whole bands / whole frames to
+     *   their place with copy-engine transfers (2-D copies for cyclic bands) on the context's copy stream — right when
+     *   pixels are cheap (small scenes, camera paths: gigabytes per second of pixels); frame_rgba8 is then any address
+     *   cudaMemcpy accepts (pinned host memory itself, local or peer device memory) and rgba8 must be NULL. With
+     *   rtx_render_async the copies of one call overlap the kernel of the next. */
     uint32_t* frame_rgba8;
+    /* What find_closest_hit (main.cpp:67-84) returns for the PRIMARY ray, beyond its index (object_id): */
+    double*   hit_distance;  /* Collision.distance: sphere = projection * |d| (scene.cpp:77), wall = t (scene.cpp:30);
+                                DBL_MAX on a miss (main.cpp:70) */
+    double*   hit_normal;    /* [..][3] Collision.normal as returned (sphere: P - c, unnormalised; wall: n as stored);
+                                (0,0,0) on a miss */
 } rtx_outputs;
 
 /* Device-side timing and diagnostics of the last rtx_render / rtx_quantise on a context.
@@ -242,6 +270,25 @@ int32_t rtx_global_row(int32_t local_row, int32_t height, int32_t band_rows, int
 int rtx_render(rtx_ctx* ctx, const rtx_camera* cameras, int32_t n_frames,
                const rtx_params* params, const rtx_outputs* outputs, rtx_stats* stats);
 
+/* The same call without the wait: everything (camera upload, kernels, read-back) is queued and the call returns.
+ * rtx_wait blocks until the OLDEST call in flight on this context has completed and yields its stats; until then
+ * the caller must not touch that call's outputs. At most two calls may be in flight per context (each owns its own
+ * staging buffers): with host outputs, frame k crosses PCIe on the context's copy stream while the kernel of frame
+ * k+1 runs — the per-call latency of small frames (host launch path + read-back) overlaps instead of adding up.
+ * A synchronous rtx_render first completes the calls in flight (their stats are dropped). */
+int rtx_render_async(rtx_ctx* ctx, const rtx_camera* cameras, int32_t n_frames,
+                     const rtx_params* params, const rtx_outputs* outputs);
+int rtx_wait(rtx_ctx* ctx, rtx_stats* stats);
+
+/* Replaces recursive_ray_tracing(scene, ray, remaining_iterations) (main.cpp:89-119, called per pixel at main.cpp:136)
+ * and find_closest_hit(scene, ray) (main.cpp:67-84) for a caller-supplied batch of rays: the same kernels as
+ * rtx_render, with ray k taking the place of pixel k's primary ray. Output planes are shaped [n_rays] (radiance
+ * [n_rays][3]); object_id / hit_distance / hit_normal describe the nearest hit of the ray itself, radiance is the
+ * value recursive_ray_tracing returns for it with params->max_depth. rays is a HOST pointer; band sharding,
+ * frame_rgba8 and the tone-map extension do not apply. */
+int rtx_trace_rays(rtx_ctx* ctx, const rtx_ray* rays, int64_t n_rays,
+                   const rtx_params* params, const rtx_outputs* outputs, rtx_stats* stats);
+
 /* The quantise loop alone (main.cpp:338-347) on a caller-supplied radiance buffer of n_pixels
  * RGB triples (exactly one of radiance_f32 / radiance_f64 non-NULL), memory = RTX_MEM_*. */
 int rtx_quantise(rtx_ctx* ctx, const float* radiance_f32, const double* radiance_f64, int64_t n_pixels,
@@ -283,6 +330,24 @@ int rtx_buffer_free(rtx_ctx* ctx, void* device_ptr);
 int rtx_buffer_export(rtx_ctx* ctx, void* device_ptr, uint8_t handle[RTX_IPC_HANDLE_BYTES]);
 int rtx_buffer_import(rtx_ctx* ctx, const uint8_t handle[RTX_IPC_HANDLE_BYTES], void** device_ptr);
 int rtx_buffer_release(rtx_ctx* ctx, void* imported_ptr);
+
+/* Pinned, mapped host memory for RTX_MEM_HOST_MAPPED outputs and for fast RTX_MEM_HOST read-back — the role of the
+ * SDL surface the reference quantises into (SDL_CreateRGBSurface, main.cpp:193; written main.cpp:338-347).
+ *   rtx_host_alloc / rtx_host_free         a new pinned + mapped buffer;
+ *   rtx_host_register / rtx_host_unregister  pin + map memory the caller already owns (e.g. a presenter's surface);
+ *   rtx_host_device_pointer                the device-side alias of such memory (what a kernel dereferences), e.g.
+ *                                          to pass a HOST frame as rtx_outputs.frame_rgba8;
+ *   rtx_host_shared_open / _close          a POSIX shared-memory object ("/name") mapped and pinned in THIS process:
+ *                                          the per-GPU processes of one box all map the same host frame and each
+ *                                          writes its own rows over its own PCIe link (create != 0 in exactly one of
+ *                                          them, before the others open it; unlink_name != NULL removes the object). */
+int rtx_host_alloc(rtx_ctx* ctx, uint64_t bytes, void** host_ptr);
+int rtx_host_free(rtx_ctx* ctx, void* host_ptr);
+int rtx_host_register(rtx_ctx* ctx, void* host_ptr, uint64_t bytes);
+int rtx_host_unregister(rtx_ctx* ctx, void* host_ptr);
+int rtx_host_device_pointer(rtx_ctx* ctx, void* host_ptr, void** device_ptr);
+int rtx_host_shared_open(rtx_ctx* ctx, const char* name, uint64_t bytes, int32_t create, void** host_ptr);
+int rtx_host_shared_close(rtx_ctx* ctx, void* host_ptr, const char* unlink_name);
 
 /* FP32 FFMA throughput microbenchmark (the roofline denominator has no entry in MEASURED_PEAKS.json):
  * returns achieved TFLOP/s of a dependent-chain-free FFMA loop over the whole chip. variant 0 = scalar

@@ -415,10 +415,17 @@ double orc_render_rows_params(const rtx_object* objs, int32_t n_objs, const rtx_
     if (n_threads <= 0) n_threads = omp_get_max_threads();
 #endif
     double t0 = now_s();
+    /* work items = (row, 64-pixel column chunk), like oracle/ref_harness.cpp: a few rows still feed every thread */
+    enum { CHUNK = 64 };
+    const int n_chunks = (W + CHUNK - 1) / CHUNK;
+    const long long n_items = (long long)n_rows * n_chunks;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads) reduction(+ : rays_sum)
-    for (int k = 0; k < n_rows; k++) {
+    for (long long item = 0; item < n_items; item++) {
+        const int k = (int)(item / n_chunks);
+        const int j0 = (int)(item - (long long)k * n_chunks) * CHUNK;
+        const int j1 = j0 + CHUNK < W ? j0 + CHUNK : W;
         const int i = rows[k];
-        for (int j = 0; j < W; j++) {
+        for (int j = j0; j < j1; j++) {
             v3 center = add(add(cam->image_top_left, scale(cam->delta_x, j)), scale(cam->delta_y, i)); /* main.cpp:132 */
             v3 d = sub(cam->position, center);                                                          /* main.cpp:133 */
             int rays = 0;

@@ -15,8 +15,9 @@
  * needed because rt_scene hard-codes the depth default and a transposed frame buffer that only works
  * for square frames (main.cpp:243 vs :136), (b) the chain walk that counts rays (main.cpp:99,111-113),
  * and (c) the byte packing SDL_MapRGB does for the RGBA8888 masks of main.cpp:193.
- * Rows are distributed over OpenMP threads ("lines of the image are distributed across hardware
- * threads", README.md:13) — the per-pixel function only reads const scene data, so this is safe.
+ * The image is distributed over OpenMP threads ("lines of the image are distributed across hardware
+ * threads", README.md:13; here in 64-pixel pieces of a line so that a sample of a few lines still occupies
+ * every thread) — the per-pixel function only reads const scene data, so this is safe.
  */
 #include <SDL.h>
 #include <chrono>
@@ -102,6 +103,7 @@ void SDL_RenderPresent(SDL_Renderer*) {}
 
 /* ---- helpers ---------------------------------------------------------------------------------- */
 using Scene = std::vector<std::unique_ptr<SceneGeometry>>;
+constexpr int kChunk = 64;   /* pixels per OpenMP work item of ref_render_rows */
 
 static inline vec3 V(const rtx_vec3& v) { return vec3(v.x, v.y, v.z); }
 static inline rtx_vec3 P(const vec3& v) { return rtx_vec3{v.x, v.y, v.z}; }
@@ -233,10 +235,18 @@ double ref_render_rows(const rtx_object* objs, int32_t n_objs, const rtx_camera*
     if (n_threads <= 0) n_threads = omp_get_max_threads();
 #endif
     auto t0 = std::chrono::high_resolution_clock::now();
+    /* Work items are (row, 64-pixel column chunk) pairs, handed out dynamically: a bounded sample of a few rows of a
+     * costly frame (bench.py) still feeds every hardware thread, and a row that crosses a dense part of the scene does
+     * not serialise the tail. The per-pixel code below is untouched. */
+    const int n_chunks = (W + kChunk - 1) / kChunk;
+    const long long n_items = static_cast<long long>(n_rows) * n_chunks;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads) reduction(+ : rays)
-    for (int k = 0; k < n_rows; k++) {
+    for (long long item = 0; item < n_items; item++) {
+        const int k = static_cast<int>(item / n_chunks);
+        const int j0 = static_cast<int>(item - static_cast<long long>(k) * n_chunks) * kChunk;
+        const int j1 = j0 + kChunk < W ? j0 + kChunk : W;
         const int i = rows[k];
-        for (int j = 0; j < W; j++) {
+        for (int j = j0; j < j1; j++) {
             /* main.cpp:132-134 */
             auto pixel_center = top_left + dx * j + dy * i;
             auto cam_pixel = pos - pixel_center;

@@ -5,13 +5,14 @@ the reference code (file:line) every field stands for.
 """
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 RTX_OK, RTX_ERR_INVALID, RTX_ERR_CUDA, RTX_ERR_NO_SCENE, RTX_ERR_NOMEM = 0, 1, 2, 3, 4
 RTX_SPHERE, RTX_WALL, RTX_BOX = 0, 1, 2        # RTX_BOX: extension, see the header
 RTX_QUANT_WRAP, RTX_QUANT_SATURATE = 0, 1
 RTX_TONEMAP_NONE, RTX_TONEMAP_REINHARD = 0, 1    # extension, see the header
-RTX_MEM_HOST, RTX_MEM_DEVICE = 0, 1
+RTX_MEM_HOST, RTX_MEM_DEVICE, RTX_MEM_HOST_MAPPED = 0, 1, 2
+RTX_FRAME_STORE, RTX_FRAME_COPY = 0, 1
 RTX_MAX_DEPTH = 254
 
 
@@ -45,6 +46,10 @@ class CameraPOD(C.Structure):
                 ("width", C.c_int32), ("height", C.c_int32)]
 
 
+class RayPOD(C.Structure):
+    _fields_ = [("origin", Vec3), ("direction", Vec3)]
+
+
 class Params(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("quantise_mode", C.c_int32), ("fuse_quantise", C.c_int32),
                 ("reserved", C.c_int32),
@@ -60,7 +65,8 @@ class Params(C.Structure):
 class Outputs(C.Structure):
     _fields_ = [("rgba8", C.c_void_p), ("radiance_f32", C.c_void_p), ("radiance_f64", C.c_void_p),
                 ("object_id", C.c_void_p), ("hit_mask", C.c_void_p), ("ray_count", C.c_void_p),
-                ("memory", C.c_int32), ("reserved", C.c_int32), ("frame_rgba8", C.c_void_p)]
+                ("memory", C.c_int32), ("frame_mode", C.c_int32), ("frame_rgba8", C.c_void_p),
+                ("hit_distance", C.c_void_p), ("hit_normal", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -79,6 +85,8 @@ class Stats(C.Structure):
 EXPORTS = (
     "rtx_abi_version", "rtx_status_string", "rtx_create", "rtx_destroy", "rtx_last_error", "rtx_set_stream",
     "rtx_set_scene", "rtx_camera_init", "rtx_default_params", "rtx_local_rows", "rtx_global_row",
-    "rtx_render", "rtx_quantise", "rtx_tonemap", "rtx_tonemap_sums", "rtx_tonemap_apply", "rtx_unpermute_bands", "rtx_ffma_peak",
+    "rtx_render", "rtx_render_async", "rtx_wait", "rtx_trace_rays", "rtx_quantise", "rtx_tonemap", "rtx_tonemap_sums", "rtx_tonemap_apply", "rtx_unpermute_bands", "rtx_ffma_peak",
+    "rtx_host_alloc", "rtx_host_free", "rtx_host_register", "rtx_host_unregister", "rtx_host_device_pointer",
+    "rtx_host_shared_open", "rtx_host_shared_close",
     "rtx_buffer_alloc", "rtx_buffer_free", "rtx_buffer_export", "rtx_buffer_import", "rtx_buffer_release",
 )

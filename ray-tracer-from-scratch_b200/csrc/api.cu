@@ -1,7 +1,12 @@
 // api.cu — the extern "C" layer of include/rtx_b200.h: context, scene upload, render, quantise, gather epilogue.
 // Host code only (kernels are in trace.cu / aux_kernels.cu). Built with -ffp-contract=off: the few doubles
 // computed here (wall normal + basis, Camera::init) must round exactly like the reference's x86-64 build.
+#include <cerrno>
 #include <cmath>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -14,37 +19,67 @@ using namespace rtx;
 
 constexpr int kRanges = 4;                        // pixel ranges of a small-scene frame rendered into host memory
 constexpr size_t kRangedMinPixels = 1u << 17;     // below this a frame is one launch and one copy
+constexpr int kPlanes = 8;                        // rgba8, radiance f32, radiance f64, object id, hit mask, ray count, hit distance, hit normal
+constexpr int kSlots = 2;                         // calls in flight per context (rtx_render_async)
+
+// Everything ONE call in flight owns: pinned + device copies of its cameras / rays, its counters, its device staging
+// for host outputs and its events. Two slots let frame k's read-back overlap frame k+1's kernel (rtx_render_async).
+struct Slot {
+    bool pending = false;
+    rtx_camera* d_cameras = nullptr;
+    rtx_camera* h_cameras = nullptr;   // pinned
+    int cameras_cap = 0;
+    rtx_ray* d_rays = nullptr;
+    rtx_ray* h_rays = nullptr;         // pinned
+    size_t rays_cap = 0;
+    unsigned long long* d_counters = nullptr;
+    unsigned long long* h_counters = nullptr;   // pinned: [0..7] read-back, [8..15] reset template, [16..23] first pixel of each range
+    void* d_out[kPlanes] = {};
+    size_t d_out_cap[kPlanes] = {};
+    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev_range[kRanges + 1] = {};   // range k traced (0..kRanges-1); all copies done (kRanges)
+    cudaEvent_t ev_done = nullptr;            // everything of the call (kernels, copies, counter read-back) is complete
+    // what rtx_wait needs to fill rtx_stats
+    int launches = 0;
+    int n_spheres = 0, n_walls = 0;
+    bool copies_on_side_stream = false;
+};
 
 struct rtx_ctx {
     int device = 0;
     int n_sms = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {};
-    cudaStream_t copy_stream = nullptr;           // read-back of finished pixel ranges while the next range is traced
-    cudaEvent_t ev_range[kRanges + 1] = {};       // range k traced (0..kRanges-1); all copies done (kRanges)
+    cudaStream_t copy_stream = nullptr;           // read-back of finished frames / pixel ranges while the next is traced
     std::string error;
+    TraceLaunchState launch_state;
 
     // scene
     bool have_scene = false;
     SceneDev scene = {};
     void* d_scene_blob = nullptr;
     size_t scene_blob_cap = 0;
+    unsigned char* h_scene_blob = nullptr;        // pinned staging of the blob: the upload is stream-ordered, no synchronise
+    size_t h_scene_blob_cap = 0;
+    cudaEvent_t ev_scene = nullptr;               // the last upload has left h_scene_blob
     double scene_bound = 0.0;          // max over objects of |coordinate| + extent
 
-    // per-call scratch (grown on demand, reused across calls)
-    rtx_camera* d_cameras = nullptr;
-    rtx_camera* h_cameras = nullptr;   // pinned
-    int cameras_cap = 0;
-    unsigned long long* d_counters = nullptr;
-    unsigned long long* h_counters = nullptr;   // pinned
-    void* d_out[6] = {};
-    size_t d_out_cap[6] = {};
-    double* d_rad_scratch = nullptr;   // radiance buffer for the unfused quantise path
+    Slot slot[kSlots];
+    int next_slot = 0;                 // slot the next call takes
+    int oldest = 0;                    // oldest pending slot (rtx_wait order)
+
+    double* d_rad_scratch = nullptr;   // radiance buffer for the unfused quantise path (stream-ordered reuse)
     size_t d_rad_scratch_cap = 0;
     void* d_tm_sums = nullptr;         // tone-map extension: per-frame fixed-point log-luminance sums
     size_t d_tm_sums_cap = 0;
     std::vector<long long> h_tm_sums;
+    // standalone calls (quantise / tonemap / ...) use slot 0's counters and these events
+    cudaEvent_t ev[6] = {};
+    void* d_aux_out = nullptr;         // device staging of rtx_quantise / rtx_tonemap with host pointers
+    size_t d_aux_out_cap = 0;
+    unsigned long long* d_aux_counters = nullptr;
+    unsigned long long* h_aux_counters = nullptr;   // pinned
+    std::vector<std::pair<void*, size_t>> shared_host;   // rtx_host_shared_open mappings (unmapped by rtx_destroy)
 };
 
 namespace {
@@ -152,14 +187,20 @@ int rtx_create(rtx_ctx** out, int device)
     }
     ctx->n_sms = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (auto& ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (auto& ev : ctx->ev_range) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaHostAlloc(&ctx->h_counters, 24 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
-    if (ok) {   // [0..7] read-back area, [8..15] reset template, [16..23] first pixel of each range
-        for (int k = 0; k < 8; k++) ctx->h_counters[8 + k] = (k >= 4 && k <= 6) ? ~0ull : 0ull;
+    for (auto& ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_scene, cudaEventDisableTiming) == cudaSuccess;
+    for (Slot& sl : ctx->slot) {
+        for (auto& ev : sl.ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+        for (auto& ev : sl.ev_range) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaMalloc(&sl.d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess;
+        ok = ok && cudaHostAlloc(&sl.h_counters, 24 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
+        if (ok)   // [0..7] read-back area, [8..15] reset template, [16..23] first pixel of each range
+            for (int k = 0; k < 8; k++) sl.h_counters[8 + k] = (k >= 4 && k <= 6) ? ~0ull : 0ull;
     }
+    ok = ok && cudaMalloc(&ctx->d_aux_counters, 8 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&ctx->h_aux_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
     if (!ok) {
         g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
         rtx_destroy(ctx);
@@ -174,21 +215,39 @@ void rtx_destroy(rtx_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
-    for (auto& ev : ctx->ev_range)
-        if (ev) cudaEventDestroy(ev);
-    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_scene) cudaEventDestroy(ctx->ev_scene);
+    for (Slot& sl : ctx->slot) {
+        for (auto& ev : sl.ev)
+            if (ev) cudaEventDestroy(ev);
+        for (auto& ev : sl.ev_range)
+            if (ev) cudaEventDestroy(ev);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+        if (sl.d_cameras) cudaFree(sl.d_cameras);
+        if (sl.h_cameras) cudaFreeHost(sl.h_cameras);
+        if (sl.d_rays) cudaFree(sl.d_rays);
+        if (sl.h_rays) cudaFreeHost(sl.h_rays);
+        if (sl.d_counters) cudaFree(sl.d_counters);
+        if (sl.h_counters) cudaFreeHost(sl.h_counters);
+        for (auto& p : sl.d_out)
+            if (p) cudaFree(p);
+    }
+    if (ctx->d_aux_counters) cudaFree(ctx->d_aux_counters);
+    if (ctx->h_aux_counters) cudaFreeHost(ctx->h_aux_counters);
+    if (ctx->d_aux_out) cudaFree(ctx->d_aux_out);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->d_scene_blob) cudaFree(ctx->d_scene_blob);
-    if (ctx->d_cameras) cudaFree(ctx->d_cameras);
-    if (ctx->h_cameras) cudaFreeHost(ctx->h_cameras);
-    if (ctx->d_counters) cudaFree(ctx->d_counters);
-    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
-    for (auto& p : ctx->d_out)
-        if (p) cudaFree(p);
+    if (ctx->h_scene_blob) cudaFreeHost(ctx->h_scene_blob);
     if (ctx->d_rad_scratch) cudaFree(ctx->d_rad_scratch);
     if (ctx->d_tm_sums) cudaFree(ctx->d_tm_sums);
+    for (auto& m : ctx->shared_host) {
+        cudaHostUnregister(m.first);
+        munmap(m.first, m.second);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -198,6 +257,10 @@ const char* rtx_last_error(const rtx_ctx* ctx) { return ctx ? ctx->error.c_str()
 int rtx_set_stream(rtx_ctx* ctx, void* cuda_stream)
 {
     if (!ctx) return RTX_ERR_INVALID;
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    // work already queued (scene upload, calls in flight) stays ordered before anything on the new stream
+    RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RTX_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     ctx->stream = cuda_stream == RTX_STREAM_PRIVATE ? ctx->own_stream : static_cast<cudaStream_t>(cuda_stream);
     return RTX_OK;
 }
@@ -308,7 +371,24 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
     const size_t o_mat = off; off = align(off + sizeof(MaterialDev) * std::max(n, 1));
     const size_t o_knd = off; off = align(off + sizeof(int32_t) * std::max(n, 1));
     const size_t o_slt = off; off = align(off + sizeof(int32_t) * std::max(n, 1));
-    std::vector<unsigned char> blob(off, 0);
+    // Pinned staging + stream-ordered upload: the copy queues behind the kernels of earlier calls (they read the old
+    // scene) and in front of those of later calls; the host never waits for the device here.
+    if (off > ctx->h_scene_blob_cap) {
+        if (ctx->h_scene_blob) {
+            RTX_CUDA(ctx, cudaEventSynchronize(ctx->ev_scene));
+            cudaFreeHost(ctx->h_scene_blob);
+        }
+        ctx->h_scene_blob = nullptr;
+        ctx->h_scene_blob_cap = 0;
+        const size_t cap = std::max<size_t>(off, 1 << 16);
+        if (cudaHostAlloc(&ctx->h_scene_blob, cap, cudaHostAllocDefault) != cudaSuccess)
+            return fail(ctx, RTX_ERR_NOMEM, "rtx_set_scene: pinned staging");
+        ctx->h_scene_blob_cap = cap;
+    } else {
+        RTX_CUDA(ctx, cudaEventSynchronize(ctx->ev_scene));   // the previous upload has left the staging buffer
+    }
+    unsigned char* blob = ctx->h_scene_blob;
+    std::memset(blob, 0, off);
     if (ns_pad) std::memcpy(&blob[o_s32], sph32.data(), sizeof(float4) * ns_pad);
     if (ns) std::memcpy(&blob[o_s64], sph64.data(), sizeof(SphereExact) * ns);
     if (ns) std::memcpy(&blob[o_sid], sph_key.data(), sizeof(int32_t) * ns);
@@ -317,18 +397,20 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
     if (n) std::memcpy(&blob[o_knd], kind.data(), sizeof(int32_t) * n);
     if (n) std::memcpy(&blob[o_slt], slot.data(), sizeof(int32_t) * n);
 
-    RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // no kernel of an earlier call still reads the old scene
     ctx->have_scene = false;
     if (off > ctx->scene_blob_cap) {                         // the allocation is kept and reused while the new scene fits
-        if (ctx->d_scene_blob) cudaFree(ctx->d_scene_blob);
+        if (ctx->d_scene_blob) {
+            RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // kernels in flight still read the old allocation
+            cudaFree(ctx->d_scene_blob);
+        }
         ctx->d_scene_blob = nullptr;
         ctx->scene_blob_cap = 0;
         cudaError_t e = cudaMalloc(&ctx->d_scene_blob, off);
         if (e != cudaSuccess) return fail(ctx, RTX_ERR_NOMEM, std::string("cudaMalloc(scene): ") + cudaGetErrorString(e));
         ctx->scene_blob_cap = off;
     }
-    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_scene_blob, blob.data(), off, cudaMemcpyHostToDevice, ctx->stream));
-    RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_scene_blob, blob, off, cudaMemcpyHostToDevice, ctx->stream));
+    RTX_CUDA(ctx, cudaEventRecord(ctx->ev_scene, ctx->stream));
     unsigned char* base = static_cast<unsigned char*>(ctx->d_scene_blob);
     SceneDev& s = ctx->scene;
     s.n_objects = n;
@@ -423,32 +505,96 @@ int32_t rtx_global_row(int32_t local_row, int32_t height, int32_t band_rows, int
     return (lb * n_ranks + rank) * band_rows + (local_row - lb * band_rows);
 }
 
-int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx_params* params, const rtx_outputs* outs,
-               rtx_stats* stats)
+}  // extern "C"
+
+namespace {
+
+// Waits for the call in `sl` and turns its events / counters into rtx_stats.
+int finish_slot(rtx_ctx* ctx, Slot& sl, rtx_stats* stats)
+{
+    sl.pending = false;
+    RTX_CUDA(ctx, cudaEventSynchronize(sl.ev_done));
+    RTX_CUDA(ctx, cudaGetLastError());
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, sl.ev[0], sl.ev[1]); stats->h2d_ms = ms;
+        cudaEventElapsedTime(&ms, sl.ev[1], sl.ev[2]); stats->raytracing_ms = ms;
+        cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[3]); stats->surface_update_ms = ms;
+        cudaEventElapsedTime(&ms, sl.ev[3], sl.ev[4]); stats->d2h_ms = ms;
+        cudaEventElapsedTime(&ms, sl.ev[0], sl.ev[4]); stats->total_ms = ms;
+        stats->total_rays = sl.h_counters[1];
+        stats->sphere_tests = stats->total_rays * static_cast<uint64_t>(sl.n_spheres);
+        stats->wall_tests = stats->total_rays * static_cast<uint64_t>(sl.n_walls);
+        stats->over_range_pixels = sl.h_counters[2];
+        long long bits = static_cast<long long>(sl.h_counters[3]);
+        std::memcpy(&stats->max_luminance, &bits, sizeof bits);
+        stats->launches = sl.launches;
+        const unsigned long long t0 = sl.h_counters[4], dry = sl.h_counters[5], first = sl.h_counters[6], last = sl.h_counters[7];
+        if (t0 != ~0ull && last >= t0) {
+            stats->drain_ms = (dry != ~0ull && last >= dry) ? (last - dry) * 1e-6 : 0.0;
+            stats->exit_spread_ms = (first != ~0ull && last >= first) ? (last - first) * 1e-6 : 0.0;
+        }
+    }
+    return RTX_OK;
+}
+
+// rtx_render / rtx_render_async / rtx_trace_rays: validate, allocate, THEN enqueue (an error after the first enqueue
+// synchronises both streams before returning, so the device never writes a caller's buffer after an error return).
+int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx_ray* rays, int64_t n_rays, const rtx_params* params,
+                const rtx_outputs* outs, rtx_stats* stats, bool async, const char* who)
 {
     if (!ctx) return RTX_ERR_INVALID;
-    if (!ctx->have_scene) return fail(ctx, RTX_ERR_NO_SCENE, "rtx_render: call rtx_set_scene first");
-    if (!cams || n_frames <= 0 || !params || !outs) return fail(ctx, RTX_ERR_INVALID, "rtx_render: null argument or n_frames <= 0");
+    const std::string W_(who);
+    if (!ctx->have_scene) return fail(ctx, RTX_ERR_NO_SCENE, W_ + ": call rtx_set_scene first");
+    const bool ray_mode = rays != nullptr || cams == nullptr;
+    if (!params || !outs) return fail(ctx, RTX_ERR_INVALID, W_ + ": null argument");
+    if (ray_mode) {
+        if (!rays || n_rays <= 0 || n_rays > 0x7fffffff) return fail(ctx, RTX_ERR_INVALID, W_ + ": null rays or n_rays out of [1, 2^31)");
+    } else if (!cams || n_frames <= 0) {
+        return fail(ctx, RTX_ERR_INVALID, W_ + ": null argument or n_frames <= 0");
+    }
     const rtx_params& p = *params;
-    if (p.max_depth < 0 || p.max_depth > RTX_MAX_DEPTH) return fail(ctx, RTX_ERR_INVALID, "rtx_render: max_depth out of [0, 254]");
+    if (p.max_depth < 0 || p.max_depth > RTX_MAX_DEPTH) return fail(ctx, RTX_ERR_INVALID, W_ + ": max_depth out of [0, 254]");
     if (p.n_ranks < 1 || p.rank < 0 || p.rank >= p.n_ranks || (p.n_ranks > 1 && p.band_rows < 1))
-        return fail(ctx, RTX_ERR_INVALID, "rtx_render: bad band sharding (band_rows, n_ranks, rank)");
+        return fail(ctx, RTX_ERR_INVALID, W_ + ": bad band sharding (band_rows, n_ranks, rank)");
     if (p.quantise_mode != RTX_QUANT_WRAP && p.quantise_mode != RTX_QUANT_SATURATE)
-        return fail(ctx, RTX_ERR_INVALID, "rtx_render: unknown quantise_mode");
-    if (outs->memory != RTX_MEM_HOST && outs->memory != RTX_MEM_DEVICE)
-        return fail(ctx, RTX_ERR_INVALID, "rtx_render: outputs.memory must be RTX_MEM_HOST or RTX_MEM_DEVICE");
-    if (p.tonemap != RTX_TONEMAP_NONE && p.tonemap != RTX_TONEMAP_REINHARD) return fail(ctx, RTX_ERR_INVALID, "rtx_render: unknown tonemap");
+        return fail(ctx, RTX_ERR_INVALID, W_ + ": unknown quantise_mode");
+    if (outs->memory != RTX_MEM_HOST && outs->memory != RTX_MEM_DEVICE && outs->memory != RTX_MEM_HOST_MAPPED)
+        return fail(ctx, RTX_ERR_INVALID, W_ + ": outputs.memory must be RTX_MEM_HOST, RTX_MEM_DEVICE or RTX_MEM_HOST_MAPPED");
+    if (p.tonemap != RTX_TONEMAP_NONE && p.tonemap != RTX_TONEMAP_REINHARD) return fail(ctx, RTX_ERR_INVALID, W_ + ": unknown tonemap");
     const bool tonemap = p.tonemap == RTX_TONEMAP_REINHARD && outs->rgba8;
-    if (tonemap && (p.n_ranks != 1 || outs->frame_rgba8))
-        return fail(ctx, RTX_ERR_INVALID, "rtx_render: the tone-map operator needs the whole frame on one GPU (n_ranks = 1, no frame_rgba8)");
-    if (tonemap && !(p.tonemap_key > 0.0)) return fail(ctx, RTX_ERR_INVALID, "rtx_render: tonemap_key must be > 0");
-    const int W = cams[0].width, Hh = cams[0].height;
-    if (W <= 0 || Hh <= 0) return fail(ctx, RTX_ERR_INVALID, "rtx_render: camera width/height must be positive");
+    if (tonemap && (p.n_ranks != 1 || outs->frame_rgba8 || ray_mode))
+        return fail(ctx, RTX_ERR_INVALID, W_ + ": the tone-map operator needs the whole frame on one GPU (n_ranks = 1, no frame_rgba8, no ray batch)");
+    if (tonemap && !(p.tonemap_key > 0.0)) return fail(ctx, RTX_ERR_INVALID, W_ + ": tonemap_key must be > 0");
+    if (ray_mode && (p.n_ranks != 1 || outs->frame_rgba8))
+        return fail(ctx, RTX_ERR_INVALID, W_ + ": a ray batch is not sharded (n_ranks = 1, no frame_rgba8)");
+    if (outs->frame_rgba8 && (p.frame_stride < 1 || p.frame_offset < 0))
+        return fail(ctx, RTX_ERR_INVALID, W_ + ": frame_offset/frame_stride must be >= 0 / >= 1");
+    if (outs->frame_mode != RTX_FRAME_STORE && outs->frame_mode != RTX_FRAME_COPY)
+        return fail(ctx, RTX_ERR_INVALID, W_ + ": unknown frame_mode");
+    const bool frame_copy = outs->frame_rgba8 && outs->frame_mode == RTX_FRAME_COPY;
+    if (frame_copy && outs->rgba8) return fail(ctx, RTX_ERR_INVALID, W_ + ": RTX_FRAME_COPY uses the rgba8 plane as its staging: pass rgba8 = NULL");
+    int W, Hh;
     double cam_bound = 0.0;
-    for (int f = 0; f < n_frames; f++) {
-        if (cams[f].width != W || cams[f].height != Hh)
-            return fail(ctx, RTX_ERR_INVALID, "rtx_render: all cameras of one call must share width/height");
-        cam_bound = std::fmax(cam_bound, amax3(H(cams[f].position)));
+    if (ray_mode) {
+        W = static_cast<int>(n_rays);
+        Hh = 1;
+        n_frames = 1;
+        for (int64_t k = 0; k < n_rays; k++) {
+            const double m = amax3(H(rays[k].origin));
+            if (std::isfinite(m)) cam_bound = std::fmax(cam_bound, m);    // a far or non-finite origin takes the exact fallback anyway
+        }
+        cam_bound = std::fmin(cam_bound, 4.0 * std::fmax(ctx->scene_bound, 1e-3));   // keep the screen's E tight: outliers fall back
+    } else {
+        W = cams[0].width;
+        Hh = cams[0].height;
+        if (W <= 0 || Hh <= 0) return fail(ctx, RTX_ERR_INVALID, W_ + ": camera width/height must be positive");
+        for (int f = 0; f < n_frames; f++) {
+            if (cams[f].width != W || cams[f].height != Hh)
+                return fail(ctx, RTX_ERR_INVALID, W_ + ": all cameras of one call must share width/height");
+            cam_bound = std::fmax(cam_bound, amax3(H(cams[f].position)));
+        }
     }
     RTX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -456,38 +602,62 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
     const int local_rows = rtx_local_rows(Hh, band_rows, p.n_ranks, p.rank);
     const size_t n_px = static_cast<size_t>(n_frames) * local_rows * W;
 
-    // cameras -> pinned staging -> device
-    if (n_frames > ctx->cameras_cap) {
-        if (ctx->d_cameras) cudaFree(ctx->d_cameras);
-        if (ctx->h_cameras) cudaFreeHost(ctx->h_cameras);
-        ctx->d_cameras = nullptr;
-        ctx->h_cameras = nullptr;
-        ctx->cameras_cap = 0;
-        const int cap = std::max(n_frames, 16);
-        if (cudaMalloc(&ctx->d_cameras, sizeof(rtx_camera) * cap) != cudaSuccess ||
-            cudaHostAlloc(&ctx->h_cameras, sizeof(rtx_camera) * cap, cudaHostAllocDefault) != cudaSuccess)
-            return fail(ctx, RTX_ERR_NOMEM, "rtx_render: camera buffers");
-        ctx->cameras_cap = cap;
-    }
-    std::memcpy(ctx->h_cameras, cams, sizeof(rtx_camera) * n_frames);
+    // ---- slot: at most kSlots calls in flight ---------------------------------------------------------------------
+    Slot& sl = ctx->slot[ctx->next_slot];
+    if (sl.pending) return fail(ctx, RTX_ERR_INVALID, W_ + ": too many calls in flight (rtx_wait first)");
 
-    // output planes: the caller's device pointers, or device staging for host pointers
-    void* user[6] = {outs->rgba8, outs->radiance_f32, outs->radiance_f64, outs->object_id, outs->hit_mask, outs->ray_count};
-    const size_t elem[6] = {4, 12, 24, 4, 1, 1};
-    void* dev[6] = {};
+    // ---- allocations (all before the first enqueue) -----------------------------------------------------------------
+    if (!ray_mode && n_frames > sl.cameras_cap) {
+        if (sl.d_cameras) cudaFree(sl.d_cameras);
+        if (sl.h_cameras) cudaFreeHost(sl.h_cameras);
+        sl.d_cameras = nullptr;
+        sl.h_cameras = nullptr;
+        sl.cameras_cap = 0;
+        const int cap = std::max(n_frames, 16);
+        if (cudaMalloc(&sl.d_cameras, sizeof(rtx_camera) * cap) != cudaSuccess ||
+            cudaHostAlloc(&sl.h_cameras, sizeof(rtx_camera) * cap, cudaHostAllocDefault) != cudaSuccess)
+            return fail(ctx, RTX_ERR_NOMEM, W_ + ": camera buffers");
+        sl.cameras_cap = cap;
+    }
+    if (ray_mode && static_cast<size_t>(n_rays) > sl.rays_cap) {
+        if (sl.d_rays) cudaFree(sl.d_rays);
+        if (sl.h_rays) cudaFreeHost(sl.h_rays);
+        sl.d_rays = nullptr;
+        sl.h_rays = nullptr;
+        sl.rays_cap = 0;
+        const size_t cap = std::max<size_t>(n_rays, 256);
+        if (cudaMalloc(&sl.d_rays, sizeof(rtx_ray) * cap) != cudaSuccess ||
+            cudaHostAlloc(&sl.h_rays, sizeof(rtx_ray) * cap, cudaHostAllocDefault) != cudaSuccess)
+            return fail(ctx, RTX_ERR_NOMEM, W_ + ": ray buffers");
+        sl.rays_cap = cap;
+    }
+    // output planes: the caller's device pointers, the device alias of the caller's mapped host memory, or device
+    // staging for plain host pointers
+    void* user[kPlanes] = {outs->rgba8, outs->radiance_f32, outs->radiance_f64, outs->object_id, outs->hit_mask, outs->ray_count,
+                           outs->hit_distance, outs->hit_normal};
+    const size_t elem[kPlanes] = {4, 12, 24, 4, 1, 1, 8, 24};
+    void* dev[kPlanes] = {};
     const bool host_out = outs->memory == RTX_MEM_HOST;
-    for (int k = 0; k < 6; k++) {
+    for (int k = 0; k < kPlanes; k++) {
         if (!user[k]) continue;
         if (host_out) {
-            int rc = grow(ctx, &ctx->d_out[k], &ctx->d_out_cap[k], std::max<size_t>(n_px * elem[k], 16));
+            int rc = grow(ctx, &sl.d_out[k], &sl.d_out_cap[k], std::max<size_t>(n_px * elem[k], 16));
             if (rc != RTX_OK) return rc;
-            dev[k] = ctx->d_out[k];
+            dev[k] = sl.d_out[k];
+        } else if (outs->memory == RTX_MEM_HOST_MAPPED) {
+            // zero copy: the kernel stores straight into the caller's pinned, mapped surface (SDL's surface->pixels, main.cpp:193,344)
+            if (cudaHostGetDevicePointer(&dev[k], user[k], 0) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(ctx, RTX_ERR_INVALID, W_ + ": RTX_MEM_HOST_MAPPED needs memory from rtx_host_alloc / rtx_host_register / rtx_host_shared_open");
+            }
         } else {
             dev[k] = user[k];
         }
     }
-    if (outs->frame_rgba8 && (p.frame_stride < 1 || p.frame_offset < 0))
-        return fail(ctx, RTX_ERR_INVALID, "rtx_render: frame_offset/frame_stride must be >= 0 / >= 1");
+    if (frame_copy) {   // the packed local frame(s) in context staging; bulk copies place them afterwards
+        int rc = grow(ctx, &sl.d_out[0], &sl.d_out_cap[0], std::max<size_t>(n_px * 4, 16));
+        if (rc != RTX_OK) return rc;
+    }
     const bool unfused = (!p.fuse_quantise || tonemap) && user[0] && !outs->frame_rgba8;
     double* rad_for_quant = nullptr;
     if (unfused) {
@@ -500,11 +670,19 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
             if (rc != RTX_OK) return rc;
             rad_for_quant = ctx->d_rad_scratch;
         }
+        if (tonemap) {
+            int rc = grow(ctx, &ctx->d_tm_sums, &ctx->d_tm_sums_cap, sizeof(long long) * std::max(n_frames, 16));
+            if (rc != RTX_OK) return rc;
+        }
     }
+
+    if (ray_mode) std::memcpy(sl.h_rays, rays, sizeof(rtx_ray) * n_rays);
+    else std::memcpy(sl.h_cameras, cams, sizeof(rtx_camera) * n_frames);
 
     TraceArgs a = {};
     a.scene = ctx->scene;
-    a.cameras = ctx->d_cameras;
+    a.cameras = ray_mode ? nullptr : sl.d_cameras;
+    a.rays = ray_mode ? sl.d_rays : nullptr;
     a.n_frames = n_frames;
     a.width = W;
     a.height = Hh;
@@ -535,101 +713,180 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx
     a.object_id = static_cast<int32_t*>(dev[3]);
     a.hit_mask = static_cast<uint8_t*>(dev[4]);
     a.ray_count = static_cast<uint8_t*>(dev[5]);
-    a.frame_rgba8 = outs->frame_rgba8;
+    a.hit_distance = static_cast<double*>(dev[6]);
+    a.hit_normal = static_cast<double*>(dev[7]);
+    a.frame_rgba8 = frame_copy ? nullptr : outs->frame_rgba8;
+    if (frame_copy) a.rgba8 = static_cast<uint32_t*>(sl.d_out[0]);
     a.frame_offset = p.frame_offset;
     a.frame_stride = p.frame_stride;
-    a.counters = ctx->d_counters;
+    a.counters = sl.d_counters;
+
+    // ---- enqueue ----------------------------------------------------------------------------------------------------------
+    cudaStream_t cs = ctx->copy_stream;
+    auto bail = [&](cudaError_t e, const char* what) {
+        cudaStreamSynchronize(st);
+        cudaStreamSynchronize(cs);
+        return cuda_fail(ctx, e, what);
+    };
+#define RTX_ENQ(call)                                        \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return bail(e__, #call);     \
+    } while (0)
 
     int launches = 0;
-    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_cameras, ctx->h_cameras, sizeof(rtx_camera) * n_frames, cudaMemcpyHostToDevice, st));
+    RTX_ENQ(cudaEventRecord(sl.ev[0], st));
+    if (ray_mode) RTX_ENQ(cudaMemcpyAsync(sl.d_rays, sl.h_rays, sizeof(rtx_ray) * n_rays, cudaMemcpyHostToDevice, st));
+    else RTX_ENQ(cudaMemcpyAsync(sl.d_cameras, sl.h_cameras, sizeof(rtx_camera) * n_frames, cudaMemcpyHostToDevice, st));
     // counters: [0..3] = 0, [4..6] = ~0 (atomicMin slots), [7] = 0 — one copy from a pinned template
-    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_counters, ctx->h_counters + 8, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    RTX_ENQ(cudaMemcpyAsync(sl.d_counters, sl.h_counters + 8, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    RTX_ENQ(cudaEventRecord(sl.ev[1], st));
     // A small scene rendered into HOST memory is bound by the PCIe read-back, not by the kernel (1080p: 0.08 ms of
     // tracing, 0.15 ms of copy): trace the frame as kRanges consecutive pixel ranges and copy each finished range on a
     // second stream while the next one is traced. (Not for the big kernel: every launch of it has its own drain tail.)
-    const bool ranged = host_out && !unfused && ctx->scene.n_entries <= kSmallSceneEntries && n_px >= kRangedMinPixels;
+    const bool ranged = host_out && !unfused && !frame_copy && ctx->scene.n_entries <= kSmallSceneEntries && n_px >= kRangedMinPixels;
     if (ranged) {
         for (int c = 0; c < kRanges; c++) {
             const size_t p0 = (n_px * c / kRanges) & ~static_cast<size_t>(3), p1 = c + 1 == kRanges ? n_px : (n_px * (c + 1) / kRanges) & ~static_cast<size_t>(3);
             a.pixel_begin = p0;
             a.pixel_end = p1;
             if (c > 0) {   // the pixel pool of this launch starts at p0 (range 0 starts at the template's 0)
-                ctx->h_counters[16 + c] = p0;
-                RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_counters, ctx->h_counters + 16 + c, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+                sl.h_counters[16 + c] = p0;
+                RTX_ENQ(cudaMemcpyAsync(sl.d_counters, sl.h_counters + 16 + c, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
             }
-            RTX_CUDA(ctx, launch_trace(a, ctx->n_sms, st, &launches));
-            RTX_CUDA(ctx, cudaEventRecord(ctx->ev_range[c], st));
+            RTX_ENQ(launch_trace(a, ctx->n_sms, st, &launches, &ctx->launch_state));
+            RTX_ENQ(cudaEventRecord(sl.ev_range[c], st));
         }
         // all launches are queued before the first copy: a copy into PAGEABLE host memory blocks this thread, and the
         // kernels behind it should already be running then
         for (int c = 0; c < kRanges; c++) {
             const size_t p0 = (n_px * c / kRanges) & ~static_cast<size_t>(3), p1 = c + 1 == kRanges ? n_px : (n_px * (c + 1) / kRanges) & ~static_cast<size_t>(3);
-            RTX_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_range[c], 0));
-            for (int k = 0; k < 6; k++)
+            RTX_ENQ(cudaStreamWaitEvent(cs, sl.ev_range[c], 0));
+            for (int k = 0; k < kPlanes; k++)
                 if (user[k])
-                    RTX_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(user[k]) + p0 * elem[k], static_cast<char*>(dev[k]) + p0 * elem[k],
-                                                  (p1 - p0) * elem[k], cudaMemcpyDeviceToHost, ctx->copy_stream));
+                    RTX_ENQ(cudaMemcpyAsync(static_cast<char*>(user[k]) + p0 * elem[k], static_cast<char*>(dev[k]) + p0 * elem[k],
+                                            (p1 - p0) * elem[k], cudaMemcpyDeviceToHost, cs));
         }
-        RTX_CUDA(ctx, cudaEventRecord(ctx->ev_range[kRanges], ctx->copy_stream));
     } else {
-        RTX_CUDA(ctx, launch_trace(a, ctx->n_sms, st, &launches));
+        RTX_ENQ(launch_trace(a, ctx->n_sms, st, &launches, &ctx->launch_state));
     }
-    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    RTX_ENQ(cudaEventRecord(sl.ev[2], st));
     if (unfused) {
-        RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 2, 0, 2 * sizeof(unsigned long long), st));
+        RTX_ENQ(cudaMemsetAsync(sl.d_counters + 2, 0, 2 * sizeof(unsigned long long), st));
         if (tonemap) {
-            int rc = grow(ctx, &ctx->d_tm_sums, &ctx->d_tm_sums_cap, sizeof(long long) * std::max(n_frames, 16));
-            if (rc != RTX_OK) return rc;
             const int64_t ppf = static_cast<int64_t>(local_rows) * W;
             long long* sums = static_cast<long long*>(ctx->d_tm_sums);
-            RTX_CUDA(ctx, cudaMemsetAsync(sums, 0, sizeof(long long) * n_frames, st));
-            RTX_CUDA(ctx, launch_tonemap_sums(nullptr, rad_for_quant, ppf, n_frames, sums, ctx->n_sms, st));
-            RTX_CUDA(ctx, launch_tonemap_apply(nullptr, rad_for_quant, ppf, n_frames, sums, ppf, p.tonemap_key, p.tonemap_white,
-                                               p.quantise_mode, static_cast<uint32_t*>(dev[0]), ctx->d_counters, ctx->n_sms, st));
+            RTX_ENQ(cudaMemsetAsync(sums, 0, sizeof(long long) * n_frames, st));
+            RTX_ENQ(launch_tonemap_sums(nullptr, rad_for_quant, ppf, n_frames, sums, ctx->n_sms, st));
+            RTX_ENQ(launch_tonemap_apply(nullptr, rad_for_quant, ppf, n_frames, sums, ppf, p.tonemap_key, p.tonemap_white,
+                                         p.quantise_mode, static_cast<uint32_t*>(dev[0]), sl.d_counters, ctx->n_sms, st));
             launches += 2;
         } else {
-            RTX_CUDA(ctx, launch_quantise_f64(rad_for_quant, static_cast<int64_t>(n_px), p.quantise_mode,
-                                              static_cast<uint32_t*>(dev[0]), ctx->d_counters, ctx->n_sms, st));
+            RTX_ENQ(launch_quantise_f64(rad_for_quant, static_cast<int64_t>(n_px), p.quantise_mode,
+                                        static_cast<uint32_t*>(dev[0]), sl.d_counters, ctx->n_sms, st));
             launches++;
         }
     }
-    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-    if (ranged) {
-        RTX_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_range[kRanges], 0));     // the last range's copies
-    } else if (host_out) {
-        for (int k = 0; k < 6; k++)
-            if (user[k]) RTX_CUDA(ctx, cudaMemcpyAsync(user[k], dev[k], n_px * elem[k], cudaMemcpyDeviceToHost, st));
-    }
-    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    RTX_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-    RTX_CUDA(ctx, cudaStreamSynchronize(st));
-    RTX_CUDA(ctx, cudaGetLastError());
-
-    if (stats) {
-        std::memset(stats, 0, sizeof *stats);
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); stats->h2d_ms = ms;
-        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); stats->raytracing_ms = ms;
-        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); stats->surface_update_ms = ms;
-        cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); stats->d2h_ms = ms;
-        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); stats->total_ms = ms;
-        stats->total_rays = ctx->h_counters[1];
-        stats->sphere_tests = stats->total_rays * static_cast<uint64_t>(ctx->scene.n_spheres);
-        stats->wall_tests = stats->total_rays * static_cast<uint64_t>(ctx->scene.n_walls);
-        stats->over_range_pixels = ctx->h_counters[2];
-        long long bits = static_cast<long long>(ctx->h_counters[3]);
-        std::memcpy(&stats->max_luminance, &bits, sizeof bits);
-        stats->launches = launches;
-        const unsigned long long t0 = ctx->h_counters[4], dry = ctx->h_counters[5], first = ctx->h_counters[6], last = ctx->h_counters[7];
-        if (t0 != ~0ull && last >= t0) {
-            stats->drain_ms = (dry != ~0ull && last >= dry) ? (last - dry) * 1e-6 : 0.0;
-            stats->exit_spread_ms = (first != ~0ull && last >= first) ? (last - first) * 1e-6 : 0.0;
+    RTX_ENQ(cudaEventRecord(sl.ev[3], st));
+    // Read-back. Host outputs leave on the copy stream, so that the NEXT call's kernels (other slot, other staging
+    // buffers) run while this frame crosses PCIe; everything else stays on the one stream.
+    sl.copies_on_side_stream = host_out || frame_copy;
+    if (frame_copy) {
+        // RTX_FRAME_COPY: whole bands / whole frames leave the staging buffer for their place in the frame set (pinned
+        // host memory, this GPU's or a peer's HBM) as copy-engine transfers on the copy stream — 2-D copies whose rows are
+        // the cyclic bands. The next call's kernel (other slot) overlaps them.
+        RTX_ENQ(cudaStreamWaitEvent(cs, sl.ev[3], 0));
+        const size_t row_bytes = static_cast<size_t>(W) * 4;
+        const char* src = static_cast<const char*>(sl.d_out[0]);
+        for (int f = 0; f < n_frames; f++) {
+            char* dst = reinterpret_cast<char*>(outs->frame_rgba8) +
+                        (static_cast<size_t>(p.frame_offset) + static_cast<size_t>(f) * p.frame_stride) * Hh * row_bytes;
+            const char* fsrc = src + static_cast<size_t>(f) * local_rows * row_bytes;
+            if (p.n_ranks == 1) {
+                RTX_ENQ(cudaMemcpyAsync(dst, fsrc, static_cast<size_t>(Hh) * row_bytes, cudaMemcpyDefault, cs));
+            } else {
+                const int full_bands = local_rows / band_rows;                       // this rank's complete bands
+                const size_t band_bytes = static_cast<size_t>(band_rows) * row_bytes;
+                char* first = dst + static_cast<size_t>(p.rank) * band_bytes;        // global band `rank`
+                if (full_bands)
+                    RTX_ENQ(cudaMemcpy2DAsync(first, band_bytes * p.n_ranks, fsrc, band_bytes, band_bytes, full_bands, cudaMemcpyDefault, cs));
+                const int tail_rows = local_rows - full_bands * band_rows;           // ragged last band
+                if (tail_rows)
+                    RTX_ENQ(cudaMemcpyAsync(first + static_cast<size_t>(full_bands) * band_bytes * p.n_ranks, fsrc + static_cast<size_t>(full_bands) * band_bytes,
+                                            static_cast<size_t>(tail_rows) * row_bytes, cudaMemcpyDefault, cs));
+            }
         }
     }
+    if (host_out || frame_copy) {
+        if (!host_out) {
+            // planes besides the frame stay where the caller put them (device / mapped): nothing more to copy
+        } else if (!ranged) {
+            RTX_ENQ(cudaStreamWaitEvent(cs, sl.ev[3], 0));
+            for (int k = 0; k < kPlanes; k++)
+                if (user[k]) RTX_ENQ(cudaMemcpyAsync(user[k], dev[k], n_px * elem[k], cudaMemcpyDeviceToHost, cs));
+        }
+        RTX_ENQ(cudaStreamWaitEvent(cs, sl.ev[3], 0));
+        RTX_ENQ(cudaMemcpyAsync(sl.h_counters, sl.d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs));
+        RTX_ENQ(cudaEventRecord(sl.ev[4], cs));
+        RTX_ENQ(cudaEventRecord(sl.ev_done, cs));
+    } else {
+        RTX_ENQ(cudaMemcpyAsync(sl.h_counters, sl.d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        RTX_ENQ(cudaEventRecord(sl.ev[4], st));
+        RTX_ENQ(cudaEventRecord(sl.ev_done, st));
+    }
+#undef RTX_ENQ
+    sl.pending = true;
+    sl.launches = launches;
+    sl.n_spheres = ctx->scene.n_spheres;
+    sl.n_walls = ctx->scene.n_walls;
+    ctx->next_slot = (ctx->next_slot + 1) % kSlots;
     ctx->error.clear();
+    if (async) return RTX_OK;
+    // synchronous call: every earlier asynchronous call completes first, in order (their stats are dropped)
+    for (;;) {
+        Slot& o = ctx->slot[ctx->oldest];
+        const bool mine = &o == &sl;
+        ctx->oldest = (ctx->oldest + 1) % kSlots;
+        int rc = finish_slot(ctx, o, mine ? stats : nullptr);
+        if (rc != RTX_OK) return rc;
+        if (mine) break;
+    }
     return RTX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rtx_render(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx_params* params, const rtx_outputs* outs,
+               rtx_stats* stats)
+{
+    if (ctx && !cams) return fail(ctx, RTX_ERR_INVALID, "rtx_render: null argument or n_frames <= 0");
+    return render_impl(ctx, cams, n_frames, nullptr, 0, params, outs, stats, false, "rtx_render");
+}
+
+int rtx_render_async(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rtx_params* params, const rtx_outputs* outs)
+{
+    if (ctx && !cams) return fail(ctx, RTX_ERR_INVALID, "rtx_render_async: null argument or n_frames <= 0");
+    return render_impl(ctx, cams, n_frames, nullptr, 0, params, outs, nullptr, true, "rtx_render_async");
+}
+
+int rtx_wait(rtx_ctx* ctx, rtx_stats* stats)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    Slot& o = ctx->slot[ctx->oldest];
+    if (!o.pending) return fail(ctx, RTX_ERR_INVALID, "rtx_wait: no call in flight");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->oldest = (ctx->oldest + 1) % kSlots;
+    int rc = finish_slot(ctx, o, stats);
+    if (rc == RTX_OK) ctx->error.clear();
+    return rc;
+}
+
+int rtx_trace_rays(rtx_ctx* ctx, const rtx_ray* rays, int64_t n_rays, const rtx_params* params, const rtx_outputs* outs, rtx_stats* stats)
+{
+    if (ctx && !rays) return fail(ctx, RTX_ERR_INVALID, "rtx_trace_rays: null rays");
+    return render_impl(ctx, nullptr, 0, rays, n_rays, params, outs, stats, false, "rtx_trace_rays");
 }
 
 int rtx_quantise(rtx_ctx* ctx, const float* rad32, const double* rad64, int64_t n_pixels, int32_t mode, uint32_t* rgba8,
@@ -651,22 +908,22 @@ int rtx_quantise(rtx_ctx* ctx, const float* rad32, const double* rad64, int64_t 
         int rc = grow(ctx, &pp, &ctx->d_rad_scratch_cap, std::max<size_t>(in_bytes, 16));
         ctx->d_rad_scratch = static_cast<double*>(pp);
         if (rc != RTX_OK) return rc;
-        rc = grow(ctx, &ctx->d_out[0], &ctx->d_out_cap[0], std::max<size_t>(static_cast<size_t>(n_pixels) * 4, 16));
+        rc = grow(ctx, &ctx->d_aux_out, &ctx->d_aux_out_cap, std::max<size_t>(static_cast<size_t>(n_pixels) * 4, 16));
         if (rc != RTX_OK) return rc;
         RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rad_scratch, d_in, in_bytes, cudaMemcpyHostToDevice, st));
         d_in = ctx->d_rad_scratch;
-        d_o = static_cast<uint32_t*>(ctx->d_out[0]);
+        d_o = static_cast<uint32_t*>(ctx->d_aux_out);
     }
-    RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_aux_counters, 0, 8 * sizeof(unsigned long long), st));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     if (rad32)
-        RTX_CUDA(ctx, launch_quantise_f32(static_cast<const float*>(d_in), n_pixels, mode, d_o, ctx->d_counters, ctx->n_sms, st));
+        RTX_CUDA(ctx, launch_quantise_f32(static_cast<const float*>(d_in), n_pixels, mode, d_o, ctx->d_aux_counters, ctx->n_sms, st));
     else
-        RTX_CUDA(ctx, launch_quantise_f64(static_cast<const double*>(d_in), n_pixels, mode, d_o, ctx->d_counters, ctx->n_sms, st));
+        RTX_CUDA(ctx, launch_quantise_f64(static_cast<const double*>(d_in), n_pixels, mode, d_o, ctx->d_aux_counters, ctx->n_sms, st));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     if (memory == RTX_MEM_HOST)
         RTX_CUDA(ctx, cudaMemcpyAsync(rgba8, d_o, static_cast<size_t>(n_pixels) * 4, cudaMemcpyDeviceToHost, st));
-    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->h_aux_counters, ctx->d_aux_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     RTX_CUDA(ctx, cudaStreamSynchronize(st));
     if (stats) {
@@ -676,8 +933,8 @@ int rtx_quantise(rtx_ctx* ctx, const float* rad32, const double* rad64, int64_t 
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); stats->surface_update_ms = ms;
         cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); stats->d2h_ms = ms;
         cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); stats->total_ms = ms;
-        stats->over_range_pixels = ctx->h_counters[2];
-        long long bits = static_cast<long long>(ctx->h_counters[3]);
+        stats->over_range_pixels = ctx->h_aux_counters[2];
+        long long bits = static_cast<long long>(ctx->h_aux_counters[3]);
         std::memcpy(&stats->max_luminance, &bits, sizeof bits);
         stats->launches = 1;
     }
@@ -710,13 +967,13 @@ int rtx_tonemap(rtx_ctx* ctx, const float* rad32, const double* rad64, int64_t p
         rc = grow(ctx, &pp, &ctx->d_rad_scratch_cap, std::max<size_t>(in_bytes, 16));
         ctx->d_rad_scratch = static_cast<double*>(pp);
         if (rc != RTX_OK) return rc;
-        rc = grow(ctx, &ctx->d_out[0], &ctx->d_out_cap[0], std::max<size_t>(n_px * 4, 16));
+        rc = grow(ctx, &ctx->d_aux_out, &ctx->d_aux_out_cap, std::max<size_t>(n_px * 4, 16));
         if (rc != RTX_OK) return rc;
         RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rad_scratch, d_in, in_bytes, cudaMemcpyHostToDevice, st));
         d_in = ctx->d_rad_scratch;
-        d_o = static_cast<uint32_t*>(ctx->d_out[0]);
+        d_o = static_cast<uint32_t*>(ctx->d_aux_out);
     }
-    RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_aux_counters, 0, 8 * sizeof(unsigned long long), st));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     long long* sums = static_cast<long long*>(ctx->d_tm_sums);
     const float* in32 = rad32 ? static_cast<const float*>(d_in) : nullptr;
@@ -724,12 +981,12 @@ int rtx_tonemap(rtx_ctx* ctx, const float* rad32, const double* rad64, int64_t p
     RTX_CUDA(ctx, cudaMemsetAsync(sums, 0, sizeof(long long) * n_frames, st));
     RTX_CUDA(ctx, launch_tonemap_sums(in32, in64, pixels_per_frame, n_frames, sums, ctx->n_sms, st));
     RTX_CUDA(ctx, launch_tonemap_apply(in32, in64, pixels_per_frame, n_frames, sums, pixels_per_frame, p.tonemap_key, p.tonemap_white,
-                                       p.quantise_mode, d_o, ctx->d_counters, ctx->n_sms, st));
+                                       p.quantise_mode, d_o, ctx->d_aux_counters, ctx->n_sms, st));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     if (memory == RTX_MEM_HOST) RTX_CUDA(ctx, cudaMemcpyAsync(rgba8, d_o, n_px * 4, cudaMemcpyDeviceToHost, st));
     ctx->h_tm_sums.resize(n_frames);
     RTX_CUDA(ctx, cudaMemcpyAsync(ctx->h_tm_sums.data(), sums, sizeof(long long) * n_frames, cudaMemcpyDeviceToHost, st));
-    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->h_aux_counters, ctx->d_aux_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     RTX_CUDA(ctx, cudaStreamSynchronize(st));
     if (log_avg_luminance)   // same expression as the kernel and the oracle: exp((sum / 2^32) / n)
@@ -742,8 +999,8 @@ int rtx_tonemap(rtx_ctx* ctx, const float* rad32, const double* rad64, int64_t p
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); stats->surface_update_ms = ms;
         cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); stats->d2h_ms = ms;
         cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); stats->total_ms = ms;
-        stats->over_range_pixels = ctx->h_counters[2];
-        long long bits = static_cast<long long>(ctx->h_counters[3]);
+        stats->over_range_pixels = ctx->h_aux_counters[2];
+        long long bits = static_cast<long long>(ctx->h_aux_counters[3]);
         std::memcpy(&stats->max_luminance, &bits, sizeof bits);
         stats->launches = 2;
     }
@@ -777,20 +1034,20 @@ int rtx_tonemap_apply(rtx_ctx* ctx, const float* rad32, const double* rad64, int
     if (p.quantise_mode != RTX_QUANT_WRAP && p.quantise_mode != RTX_QUANT_SATURATE) return fail(ctx, RTX_ERR_INVALID, "rtx_tonemap_apply: unknown quantise_mode");
     RTX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    RTX_CUDA(ctx, cudaMemsetAsync(ctx->d_aux_counters, 0, 8 * sizeof(unsigned long long), st));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     RTX_CUDA(ctx, launch_tonemap_apply(rad32, rad64, pixels_per_frame, n_frames, reinterpret_cast<const long long*>(sums), pixels_per_frame_global,
-                                       p.tonemap_key, p.tonemap_white, p.quantise_mode, rgba8, ctx->d_counters, ctx->n_sms, st));
+                                       p.tonemap_key, p.tonemap_white, p.quantise_mode, rgba8, ctx->d_aux_counters, ctx->n_sms, st));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->h_aux_counters, ctx->d_aux_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     RTX_CUDA(ctx, cudaStreamSynchronize(st));
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
         stats->surface_update_ms = stats->total_ms = ms;
-        stats->over_range_pixels = ctx->h_counters[2];
-        long long bits = static_cast<long long>(ctx->h_counters[3]);
+        stats->over_range_pixels = ctx->h_aux_counters[2];
+        long long bits = static_cast<long long>(ctx->h_aux_counters[3]);
         std::memcpy(&stats->max_luminance, &bits, sizeof bits);
         stats->launches = 1;
     }
@@ -808,7 +1065,7 @@ int rtx_unpermute_bands(rtx_ctx* ctx, const void* band_major, void* row_major, i
         if (rtx_local_rows(height, band_rows, n_ranks, r) > rows_per_rank)
             return fail(ctx, RTX_ERR_INVALID, "rtx_unpermute_bands: rows_per_rank smaller than a rank's row count");
     RTX_CUDA(ctx, cudaSetDevice(ctx->device));
-    RTX_CUDA(ctx, launch_unpermute(band_major, row_major, height, width, elem_bytes, band_rows, n_ranks, rows_per_rank, ctx->stream));
+    RTX_CUDA(ctx, launch_unpermute(band_major, row_major, height, width, elem_bytes, band_rows, n_ranks, rows_per_rank, ctx->n_sms, ctx->stream));
     RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->error.clear();
     return RTX_OK;
@@ -858,6 +1115,88 @@ int rtx_buffer_release(rtx_ctx* ctx, void* imported_ptr)
     RTX_CUDA(ctx, cudaSetDevice(ctx->device));
     RTX_CUDA(ctx, cudaIpcCloseMemHandle(imported_ptr));
     return RTX_OK;
+}
+
+int rtx_host_alloc(rtx_ctx* ctx, uint64_t bytes, void** host_ptr)
+{
+    if (!ctx || !host_ptr || bytes == 0) return fail(ctx, RTX_ERR_INVALID, "rtx_host_alloc: bad argument");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaHostAlloc(host_ptr, bytes, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) return fail(ctx, RTX_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    return RTX_OK;
+}
+
+int rtx_host_free(rtx_ctx* ctx, void* host_ptr)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    RTX_CUDA(ctx, cudaFreeHost(host_ptr));
+    return RTX_OK;
+}
+
+int rtx_host_register(rtx_ctx* ctx, void* host_ptr, uint64_t bytes)
+{
+    if (!ctx || !host_ptr || bytes == 0) return fail(ctx, RTX_ERR_INVALID, "rtx_host_register: bad argument");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    RTX_CUDA(ctx, cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return RTX_OK;
+}
+
+int rtx_host_unregister(rtx_ctx* ctx, void* host_ptr)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    RTX_CUDA(ctx, cudaHostUnregister(host_ptr));
+    return RTX_OK;
+}
+
+int rtx_host_device_pointer(rtx_ctx* ctx, void* host_ptr, void** device_ptr)
+{
+    if (!ctx || !host_ptr || !device_ptr) return fail(ctx, RTX_ERR_INVALID, "rtx_host_device_pointer: bad argument");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    RTX_CUDA(ctx, cudaHostGetDevicePointer(device_ptr, host_ptr, 0));
+    return RTX_OK;
+}
+
+int rtx_host_shared_open(rtx_ctx* ctx, const char* name, uint64_t bytes, int32_t create, void** host_ptr)
+{
+    if (!ctx || !name || name[0] != '/' || bytes == 0 || !host_ptr) return fail(ctx, RTX_ERR_INVALID, "rtx_host_shared_open: bad argument (name must start with '/')");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int fd = shm_open(name, create ? (O_CREAT | O_RDWR) : O_RDWR, 0600);
+    if (fd < 0) return fail(ctx, RTX_ERR_INVALID, std::string("rtx_host_shared_open: shm_open(") + name + "): " + std::strerror(errno));
+    if (create && ftruncate(fd, static_cast<off_t>(bytes)) != 0) {
+        const std::string msg = std::string("rtx_host_shared_open: ftruncate: ") + std::strerror(errno);
+        close(fd);
+        return fail(ctx, RTX_ERR_NOMEM, msg);
+    }
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_POPULATE, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return fail(ctx, RTX_ERR_NOMEM, std::string("rtx_host_shared_open: mmap: ") + std::strerror(errno));
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) {
+        munmap(p, bytes);
+        return cuda_fail(ctx, e, "cudaHostRegister(shared host frame)");
+    }
+    ctx->shared_host.emplace_back(p, static_cast<size_t>(bytes));
+    *host_ptr = p;
+    return RTX_OK;
+}
+
+int rtx_host_shared_close(rtx_ctx* ctx, void* host_ptr, const char* unlink_name)
+{
+    if (!ctx || !host_ptr) return fail(ctx, RTX_ERR_INVALID, "rtx_host_shared_close: bad argument");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (size_t k = 0; k < ctx->shared_host.size(); k++) {
+        if (ctx->shared_host[k].first != host_ptr) continue;
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaHostUnregister(host_ptr);
+        munmap(host_ptr, ctx->shared_host[k].second);
+        ctx->shared_host.erase(ctx->shared_host.begin() + k);
+        if (unlink_name) shm_unlink(unlink_name);
+        return RTX_OK;
+    }
+    return fail(ctx, RTX_ERR_INVALID, "rtx_host_shared_close: not a mapping of this context");
 }
 
 int rtx_ffma_peak(rtx_ctx* ctx, int32_t variant, double* tflops, double* mhz)

@@ -98,6 +98,22 @@ __global__ void __launch_bounds__(256) quantise_f64_kernel(const double* __restr
     stats_commit(st, counters);
 }
 
+// Any 4- / 8-byte aligned pointers (tensor slices, odd frame offsets): one pixel per thread, scalar loads and stores.
+template <typename T>
+__global__ void __launch_bounds__(256) quantise_scalar_kernel(const T* __restrict__ rad, long long n_pixels, int mode,
+                                                              uint32_t* __restrict__ out, unsigned long long* counters)
+{
+    FrameStats st{0ull, 0.0};
+    for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < n_pixels;
+         p += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const double r = rad[3 * p], g = rad[3 * p + 1], b = rad[3 * p + 2];
+        out[p] = quantise_pixel(st, r, g, b, mode);
+    }
+    stats_commit(st, counters);
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 static int stream_grid(long long work_items, int threads, int n_sms)
 {
     long long blocks = (work_items + threads - 1) / threads;
@@ -111,6 +127,9 @@ cudaError_t launch_quantise_f64(const double* rad, int64_t n_pixels, int mode, u
                                 unsigned long long* counters, int n_sms, cudaStream_t stream)
 {
     if (n_pixels <= 0) return cudaSuccess;
+    if (!aligned16(rad) || !aligned16(rgba8))
+        quantise_scalar_kernel<double><<<stream_grid(n_pixels, 256, n_sms), 256, 0, stream>>>(rad, n_pixels, mode, rgba8, counters);
+    else
     quantise_f64_kernel<<<stream_grid((n_pixels + 3) / 4, 256, n_sms), 256, 0, stream>>>(rad, n_pixels, mode, rgba8, counters);
     return cudaGetLastError();
 }
@@ -119,6 +138,9 @@ cudaError_t launch_quantise_f32(const float* rad, int64_t n_pixels, int mode, ui
                                 unsigned long long* counters, int n_sms, cudaStream_t stream)
 {
     if (n_pixels <= 0) return cudaSuccess;
+    if (!aligned16(rad) || !aligned16(rgba8))
+        quantise_scalar_kernel<float><<<stream_grid(n_pixels, 256, n_sms), 256, 0, stream>>>(rad, n_pixels, mode, rgba8, counters);
+    else
     quantise_f32_kernel<<<stream_grid((n_pixels + 3) / 4, 256, n_sms), 256, 0, stream>>>(rad, n_pixels, mode, rgba8, counters);
     return cudaGetLastError();
 }
@@ -143,7 +165,7 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const T* __restrict__ sr
 }
 
 cudaError_t launch_unpermute(const void* band_major, void* row_major, int height, int width, int elem_bytes,
-                             int band_rows, int n_ranks, int rows_per_rank, cudaStream_t stream)
+                             int band_rows, int n_ranks, int rows_per_rank, int n_sms, cudaStream_t stream)
 {
     const long long row_bytes = static_cast<long long>(width) * elem_bytes;
     const bool vec16 = (row_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(band_major) % 16 == 0) &&
@@ -151,17 +173,17 @@ cudaError_t launch_unpermute(const void* band_major, void* row_major, int height
     if (vec16) {
         const int row_elems = static_cast<int>(row_bytes / 16);
         const long long total = static_cast<long long>(height) * row_elems;
-        unpermute_kernel<uint4><<<stream_grid(total, 256, 148), 256, 0, stream>>>(
+        unpermute_kernel<uint4><<<stream_grid(total, 256, n_sms), 256, 0, stream>>>(
             static_cast<const uint4*>(band_major), static_cast<uint4*>(row_major), height, row_elems, band_rows, n_ranks,
             rows_per_rank);
     } else if (elem_bytes == 4) {
         const long long total = static_cast<long long>(height) * width;
-        unpermute_kernel<uint32_t><<<stream_grid(total, 256, 148), 256, 0, stream>>>(
+        unpermute_kernel<uint32_t><<<stream_grid(total, 256, n_sms), 256, 0, stream>>>(
             static_cast<const uint32_t*>(band_major), static_cast<uint32_t*>(row_major), height, width, band_rows, n_ranks,
             rows_per_rank);
     } else {
         const long long total = static_cast<long long>(height) * width;
-        unpermute_kernel<uint8_t><<<stream_grid(total, 256, 148), 256, 0, stream>>>(
+        unpermute_kernel<uint8_t><<<stream_grid(total, 256, n_sms), 256, 0, stream>>>(
             static_cast<const uint8_t*>(band_major), static_cast<uint8_t*>(row_major), height, width, band_rows, n_ranks,
             rows_per_rank);
     }

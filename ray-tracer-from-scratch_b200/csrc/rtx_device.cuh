@@ -91,6 +91,7 @@ struct SceneDev {
 struct TraceArgs {
     SceneDev scene;
     const rtx_camera* cameras;         // [n_frames] device copy
+    const rtx_ray* rays;               // rtx_trace_rays: ray p replaces pixel p's primary ray (n_frames = local_rows = 1, width = n_rays)
     int32_t n_frames, width, height;   // global frame size
     int32_t local_rows;                // rows this rank renders per frame
     int32_t band_rows, n_ranks, rank;
@@ -108,7 +109,9 @@ struct TraceArgs {
     int32_t* object_id;
     uint8_t* hit_mask;
     uint8_t* ray_count;
-    uint32_t* frame_rgba8;             // whole row-major frame set, possibly peer memory (fused gather); may be null
+    uint32_t* frame_rgba8;             // whole row-major frame set, possibly peer or mapped host memory (fused gather); may be null
+    double* hit_distance;              // primary ray: Collision.distance (DBL_MAX on a miss, main.cpp:70)
+    double* hit_normal;                // primary ray: Collision.normal as returned, (0,0,0) on a miss
     int32_t frame_offset, frame_stride;
     // Pixel range of this launch in the packed pixel space [n_frames][local_rows][width]; pixel_end = 0 means all.
     // rtx_render launches a small scene as a few consecutive ranges so that the read-back of one range overlaps the
@@ -170,8 +173,15 @@ __device__ __forceinline__ bool over_range(double r, double g, double b)
 
 constexpr int kSmallSceneEntries = 16;   // scenes of at most this many screen entries run trace_small_kernel
 
+// Per-context (= per-device) launch state of the trace kernels: cudaFuncAttributeMaxDynamicSharedMemorySize is a
+// per-device attribute, so what has been raised is remembered per context, not per thread or per process.
+struct TraceLaunchState {
+    size_t smem_set[2] = {0, 0};       // largest dynamic shared-memory size requested so far: resident / streamed kernel
+    int small_per_sm = 0;              // resident CTAs per SM of trace_small_kernel (occupancy query, once)
+};
+
 // Launch wrappers implemented in the .cu files, called by api.cu.
-cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, int* launches);
+cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, int* launches, TraceLaunchState* state);
 cudaError_t launch_quantise_f64(const double* rad, int64_t n_pixels, int mode, uint32_t* rgba8,
                                 unsigned long long* counters, int n_sms, cudaStream_t stream);
 cudaError_t launch_quantise_f32(const float* rad, int64_t n_pixels, int mode, uint32_t* rgba8,
@@ -182,7 +192,7 @@ cudaError_t launch_tonemap_apply(const float* rad32, const double* rad64, int64_
                                  int64_t pixels_global, double key, double white, int mode, uint32_t* rgba8, unsigned long long* counters,
                                  int n_sms, cudaStream_t stream);
 cudaError_t launch_unpermute(const void* band_major, void* row_major, int height, int width, int elem_bytes,
-                             int band_rows, int n_ranks, int rows_per_rank, cudaStream_t stream);
+                             int band_rows, int n_ranks, int rows_per_rank, int n_sms, cudaStream_t stream);
 cudaError_t run_ffma_peak(int variant, int n_sms, cudaStream_t stream, double* tflops, double* mhz);
 
 }  // namespace rtx

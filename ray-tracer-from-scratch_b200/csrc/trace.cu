@@ -406,6 +406,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
+#ifdef RTX_TAIL_TRACE
+// Developer build only (tools/tail_trace.py): what every warp does once the pixel pool is dry — per scan segment the
+// start time, the live chains, the mode, and the times after the scan and after drain + shading.
+constexpr int kTailRecords = 32;
+__device__ unsigned long long g_tail_log[160 * 32 * kTailRecords * 4];
+__device__ unsigned long long g_tail_dry;
+#endif
+
 struct FrameTotals {
     unsigned long long rays, over;
     double maxlum;
@@ -418,9 +426,18 @@ __device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, const S
     using namespace ex;
     c.rays++;
     const int best_id = c.best_key >> 3;          // object id (-1 stays -1); the low bits are the box face
-    if (c.rays == 1) c.first_id = best_id;
+    const bool primary = c.rays == 1;
+    if (primary) {
+        c.first_id = best_id;
+        if (a.hit_distance) a.hit_distance[c.pixel] = c.best_dist;        // DBL_MAX when nothing was hit (main.cpp:70)
+    }
     bool done;
     if (best_id < 0) {
+        if (primary && a.hit_normal) {
+            a.hit_normal[3 * c.pixel + 0] = 0.0;
+            a.hit_normal[3 * c.pixel + 1] = 0.0;
+            a.hit_normal[3 * c.pixel + 2] = 0.0;
+        }
         // out_color, main.cpp:28-37 (sign test on the unnormalised z)
         d3 col;
         if (c.d.z < 0.0) {
@@ -442,6 +459,11 @@ __device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, const S
             sphere_exact(c.o, c.d, c.a_dd, c.dlen, sc.sph64[slot], &normal);
         } else {
             normal = sc.walls[slot + (c.best_key & 7)].n;      // a wall, or the face of a box that was hit
+        }
+        if (primary && a.hit_normal) {
+            a.hit_normal[3 * c.pixel + 0] = normal.x;
+            a.hit_normal[3 * c.pixel + 1] = normal.y;
+            a.hit_normal[3 * c.pixel + 2] = normal.z;
         }
         const MaterialDev m = sc.mats[best_id];
         const d3 pos = add(c.o, scale(c.d, c.best_dist));                  // main.cpp:99
@@ -531,21 +553,27 @@ __device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, const S
 __device__ __forceinline__ void start_pixel_body(Chain& c, unsigned long long p, const TraceArgs& a)
 {
     using namespace ex;
-    const unsigned long long frame_pixels = static_cast<unsigned long long>(a.local_rows) * a.width;
-    const int frame = static_cast<int>(p / frame_pixels);
-    const unsigned rem = static_cast<unsigned>(p - frame * frame_pixels);
-    const int lrow = rem / a.width;
-    const int col = rem - lrow * a.width;
-    int grow = lrow;
-    if (a.n_ranks > 1) {
-        const int lb = lrow / a.band_rows;
-        grow = (lb * a.n_ranks + a.rank) * a.band_rows + (lrow - lb * a.band_rows);
+    if (a.rays) {
+        // rtx_trace_rays: the caller's ray, as recursive_ray_tracing(scene, ray, depth) receives it (main.cpp:89)
+        c.o = mk(a.rays[p].origin);
+        c.d = mk(a.rays[p].direction);
+    } else {
+        const unsigned long long frame_pixels = static_cast<unsigned long long>(a.local_rows) * a.width;
+        const int frame = static_cast<int>(p / frame_pixels);
+        const unsigned rem = static_cast<unsigned>(p - frame * frame_pixels);
+        const int lrow = rem / a.width;
+        const int col = rem - lrow * a.width;
+        int grow = lrow;
+        if (a.n_ranks > 1) {
+            const int lb = lrow / a.band_rows;
+            grow = (lb * a.n_ranks + a.rank) * a.band_rows + (lrow - lb * a.band_rows);
+        }
+        const rtx_camera& cam = a.cameras[frame];
+        const d3 centre = add(add(mk(cam.image_top_left), scale(mk(cam.delta_x), static_cast<double>(col))),
+                              scale(mk(cam.delta_y), static_cast<double>(grow)));   // main.cpp:132
+        c.o = mk(cam.position);
+        c.d = sub(mk(cam.position), centre);                                           // main.cpp:133
     }
-    const rtx_camera& cam = a.cameras[frame];
-    const d3 centre = add(add(mk(cam.image_top_left), scale(mk(cam.delta_x), static_cast<double>(col))),
-                          scale(mk(cam.delta_y), static_cast<double>(grow)));   // main.cpp:132
-    c.o = mk(cam.position);
-    c.d = sub(mk(cam.position), centre);                                           // main.cpp:133
     c.acc = d3{0.0, 0.0, 0.0};
     c.weight = 1.0;
     c.pixel = p;
@@ -679,6 +707,10 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
     Mailbox* const mbox = reinterpret_cast<Mailbox*>(s_tile + 2 * plane_pairs) + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicMin(&a.counters[4], globaltimer_ns());   // kernel start
 
+#ifdef RTX_TAIL_TRACE
+    int tail_n = 0;
+    unsigned long long* const tail_log = g_tail_log + (static_cast<size_t>(blockIdx.x) * 32 + (threadIdx.x >> 5)) * kTailRecords * 4;
+#endif
     for (;;) {
         __syncwarp();
         // ---- refill idle chains with fresh pixels ------------------------------------------------------------------
@@ -691,8 +723,12 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
             base = __shfl_sync(kFull, base, 0);
             const unsigned below = (1u << lane_id) - 1u;
             if (base + n0 + n1 > total_pixels) pool_dry = true;
-            if (lane_id == 0 && base + n0 + n1 > total_pixels && base <= total_pixels)   // this fetch emptied the pool
+            if (lane_id == 0 && base + n0 + n1 > total_pixels && base <= total_pixels) {  // this fetch emptied the pool
                 atomicMin(&a.counters[5], globaltimer_ns());
+#ifdef RTX_TAIL_TRACE
+                g_tail_dry = globaltimer_ns();
+#endif
+            }
             if (!ch[0].active) {
                 const unsigned long long p = base + __popc(idle0 & below);
                 if (p < total_pixels) start_pixel(ch[0], p, a);
@@ -709,6 +745,11 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
             if (__ballot_sync(kFull, any_active) == 0u) break;
         }
 
+#ifdef RTX_TAIL_TRACE
+        const unsigned long long tt0 = globaltimer_ns();
+        const int tt_live = __popc(__ballot_sync(kFull, ch[0].active)) + __popc(__ballot_sync(kFull, ch[1].active));
+        int tt_coop = 0;
+#endif
         // ---- nearest hit (find_closest_hit, main.cpp:67-84): FP32 screen of every entry, exact test of survivors ----
         const Packed k0 = setup_chain(ch[0], a.origin_bound);
         const Packed k1 = setup_chain(ch[1], a.origin_bound);
@@ -765,14 +806,31 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
                     coop = false;
                 }
             }
+#ifdef RTX_TAIL_TRACE
+            tt_coop = coop ? 1 : 0;
+#endif
             if (!coop) scan_tile(tile_addr, plane_bytes, total_pairs, 0, k0, k1, ch[0], ch[1], sc, a.filter_eps);
         }
+#ifdef RTX_TAIL_TRACE
+        __syncwarp();
+        const unsigned long long tt1 = globaltimer_ns();
+#endif
         drain_queue(ch[0], sc, a.filter_eps);
         drain_queue(ch[1], sc, a.filter_eps);
 
         // ---- shading, bounce or pixel write --------------------------------------------------------------------------------
         if (ch[0].active) shade_chain(ch[0], a, tot);
         if (ch[1].active) shade_chain(ch[1], a, tot);
+#ifdef RTX_TAIL_TRACE
+        __syncwarp();
+        if (pool_dry && lane_id == 0 && tail_n < kTailRecords) {
+            tail_log[4 * tail_n + 0] = tt0;
+            tail_log[4 * tail_n + 1] = static_cast<unsigned long long>(tt_live) | (static_cast<unsigned long long>(tt_coop) << 8);
+            tail_log[4 * tail_n + 2] = tt1;
+            tail_log[4 * tail_n + 3] = globaltimer_ns();
+            tail_n++;
+        }
+#endif
     }
 
     // ---- diagnostics: warp-shuffle reduction, one atomic per warp (never alters a pixel) ----------------------
@@ -796,7 +854,23 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
     }
 }
 
-cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, int* launches)
+#ifdef RTX_TAIL_TRACE
+extern "C" int rtx_debug_tail_log(unsigned long long* host_dst, unsigned long long* dry)
+{
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(host_dst, g_tail_log, sizeof(unsigned long long) * 160 * 32 * kTailRecords * 4) != cudaSuccess) return 1;
+    if (cudaMemcpyFromSymbol(dry, g_tail_dry, sizeof(unsigned long long)) != cudaSuccess) return 1;
+    return 0;
+}
+extern "C" int rtx_debug_tail_clear(void)
+{
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_tail_log) != cudaSuccess) return 1;
+    return cudaMemset(p, 0, sizeof(unsigned long long) * 160 * 32 * kTailRecords * 4) != cudaSuccess;
+}
+#endif
+
+cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, int* launches, TraceLaunchState* state)
 {
     constexpr int iter_bytes = kPairsPerIter * 32;
     const size_t mbox_bytes = sizeof(Mailbox) * kWarps;
@@ -810,7 +884,7 @@ cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, 
     if (total == 0) return cudaSuccess;
     if (args.scene.n_entries <= kSmallScene) {
         if (args.pixel_end) total = args.pixel_end - args.pixel_begin;      // a range of the frame (see TraceArgs)
-        static int per_sm = 0;
+        int& per_sm = state->small_per_sm;
         if (per_sm == 0) {
             cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_small_kernel, kSmallThreads, 0);
             if (e != cudaSuccess) return e;
@@ -825,7 +899,7 @@ cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, 
     unsigned long long blocks = (total + kThreads * kChains - 1) / (kThreads * kChains);
     if (blocks > static_cast<unsigned long long>(n_sms)) blocks = n_sms;
     cudaError_t err;
-    static thread_local size_t smem_set[2] = {0, 0};   // the attribute is sticky per function: raise it only when needed
+    size_t* const smem_set = state->smem_set;          // the attribute is sticky per function AND device: raise it only when needed
     if (stream_tiles) {
         if (smem > smem_set[1]) {
             err = cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

@@ -13,6 +13,7 @@
 // a missing GPU is a thrown std::runtime_error.
 #pragma once
 #include <cmath>
+#include <cstring>
 #include <cstdint>
 #include <memory>
 #include <stdexcept>
@@ -210,8 +211,8 @@ public:
 // ---- the renderer: one rtx_ctx -------------------------------------------------------------------------------------------
 class Renderer {
     rtx_ctx* ctx = nullptr;
-    const Scene* uploaded = nullptr;
-    size_t uploaded_size = 0;
+    std::vector<rtx_object> uploaded;      // what the device holds: compared by content before every frame
+    bool have_uploaded = false;
     void check(int rc, const char* what) const
     {
         if (rc != RTX_OK) throw std::runtime_error(std::string(what) + ": " + rtx_status_string(rc) + ": " + rtx_last_error(ctx));
@@ -234,16 +235,28 @@ public:
         std::vector<rtx_object> objs;
         objs.reserve(scene.size());
         for (const auto& g : scene) objs.push_back(g->describe());
-        check(rtx_set_scene(ctx, objs.data(), static_cast<int32_t>(objs.size())), "rtx_set_scene");
-        uploaded = &scene;
-        uploaded_size = scene.size();
+        upload(std::move(objs));
+    }
+
+    // The reference reads the scene vector afresh on every frame (main.cpp:329), so an element replaced or edited in
+    // place must show in the next frame: the scene is re-described per call (O(N), nothing next to a frame) and
+    // uploaded again whenever its CONTENT differs from what the device holds — not merely its address or size.
+    void sync_scene(const Scene& scene)
+    {
+        std::vector<rtx_object> objs;
+        objs.reserve(scene.size());
+        for (const auto& g : scene) objs.push_back(g->describe());
+        if (have_uploaded && objs.size() == uploaded.size() &&
+            (objs.empty() || std::memcmp(objs.data(), uploaded.data(), objs.size() * sizeof(rtx_object)) == 0))
+            return;
+        upload(std::move(objs));
     }
 
     // rt_scene (main.cpp:124-139): fills frame_buffer[i][j] (row i, column j) with the radiance of every pixel.
-    // The scene is uploaded on first use and whenever a different scene object (or size) is passed.
+    // The scene is uploaded on first use and whenever its content has changed (sync_scene).
     void rt_scene(const std::vector<vec3>& u, const Scene& scene, const Camera& cam, std::vector<std::vector<RGB>>& frame_buffer)
     {
-        if (uploaded != &scene || uploaded_size != scene.size()) set_scene(scene);
+        sync_scene(scene);
         const rtx_camera c = cam.pod(u);
         const size_t W = c.width, H = c.height;
         if (frame_buffer.size() < H) throw std::out_of_range("frame_buffer has fewer rows than image_height");   // .at(i), main.cpp:136
@@ -264,7 +277,7 @@ public:
     // pixels[i * pitch/4 + j] = RGBA8888 word. pitch in bytes, as SDL_Surface::pitch.
     void render_surface(const std::vector<vec3>& u, const Scene& scene, const Camera& cam, uint32_t* pixels, int pitch)
     {
-        if (uploaded != &scene || uploaded_size != scene.size()) set_scene(scene);
+        sync_scene(scene);
         const rtx_camera c = cam.pod(u);
         const size_t W = c.width, H = c.height;
         rtx_outputs out{};
@@ -304,6 +317,13 @@ public:
     }
 
 private:
+    void upload(std::vector<rtx_object>&& objs)
+    {
+        have_uploaded = false;
+        check(rtx_set_scene(ctx, objs.data(), static_cast<int32_t>(objs.size())), "rtx_set_scene");
+        uploaded = std::move(objs);
+        have_uploaded = true;
+    }
     std::vector<double> radiance;
     std::vector<uint32_t> surface;
 };

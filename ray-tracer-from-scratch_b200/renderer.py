@@ -69,6 +69,27 @@ def load_library(path=LIB_PATH):
     lib.rtx_render.restype = C.c_int
     lib.rtx_render.argtypes = [ctx, C.POINTER(abi.CameraPOD), C.c_int32, C.POINTER(abi.Params),
                                C.POINTER(abi.Outputs), C.POINTER(abi.Stats)]
+    lib.rtx_render_async.restype = C.c_int
+    lib.rtx_render_async.argtypes = [ctx, C.POINTER(abi.CameraPOD), C.c_int32, C.POINTER(abi.Params), C.POINTER(abi.Outputs)]
+    lib.rtx_wait.restype = C.c_int
+    lib.rtx_wait.argtypes = [ctx, C.POINTER(abi.Stats)]
+    lib.rtx_trace_rays.restype = C.c_int
+    lib.rtx_trace_rays.argtypes = [ctx, C.POINTER(abi.RayPOD), C.c_int64, C.POINTER(abi.Params), C.POINTER(abi.Outputs),
+                                   C.POINTER(abi.Stats)]
+    lib.rtx_host_alloc.restype = C.c_int
+    lib.rtx_host_alloc.argtypes = [ctx, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.rtx_host_free.restype = C.c_int
+    lib.rtx_host_free.argtypes = [ctx, C.c_void_p]
+    lib.rtx_host_register.restype = C.c_int
+    lib.rtx_host_register.argtypes = [ctx, C.c_void_p, C.c_uint64]
+    lib.rtx_host_unregister.restype = C.c_int
+    lib.rtx_host_unregister.argtypes = [ctx, C.c_void_p]
+    lib.rtx_host_device_pointer.restype = C.c_int
+    lib.rtx_host_device_pointer.argtypes = [ctx, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.rtx_host_shared_open.restype = C.c_int
+    lib.rtx_host_shared_open.argtypes = [ctx, C.c_char_p, C.c_uint64, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.rtx_host_shared_close.restype = C.c_int
+    lib.rtx_host_shared_close.argtypes = [ctx, C.c_void_p, C.c_char_p]
     lib.rtx_quantise.restype = C.c_int
     lib.rtx_quantise.argtypes = [ctx, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
                                  C.POINTER(abi.Stats)]
@@ -141,6 +162,8 @@ _PLANES = {  # name -> (Outputs field, numpy dtype, trailing shape)
     "object_id": ("object_id", np.int32, ()),
     "hit_mask": ("hit_mask", np.uint8, ()),
     "ray_count": ("ray_count", np.uint8, ()),
+    "hit_distance": ("hit_distance", np.float64, ()),
+    "hit_normal": ("hit_normal", np.float64, (3,)),
 }
 
 
@@ -201,6 +224,65 @@ class Renderer:
         self._check(self.lib.rtx_render(self._ctx, arr, len(cams), C.byref(params), C.byref(outputs), C.byref(st)))
         self.last_stats = st
         return st
+
+    def render_async(self, cams, params, outputs):
+        """rtx_render_async: queues the call and returns; wait() completes the oldest call in flight (at most two)."""
+        arr = (abi.CameraPOD * len(cams))(*cams)
+        self._check(self.lib.rtx_render_async(self._ctx, arr, len(cams), C.byref(params), C.byref(outputs)))
+
+    def wait(self):
+        st = abi.Stats()
+        self._check(self.lib.rtx_wait(self._ctx, C.byref(st)))
+        self.last_stats = st
+        return st
+
+    def trace_rays(self, rays, params=None, want=("radiance_f64", "object_id", "hit_distance", "hit_normal", "ray_count")):
+        """rtx_trace_rays: recursive_ray_tracing / find_closest_hit (main.cpp:67-119) for a batch of rays.
+        rays: sequence of (origin, direction) triples. Returns (numpy planes [n_rays](+[3]), Stats)."""
+        params = params if params is not None else default_params()
+        n = len(rays)
+        arr = (abi.RayPOD * n)()
+        for k, (o, d) in enumerate(rays):
+            arr[k].origin, arr[k].direction = abi.Vec3(*o), abi.Vec3(*d)
+        o = abi.Outputs()
+        o.memory = abi.RTX_MEM_HOST
+        planes = {}
+        for name in want:
+            field, dtype, tail = _PLANES[name]
+            planes[name] = np.empty((n,) + tail, dtype)
+            setattr(o, field, planes[name].ctypes.data)
+        st = abi.Stats()
+        self._check(self.lib.rtx_trace_rays(self._ctx, arr, n, C.byref(params), C.byref(o), C.byref(st)))
+        self.last_stats = st
+        return planes, st
+
+    # -- pinned / mapped / shared host memory (zero-copy surfaces, multi-process host frames) ------------------
+    def host_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self.lib.rtx_host_alloc(self._ctx, int(nbytes), C.byref(p)))
+        return p.value
+
+    def host_free(self, ptr):
+        self._check(self.lib.rtx_host_free(self._ctx, C.c_void_p(ptr)))
+
+    def host_register(self, ptr, nbytes):
+        self._check(self.lib.rtx_host_register(self._ctx, C.c_void_p(ptr), int(nbytes)))
+
+    def host_unregister(self, ptr):
+        self._check(self.lib.rtx_host_unregister(self._ctx, C.c_void_p(ptr)))
+
+    def host_device_pointer(self, ptr):
+        p = C.c_void_p()
+        self._check(self.lib.rtx_host_device_pointer(self._ctx, C.c_void_p(ptr), C.byref(p)))
+        return p.value
+
+    def host_shared_open(self, name, nbytes, create):
+        p = C.c_void_p()
+        self._check(self.lib.rtx_host_shared_open(self._ctx, name.encode(), int(nbytes), 1 if create else 0, C.byref(p)))
+        return p.value
+
+    def host_shared_close(self, ptr, unlink_name=None):
+        self._check(self.lib.rtx_host_shared_close(self._ctx, C.c_void_p(ptr), unlink_name.encode() if unlink_name else None))
 
     def render(self, cams, params=None, want=("rgba8",), out=None):
         """Renders len(cams) frames into host numpy planes shaped [F][rows][W](+[3]).

@@ -3,27 +3,39 @@
 Pixels are independent (main.cpp:129-138 has no cross-iteration state), so the only exchange is the final gather:
 
   * one big frame (config C4): image rows are grouped into cyclic bands of `band_rows` rows, band b -> rank b % G
-    (contiguous stripes are measurably imbalanced: SURVEY.md §7 hard part 4). Each rank renders its rows with
-    rtx_render(n_ranks=G, rank=r) into a packed device buffer; ONE all-gather delivers the band-major frame; rank 0
-    scatters it to row-major with the rtx_unpermute_bands kernel.
-  * a camera path (config C5): frame f -> rank f % G; each rank renders its frames in chunks and bulk-copies every
-    finished chunk into rank 0's frame set over NVLink while the next chunk renders (or, in gather mode, one batched
-    launch + ONE all-gather + a reindexing on rank 0).
+    (contiguous stripes are measurably imbalanced: SURVEY.md §7 hard part 4).
+  * a camera path (config C5): frame f -> rank f % G, rendered in chunks.
 
-Two ways to bring the pixels to rank 0:
+Where the pixels go (`to_host`):
 
-  * fused (default): rank 0 allocates the frame with rtx_buffer_alloc and exports a CUDA-IPC handle; every other rank
-    maps it (rtx_buffer_import, peer access over NVLink) and passes it as rtx_outputs.frame_rgba8. The trace kernel
-    then stores each finished pixel directly at its global position in rank 0's memory — the gather is part of the
-    kernel, there is no all-gather and no unpermute pass, only one barrier.
-  * gather: packed local buffers + all_gather_into_tensor + rtx_unpermute_bands (kept for comparison and for the
-    optional object-id plane).
+  * rank 0's HBM (default; BASELINE.json: "gathered to rank 0"): rank 0 allocates the frame (set) with
+    rtx_buffer_alloc and exports a CUDA-IPC handle; the other ranks map it (peer access over NVLink).
+  * a pinned HOST frame shared by all ranks (`to_host=True`; the end-to-end path): a POSIX shared-memory object that
+    every rank maps and pins (rtx_host_shared_open). Each rank delivers its own rows over its OWN PCIe link — rank 0's
+    link no longer carries the whole frame.
+
+How they get there (rtx_outputs.frame_mode):
+
+  * RTX_FRAME_STORE — the trace kernel stores every finished pixel at its global position (peer memory or the device
+    alias of the host frame): the gather is part of the kernel, only a barrier follows. Right for the 10k-object
+    scene, where a pixel costs microseconds.
+  * RTX_FRAME_COPY — each call renders into context staging and copy-engine transfers (2-D copies for bands, whole
+    frames for a camera path) move it, overlapped with the next chunk's kernel through rtx_render_async. Right for
+    the three-object scene, where pixels are produced at tens of gigabytes per second.
+  * gather (`fused=False`): packed local buffers + ONE all_gather_into_tensor + rtx_unpermute_bands (kept as the
+    comparison BASELINE.json names, and for the optional object-id plane).
 
 No data-path collective happens during tracing. Everything here is host logic + collectives; pixels are computed
 only by the CUDA kernels behind the C ABI.
+
+Streams: the Renderer is bound to torch's current stream on construction, so that kernels, NCCL collectives and the
+unpermute pass are all ordered on ONE stream (the collectives are ordered against torch's current stream only).
 """
 import ctypes as C
+import os
+import uuid
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -77,6 +89,14 @@ def frame_owner(n_frames, world):
     return [list(range(r, n_frames, world)) for r in range(world)]
 
 
+def chunks_of(frames, n_chunks):
+    """A rank's frames in at most n_chunks consecutive pieces (the units of the render/copy pipeline)."""
+    if not frames:
+        return []
+    size = max(1, (len(frames) + n_chunks - 1) // n_chunks)
+    return [frames[k:k + size] for k in range(0, len(frames), size)]
+
+
 class _DevicePtr:
     """Wraps a raw device pointer for torch.as_tensor through the CUDA array interface."""
 
@@ -84,25 +104,40 @@ class _DevicePtr:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
 
 
+def _add_stats(total, st):
+    if total is None:
+        return st
+    total.total_rays += st.total_rays
+    total.raytracing_ms += st.raytracing_ms
+    total.sphere_tests += st.sphere_tests
+    total.wall_tests += st.wall_tests
+    total.d2h_ms += st.d2h_ms
+    total.launches += st.launches
+    return total
+
+
 class ShardedRenderer:
     """Row-band / frame sharding around one Renderer per rank."""
 
-    def __init__(self, renderer, rank, world, band_rows=4, group=None, fused=True):
+    def __init__(self, renderer, rank, world, band_rows=4, group=None, fused=True, n_chunks=4):
         self.r = renderer
         self.rank, self.world, self.band_rows, self.group = rank, world, band_rows, group
         self.device = torch.device("cuda", renderer.device)
         self.fused = fused
-        self._frame = None      # (key, pointer valid in THIS process, tensor view on rank 0)
+        self.n_chunks = n_chunks
+        self._frame = None      # device frame (set) on rank 0: (key, pointer valid in THIS process, tensor view on rank 0)
+        self._host = None       # shared pinned host frame (set): (key, host pointer, device alias, numpy view)
         self._token = None
-        self._side = None       # side stream + double buffers of the pipelined camera-path gather
-        self._bufs = {}
+        # NCCL orders its collectives against torch's CURRENT stream only: bind the renderer's work to that stream, so
+        # that the all-gather -> unpermute and kernel -> barrier orders hold without extra synchronisation.
+        renderer.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
     # -- the shared frame on rank 0 -------------------------------------------------------------------
     def _shared_frame(self, n_frames, H, W):
         key = (n_frames, H, W)
         if self._frame is not None and self._frame[0] == key:
             return self._frame[1], self._frame[2]
-        self.close()
+        self._close_device_frame()
         handle = [None]
         ptr = None
         if self.rank == 0:
@@ -116,98 +151,98 @@ class ShardedRenderer:
         self._frame = (key, ptr, view)
         return ptr, view
 
-    def close(self):
+    def _shared_host_frame(self, n_frames, H, W):
+        """A pinned host frame set every rank can write: POSIX shared memory, mapped + cudaHostRegister'ed in each process."""
+        key = (n_frames, H, W)
+        if self._host is not None and self._host[0] == key:
+            return self._host[1:]
+        self._close_host_frame()
+        nbytes = n_frames * H * W * 4
+        if self.world == 1:
+            hptr = self.r.host_alloc(nbytes)
+            name = None
+        else:
+            box = [None]
+            if self.rank == 0:
+                box[0] = "/rtx_b200_%d_%s" % (os.getpid(), uuid.uuid4().hex[:12])
+                hptr = self.r.host_shared_open(box[0], nbytes, create=True)
+            dist.broadcast_object_list(box, src=0, group=self.group)
+            name = box[0]
+            if self.rank != 0:
+                hptr = self.r.host_shared_open(name, nbytes, create=False)
+            dist.barrier(group=self.group)                 # everyone has it mapped ...
+            if self.rank == 0:
+                os.unlink("/dev/shm" + name)               # ... so the name can go; the mappings keep the memory alive
+        dptr = self.r.host_device_pointer(hptr)
+        view = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_uint32)), shape=(n_frames, H, W))
+        self._host = (key, hptr, dptr, view, name)
+        return hptr, dptr, view, name
+
+    def _close_device_frame(self):
         if self._frame is not None:
             _, ptr, _ = self._frame
+            self._frame = None
+            torch.cuda.synchronize(self.device)
+            # importers unmap FIRST, then everybody meets, then the owner frees: freeing exported memory that a peer
+            # still has open is undefined behaviour
+            if self.rank != 0:
+                self.r.buffer_release(ptr)
             if self.world > 1:
                 dist.barrier(group=self.group)
             if self.rank == 0:
                 self.r.buffer_free(ptr)
-            else:
-                self.r.buffer_release(ptr)
-            self._frame = None
 
-    def _fused_render(self, cam_pods, total_frames, H, W, params):
-        ptr, view = self._shared_frame(total_frames, H, W)
-        o = abi.Outputs()
-        o.memory = abi.RTX_MEM_DEVICE
-        o.frame_rgba8 = ptr
-        st = self.r.render_raw(cam_pods, params, o) if cam_pods else None
+    def _close_host_frame(self):
+        if self._host is not None:
+            _, hptr, _, _, name = self._host
+            self._host = None
+            torch.cuda.synchronize(self.device)
+            if self.world > 1:
+                dist.barrier(group=self.group)             # nobody still writes it
+                self.r.host_shared_close(hptr)
+            else:
+                self.r.host_free(hptr)
+
+    def close(self):
+        self._close_device_frame()
+        self._close_host_frame()
+
+    def _barrier(self):
+        """Stream-ordered barrier: a 1-element all-reduce completes on rank 0 only after every rank's contribution,
+        which each rank enqueues behind its own work on the same stream. Work queued after it sees the whole frame."""
         if self.world > 1:
-            # Stream-ordered barrier: a 1-element all-reduce completes on rank 0 only after every rank's contribution,
-            # which each rank enqueues behind its own trace kernel. Work queued after it on rank 0 sees the whole frame.
             if self._token is None:
                 self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
             dist.all_reduce(self._token, group=self.group)
-        return view, st, (st.launches if st else 0)
 
-    def _pipelined_frames(self, cam_pods, mine, F, H, W, params, n_chunks=4):
-        """Camera path, whole frames per rank: a frame is 8 MB, so instead of scattering 4-byte pixel stores over
-        NVLink (fine for one frame spread over ranks, wasteful for gigabytes) each rank renders chunks of frames into
-        local double buffers and copies every finished chunk into rank 0's IPC-mapped frame set with bulk peer copies
-        on a side stream, overlapped with the rendering of the next chunk."""
-        ptr, view = self._shared_frame(F, H, W)
-        if self.rank == 0:
-            # rank 0 owns the frame set: one launch, pixels stored straight at their place (local stores, no copies)
-            params.frame_offset, params.frame_stride = 0, self.world
-            o = abi.Outputs()
-            o.memory, o.frame_rgba8 = abi.RTX_MEM_DEVICE, ptr
-            st = self.r.render_raw([cam_pods[f] for f in mine], params, o) if mine else None
-            if self.world > 1:
-                if self._token is None:
-                    self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
-                dist.all_reduce(self._token, group=self.group)
-            return view, st, (st.launches if st else 0)
-        dest = torch.as_tensor(_DevicePtr(ptr, (F, H, W)), device=self.device)
-        chunk = max(1, (len(mine) + n_chunks - 1) // n_chunks)
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
-            self._bufs = {}
-        key = (chunk, H, W)
-        if key not in self._bufs:
-            self._bufs = {key: ([torch.empty((chunk, H, W), dtype=torch.int32, device=self.device) for _ in range(2)],
-                                [torch.cuda.Event(), torch.cuda.Event()])}
-        bufs, events = self._bufs[key]
-        o = abi.Outputs()
-        o.memory = abi.RTX_MEM_DEVICE
-        total = None
-        launches = 0
-        for ci, start in enumerate(range(0, len(mine), chunk)):
-            frames = mine[start:start + chunk]
-            buf = bufs[ci % 2]
-            if ci >= 2:
-                events[ci % 2].synchronize()           # the copies that read this buffer two chunks ago are done
-            o.rgba8 = buf.data_ptr()
-            st = self.r.render_raw([cam_pods[f] for f in frames], params, o)      # returns when the chunk is rendered
-            launches += st.launches
-            if total is None:
-                total = st
-            else:
-                total.total_rays += st.total_rays
-                total.raytracing_ms += st.raytracing_ms
-                total.sphere_tests += st.sphere_tests
-                total.wall_tests += st.wall_tests
-            with torch.cuda.stream(self._side):
-                for k, f in enumerate(frames):
-                    dest[f].copy_(buf[k], non_blocking=True)
-                events[ci % 2].record(self._side)
-        torch.cuda.current_stream().wait_stream(self._side)
-        if self.world > 1:
-            if self._token is None:
-                self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
-            dist.all_reduce(self._token, group=self.group)     # stream-ordered barrier: all copies have landed
-        return view, total, launches
+    def _destination(self, n_frames, H, W, to_host):
+        """(pointer to hand to rtx_outputs.frame_rgba8 in STORE mode, same in COPY mode, rank 0's view of the result)."""
+        if to_host:
+            hptr, dptr, view, _ = self._shared_host_frame(n_frames, H, W)
+            return dptr, hptr, (view if self.rank == 0 else None)
+        ptr, view = self._shared_frame(n_frames, H, W)
+        return ptr, ptr, view
 
-    def render_frame(self, cam_pod, max_depth=10, want_ids=False, **param_overrides):
-        """Renders one frame across all ranks. Returns (frame, stats): frame is an int32 CUDA tensor [H][W] of
-        RGBA8888 words on rank 0 (None elsewhere); with want_ids also the object-id plane."""
+    # -- one frame, rows sharded ------------------------------------------------------------------------------------
+    def render_frame(self, cam_pod, max_depth=10, want_ids=False, to_host=False, frame_mode=abi.RTX_FRAME_STORE, **param_overrides):
+        """Renders one frame across all ranks. Returns (frame, stats, launches): on rank 0 the frame is an int32 CUDA
+        tensor [H][W] of RGBA8888 words (to_host: a uint32 numpy view of the shared pinned host frame), None elsewhere;
+        with want_ids also the object-id plane (all-gather path)."""
         H, W = cam_pod.height, cam_pod.width
         rpr = rows_per_rank(H, self.band_rows, self.world)
         p = default_params(max_depth=max_depth, band_rows=self.band_rows, n_ranks=self.world, rank=self.rank,
                            **param_overrides)
         if self.fused and not want_ids:
-            view, st, launches = self._fused_render([cam_pod], 1, H, W, p)
-            return (view[0] if view is not None else None), st, launches
+            store_ptr, copy_ptr, view = self._destination(1, H, W, to_host)
+            o = abi.Outputs()
+            o.memory = abi.RTX_MEM_DEVICE
+            o.frame_mode = frame_mode
+            o.frame_rgba8 = copy_ptr if frame_mode == abi.RTX_FRAME_COPY else store_ptr
+            st = self.r.render_raw([cam_pod], p, o)          # COPY mode: returns when this rank's bands have landed
+            self._barrier()
+            if to_host and self.rank == 0:
+                torch.cuda.current_stream(self.device).synchronize()      # the barrier has completed: every rank's rows are in host memory
+            return (view[0] if view is not None else None), st, st.launches
         local = torch.empty((rpr, W), dtype=torch.int32, device=self.device)
         ids = torch.empty((rpr, W), dtype=torch.int32, device=self.device) if want_ids else None
         o = abi.Outputs()
@@ -230,14 +265,50 @@ class ShardedRenderer:
                 launches += 1
         return (frame, frame_ids) if want_ids else frame, st, launches
 
-    def render_frames(self, cam_pods, max_depth=10, **param_overrides):
-        """Camera path: frame f on rank f % world, one batched launch per rank, one all-gather.
-        Returns (frames, stats): int32 CUDA tensor [F][H][W] in frame order on rank 0 (None elsewhere)."""
+    # -- a camera path, frames sharded ------------------------------------------------------------------------------
+    def _pipelined_frames(self, cam_pods, mine, F, H, W, params, to_host):
+        """Camera path, whole frames per rank: a frame is 8 MB, so instead of scattering 4-byte pixel stores (fine for
+        one costly frame spread over ranks, wasteful for gigabytes of cheap pixels) each rank renders chunks of frames with
+        rtx_render_async in RTX_FRAME_COPY mode: a chunk is traced into one of the context's two staging slots and
+        copy-engine transfers on the context's copy stream place its frames in the frame set (rank 0's HBM over NVLink,
+        or the shared pinned host frame over this rank's own PCIe link) while the next chunk is traced."""
+        store_ptr, copy_ptr, view = self._destination(F, H, W, to_host)
+        o = abi.Outputs()
+        o.memory = abi.RTX_MEM_DEVICE
+        params.frame_stride = self.world
+        total = None
+        if self.rank == 0 and not to_host:
+            # rank 0 owns the device frame set: one launch, pixels stored straight at their place (local stores, no copies)
+            params.frame_offset = 0
+            o.frame_mode, o.frame_rgba8 = abi.RTX_FRAME_STORE, store_ptr
+            if mine:
+                total = self.r.render_raw([cam_pods[f] for f in mine], params, o)
+        else:
+            o.frame_mode, o.frame_rgba8 = abi.RTX_FRAME_COPY, copy_ptr
+            in_flight = 0
+            for frames in chunks_of(mine, self.n_chunks):
+                if in_flight == 2:
+                    total = _add_stats(total, self.r.wait())
+                    in_flight -= 1
+                params.frame_offset = frames[0]              # frame k of this call is global frame frames[0] + k * world
+                self.r.render_async([cam_pods[f] for f in frames], params, o)
+                in_flight += 1
+            while in_flight:
+                total = _add_stats(total, self.r.wait())     # returns when that chunk's frames have landed
+                in_flight -= 1
+        self._barrier()
+        if to_host and self.rank == 0:
+            torch.cuda.current_stream(self.device).synchronize()
+        return view, total, (total.launches if total else 0)
+
+    def render_frames(self, cam_pods, max_depth=10, to_host=False, **param_overrides):
+        """Camera path: frame f on rank f % world. Returns (frames, stats, launches): on rank 0 an int32 CUDA tensor
+        [F][H][W] in frame order (to_host: a uint32 numpy view of the shared pinned host frame set), None elsewhere."""
         F = len(cam_pods)
         H, W = cam_pods[0].height, cam_pods[0].width
         mine = frame_owner(F, self.world)[self.rank]
         if self.fused:
-            return self._pipelined_frames(cam_pods, mine, F, H, W, default_params(max_depth=max_depth, **param_overrides))
+            return self._pipelined_frames(cam_pods, mine, F, H, W, default_params(max_depth=max_depth, **param_overrides), to_host)
         per_rank = (F + self.world - 1) // self.world
         local = torch.zeros((per_rank, H, W), dtype=torch.int32, device=self.device)
         st = None

@@ -79,3 +79,27 @@ def test_c4_8k_bands_and_properties(gpu, renderer_mod, S):
     # the separate quantise kernel on the double radiance gives the fused result
     unf, su = gpu.render([pod], renderer_mod.default_params(max_depth=10, fuse_quantise=0), want=("rgba8",))
     assert np.array_equal(unf["rgba8"], full["rgba8"]) and su.launches == 2
+
+
+def test_c5_full_1080p_orbit_frames_match_reference(gpu, renderer_mod, S):
+    """Config C5 at full size: frames 48 and 224 of the orbit see the walls from BEHIND (the pass-through of
+    main.cpp:111-113: two depth levels spent, the wall shaded twice), frame 128 is the far side. Every row of the
+    three frames against the unmodified reference's per-row CRCs, rendered in one batched call like the orbit itself."""
+    g = load_json("fullsize_c5.json")
+    cams = S.flythrough_cameras(g["n_frames"], g["width"], 16.0 / 9.0)
+    ks = sorted(int(k) for k in g["frames"])
+    gpu.set_scene(S.default_scene())
+    planes, st = gpu.render([cams[k].pod() for k in ks], renderer_mod.default_params(max_depth=g["depth"]),
+                            want=("rgba8", "ray_count", "object_id"))
+    assert planes["rgba8"].shape == (len(ks), 1080, 1920)
+    total = 0
+    for n, k in enumerate(ks):
+        gf = g["frames"][str(k)]
+        one = {name: a[n:n + 1] for name, a in planes.items()}
+        check_against_fullsize(one, st, gf, np.array(gf["rows"]))
+        total += gf["total_rays"]
+        # back faces really occur in frames 48 and 224: a primary wall hit followed by the same wall again
+        if k in (48, 224):
+            ids, rc = planes["object_id"][n], planes["ray_count"][n]
+            assert ((ids >= 1) & (rc >= 3)).any()
+    assert st.total_rays == total and st.over_range_pixels == 0
