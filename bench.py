@@ -675,6 +675,30 @@ def main():
                 e1.record()
                 e1.synchronize()
             ms_stream = e0.elapsed_time(e1) / n_stream
+            # ... and the device-resident frame as a stream (no host wait between frames: launch latency overlaps the kernel)
+            for rep in range(2):
+                flush.add_(1)
+                e0.record()
+                for k in range(n_stream):
+                    r.render_async([pod2], p2, o_dev)
+                    if k >= 1:
+                        st2 = r.wait()
+                st2 = r.wait()
+                e1.record()
+                e1.synchronize()
+            ms_dstream = e0.elapsed_time(e1) / n_stream
+            res["device_stream"] = {"ms_per_frame": ms_dstream, "mrays_s": st2.total_rays / (ms_dstream * 1e-3) / 1e6, "frames": n_stream,
+                                    "frames_in_flight": 2, "api": "rtx_render_async + rtx_wait"}
+            # the PCIe read-back of one frame alone (pinned memory): the floor of any host-facing 1080p frame on this box
+            ts = []
+            for _ in range(8):
+                e0.record()
+                host2.copy_(dev2, non_blocking=True)
+                e1.record()
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            d2h_ms = sorted(ts)[len(ts) // 2]
+            res["d2h_copy_alone"] = {"ms": d2h_ms, "gbs": dev2.numel() * 4 / (d2h_ms * 1e-3) / 1e9}
             res["e2e_stream"] = {"ms_per_frame": ms_stream, "mrays_s": st2.total_rays / (ms_stream * 1e-3) / 1e6, "frames": n_stream,
                                  "frames_in_flight": 2, "api": "rtx_render_async + rtx_wait"}
             import numpy as np
@@ -715,6 +739,23 @@ def main():
                                              "tflops_algorithmic": fl3 / (k3 * 1e-3) / 1e12, "frac_of_fp32_peak": fl3 / (k3 * 1e-3) / 1e12 / peak},
                                   "parity": par3}
             if par3.get("rows_bad"):
+                rc = 1
+            # EXTENSION (rtx_params.accel = RTX_ACCEL_GRID): the same 4K frame with the uniform grid in front of
+            # the same exact tests. Never the roofline line: it removes work instead of doing it faster.
+            p3g = R.default_params(max_depth=spec3["depth"], accel=abi.RTX_ACCEL_GRID)
+            ks = []
+            for _ in range(8):
+                flush.add_(1)
+                torch.cuda.synchronize()
+                st3g = r.render_raw([pod3], p3g, o3)
+                ks.append(st3g.raytracing_ms)
+            k3g = sorted(ks[3:])[len(ks[3:]) // 2]
+            par3g = parity_check(spec3, {"device frame": dev3.cpu().numpy().view(np.uint32)})
+            line["also"]["c3_accel"] = {"workload": spec3["label"].replace("brute force", "uniform grid (extension, default off)"),
+                                        "rays_per_frame": st3g.total_rays, "rays_equal_brute_force": st3g.total_rays == st3.total_rays,
+                                        "device": {"kernel_ms": k3g, "mrays_s": st3g.total_rays / (k3g * 1e-3) / 1e6, "speedup_over_brute_force": k3 / k3g},
+                                        "parity": par3g}
+            if par3g.get("rows_bad"):
                 rc = 1
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -10,6 +10,7 @@ ABI_VERSION = 4
 RTX_OK, RTX_ERR_INVALID, RTX_ERR_CUDA, RTX_ERR_NO_SCENE, RTX_ERR_NOMEM = 0, 1, 2, 3, 4
 RTX_SPHERE, RTX_WALL, RTX_BOX = 0, 1, 2        # RTX_BOX: extension, see the header
 RTX_QUANT_WRAP, RTX_QUANT_SATURATE = 0, 1
+RTX_ACCEL_NONE, RTX_ACCEL_GRID = 0, 1               # extension, see the header
 RTX_TONEMAP_NONE, RTX_TONEMAP_REINHARD = 0, 1    # extension, see the header
 RTX_MEM_HOST, RTX_MEM_DEVICE, RTX_MEM_HOST_MAPPED = 0, 1, 2
 RTX_FRAME_STORE, RTX_FRAME_COPY = 0, 1
@@ -52,7 +53,7 @@ class RayPOD(C.Structure):
 
 class Params(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("quantise_mode", C.c_int32), ("fuse_quantise", C.c_int32),
-                ("reserved", C.c_int32),
+                ("accel", C.c_int32),
                 ("light_pos", Vec3), ("ground_color", Vec3), ("sky_low", Vec3), ("sky_high", Vec3),
                 ("reflect_offset", C.c_double), ("sky_exponent", C.c_double),
                 ("band_rows", C.c_int32), ("n_ranks", C.c_int32), ("rank", C.c_int32), ("reserved2", C.c_int32),

@@ -10,7 +10,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
     -Xcompiler -fPIC,-ffp-contract=off,-Wall ${RTX_NVCC_EXTRA:-} \
     -I"$here/../include" -I"$here/csrc" -shared \
-    "$here/csrc/api.cu" "$here/csrc/trace.cu" "$here/csrc/aux_kernels.cu" "$here/csrc/tonemap.cu" \
+    "$here/csrc/api.cu" "$here/csrc/trace.cu" "$here/csrc/trace_grid.cu" "$here/csrc/aux_kernels.cu" "$here/csrc/tonemap.cu" \
     -o "$here/librtx_b200.so"
 echo "built $here/librtx_b200.so"
 # Test-only builds with 1-slot internal buffers (tests/test_gpu_parity.py::test_overflow_paths_of_the_trace_kernel):
@@ -19,11 +19,11 @@ mkdir -p "$here/test_builds"
 for flag in RTX_MBOX_CAP=1 RTX_QUEUE_CAP=1; do
     "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off -D$flag \
         -I"$here/../include" -I"$here/csrc" -shared \
-        "$here/csrc/api.cu" "$here/csrc/trace.cu" "$here/csrc/aux_kernels.cu" "$here/csrc/tonemap.cu" \
+        "$here/csrc/api.cu" "$here/csrc/trace.cu" "$here/csrc/trace_grid.cu" "$here/csrc/aux_kernels.cu" "$here/csrc/tonemap.cu" \
         -o "$here/test_builds/librtx_b200_$flag.so" &
 done
 wait
-cat $(ls "$here"/csrc/*.cu | LC_ALL=C sort) "$here/csrc/rtx_device.cuh" "$here/../include/rtx_b200.h" \
+cat $(ls "$here"/csrc/*.cu | LC_ALL=C sort) "$here/csrc/rtx_device.cuh" "$here/csrc/trace_common.cuh" "$here/../include/rtx_b200.h" \
     | sha256sum | cut -d' ' -f1 > "$here/test_builds/SOURCES.sha256"
 echo "built $here/test_builds/"
 # C++ host facade example: the reference's main loop, headless (writes PPM). Links the C ABI only.

@@ -1,6 +1,7 @@
 // api.cu — the extern "C" layer of include/rtx_b200.h: context, scene upload, render, quantise, gather epilogue.
 // Host code only (kernels are in trace.cu / aux_kernels.cu). Built with -ffp-contract=off: the few doubles
 // computed here (wall normal + basis, Camera::init) must round exactly like the reference's x86-64 build.
+#include <algorithm>
 #include <cerrno>
 #include <cmath>
 #include <fcntl.h>
@@ -63,6 +64,12 @@ struct rtx_ctx {
     size_t h_scene_blob_cap = 0;
     cudaEvent_t ev_scene = nullptr;               // the last upload has left h_scene_blob
     double scene_bound = 0.0;          // max over objects of |coordinate| + extent
+    // uniform grid (extension, rtx_params.accel): built lazily from the host copy of the spheres
+    std::vector<SphereExact> h_sph64;
+    bool grid_valid = false;
+    GridDev grid = {};
+    void* d_grid_blob = nullptr;
+    size_t grid_blob_cap = 0;
 
     Slot slot[kSlots];
     int next_slot = 0;                 // slot the next call takes
@@ -244,6 +251,7 @@ void rtx_destroy(rtx_ctx* ctx)
     if (ctx->h_scene_blob) cudaFreeHost(ctx->h_scene_blob);
     if (ctx->d_rad_scratch) cudaFree(ctx->d_rad_scratch);
     if (ctx->d_tm_sums) cudaFree(ctx->d_tm_sums);
+    if (ctx->d_grid_blob) cudaFree(ctx->d_grid_blob);
     for (auto& m : ctx->shared_host) {
         cudaHostUnregister(m.first);
         munmap(m.first, m.second);
@@ -426,6 +434,8 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
     s.kind = reinterpret_cast<const int32_t*>(base + o_knd);
     s.slot = reinterpret_cast<const int32_t*>(base + o_slt);
     ctx->scene_bound = bound;
+    ctx->h_sph64 = std::move(sph64);
+    ctx->grid_valid = false;
     ctx->have_scene = true;
     ctx->error.clear();
     return RTX_OK;
@@ -509,6 +519,143 @@ int32_t rtx_global_row(int32_t local_row, int32_t height, int32_t band_rows, int
 
 namespace {
 
+// EXTENSION (rtx_params.accel = RTX_ACCEL_GRID): builds the uniform grid of the current scene on first use.
+// A sphere is listed in every cell that its bounding box, inflated by `margin`, overlaps. margin = 1e-6 x scene extent:
+// six orders of magnitude above the rounding of the double-precision walk and of the exact test's own accept/reject
+// boundary, and far below a cell. Spheres that are not finite, or that would land in more than kMaxCellsPerSphere cells,
+// go to the always list instead.
+int ensure_grid(rtx_ctx* ctx)
+{
+    if (ctx->grid_valid) return RTX_OK;
+    constexpr int kMaxCellsPerSphere = 512, kMaxDim = 512;
+    constexpr size_t kMaxCells = size_t(1) << 21;
+    const std::vector<SphereExact>& sp = ctx->h_sph64;
+    const int ns = static_cast<int>(sp.size());
+    const double B = std::fmax(ctx->scene_bound, 1e-3);
+    const double margin = 1e-6 * B;
+    std::vector<int32_t> always;
+    std::vector<int> in_grid;
+    std::vector<double> rad(ns, 0.0);
+    // a few huge spheres (a "ground" sphere of radius 1000 under a scene of unit spheres) must not stretch the grid: anything
+    // above 16 x the median radius is screened for every ray instead of being registered
+    double big = 1e300;
+    {
+        std::vector<double> radii;
+        for (const SphereExact& s : sp)
+            if (std::isfinite(s.r)) radii.push_back(std::fabs(s.r));
+        if (radii.size() >= 8) {
+            std::nth_element(radii.begin(), radii.begin() + radii.size() / 2, radii.end());
+            big = 16.0 * std::fmax(radii[radii.size() / 2], 1e-6 * B);
+        }
+    }
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int e = 0; e < ns; e++) {
+        const SphereExact& s = sp[e];
+        if (!(std::isfinite(s.cx) && std::isfinite(s.cy) && std::isfinite(s.cz) && std::isfinite(s.r)) || std::fabs(s.r) > big) {
+            always.push_back(e);
+            continue;
+        }
+        rad[e] = std::fabs(s.r) * (1.0 + 1e-9) + margin;
+        in_grid.push_back(e);
+        const double c[3] = {s.cx, s.cy, s.cz};
+        for (int k = 0; k < 3; k++) {
+            lo[k] = std::fmin(lo[k], c[k] - rad[e]);
+            hi[k] = std::fmax(hi[k], c[k] + rad[e]);
+        }
+    }
+    GridDev g = {};
+    std::vector<uint32_t> cell_start(1, 0u);
+    std::vector<uint32_t> items;
+    if (!in_grid.empty()) {
+        double ext[3];
+        for (int k = 0; k < 3; k++) ext[k] = std::fmax(hi[k] - lo[k], 4.0 * margin);
+        const double target = std::fmax(1.0, in_grid.size() / 4.0);            // about four spheres per cell
+        double cell = std::cbrt(ext[0] * ext[1] * ext[2] / target);
+        cell = std::fmax(cell, std::fmax(ext[0], std::fmax(ext[1], ext[2])) / kMaxDim);
+        int n[3];
+        for (;;) {
+            size_t total = 1;
+            for (int k = 0; k < 3; k++) {
+                n[k] = std::max(1, std::min(kMaxDim, static_cast<int>(std::ceil(ext[k] / cell))));
+                total *= static_cast<size_t>(n[k]);
+            }
+            if (total <= kMaxCells) break;
+            cell *= 1.26;
+        }
+        g.nx = n[0]; g.ny = n[1]; g.nz = n[2];
+        g.x0 = lo[0]; g.y0 = lo[1]; g.z0 = lo[2];
+        g.x1 = lo[0] + n[0] * cell; g.y1 = lo[1] + n[1] * cell; g.z1 = lo[2] + n[2] * cell;    // covers hi[] (n = ceil(ext / cell))
+        g.cell = cell;
+        g.inv_cell = 1.0 / cell;
+        g.slack = 1e-7 * B;
+        const size_t n_cells = static_cast<size_t>(n[0]) * n[1] * n[2];
+        auto range = [&](double c, double r, int k, int& a, int& b) {
+            a = std::max(0, std::min(n[k] - 1, static_cast<int>(std::floor((c - r - lo[k]) / cell))));
+            b = std::max(0, std::min(n[k] - 1, static_cast<int>(std::floor((c + r - lo[k]) / cell))));
+        };
+        std::vector<uint32_t> count(n_cells + 1, 0u);
+        std::vector<int> kept;
+        for (int e : in_grid) {
+            int a[3], b[3];
+            range(sp[e].cx, rad[e], 0, a[0], b[0]);
+            range(sp[e].cy, rad[e], 1, a[1], b[1]);
+            range(sp[e].cz, rad[e], 2, a[2], b[2]);
+            const long long cells = static_cast<long long>(b[0] - a[0] + 1) * (b[1] - a[1] + 1) * (b[2] - a[2] + 1);
+            if (cells > kMaxCellsPerSphere) {
+                always.push_back(e);
+                continue;
+            }
+            kept.push_back(e);
+            for (int z = a[2]; z <= b[2]; z++)
+                for (int y = a[1]; y <= b[1]; y++)
+                    for (int x = a[0]; x <= b[0]; x++) count[(static_cast<size_t>(z) * n[1] + y) * n[0] + x + 1]++;
+        }
+        for (size_t k = 0; k < n_cells; k++) count[k + 1] += count[k];
+        cell_start = count;
+        items.resize(cell_start[n_cells]);
+        std::vector<uint32_t> cursor(cell_start.begin(), cell_start.end() - 1);
+        for (int e : kept) {
+            int a[3], b[3];
+            range(sp[e].cx, rad[e], 0, a[0], b[0]);
+            range(sp[e].cy, rad[e], 1, a[1], b[1]);
+            range(sp[e].cz, rad[e], 2, a[2], b[2]);
+            for (int z = a[2]; z <= b[2]; z++)
+                for (int y = a[1]; y <= b[1]; y++)
+                    for (int x = a[0]; x <= b[0]; x++) items[cursor[(static_cast<size_t>(z) * n[1] + y) * n[0] + x]++] = static_cast<uint32_t>(e);
+        }
+    }
+    g.n_items = static_cast<int32_t>(items.size());
+    g.items16 = ns <= 65535 ? 1 : 0;
+    g.n_always = static_cast<int32_t>(always.size());
+    // one blob: cell_start | items (16 or 32 bit) | always
+    auto align = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
+    const size_t o_cs = 0;
+    const size_t o_it = align(cell_start.size() * 4);
+    const size_t it_bytes = g.items16 ? ((items.size() + 1) / 2) * 4 : items.size() * 4;
+    const size_t o_al = align(o_it + std::max<size_t>(it_bytes, 4));
+    const size_t total = align(o_al + std::max<size_t>(always.size() * 4, 4));
+    std::vector<unsigned char> blob(total, 0);
+    std::memcpy(&blob[o_cs], cell_start.data(), cell_start.size() * 4);
+    if (g.items16) {
+        uint16_t* d = reinterpret_cast<uint16_t*>(&blob[o_it]);
+        for (size_t k = 0; k < items.size(); k++) d[k] = static_cast<uint16_t>(items[k]);
+    } else if (!items.empty()) {
+        std::memcpy(&blob[o_it], items.data(), items.size() * 4);
+    }
+    if (!always.empty()) std::memcpy(&blob[o_al], always.data(), always.size() * 4);
+    RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // a kernel of an earlier call may still walk the old grid
+    int rc = grow(ctx, &ctx->d_grid_blob, &ctx->grid_blob_cap, total);
+    if (rc != RTX_OK) return rc;
+    RTX_CUDA(ctx, cudaMemcpy(ctx->d_grid_blob, blob.data(), total, cudaMemcpyHostToDevice));
+    unsigned char* base = static_cast<unsigned char*>(ctx->d_grid_blob);
+    g.cell_start = reinterpret_cast<const uint32_t*>(base + o_cs);
+    g.items = base + o_it;
+    g.always = reinterpret_cast<const int32_t*>(base + o_al);
+    ctx->grid = g;
+    ctx->grid_valid = true;
+    return RTX_OK;
+}
+
 // Waits for the call in `sl` and turns its events / counters into rtx_stats.
 int finish_slot(rtx_ctx* ctx, Slot& sl, rtx_stats* stats)
 {
@@ -563,6 +710,7 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
     if (outs->memory != RTX_MEM_HOST && outs->memory != RTX_MEM_DEVICE && outs->memory != RTX_MEM_HOST_MAPPED)
         return fail(ctx, RTX_ERR_INVALID, W_ + ": outputs.memory must be RTX_MEM_HOST, RTX_MEM_DEVICE or RTX_MEM_HOST_MAPPED");
     if (p.tonemap != RTX_TONEMAP_NONE && p.tonemap != RTX_TONEMAP_REINHARD) return fail(ctx, RTX_ERR_INVALID, W_ + ": unknown tonemap");
+    if (p.accel != RTX_ACCEL_NONE && p.accel != RTX_ACCEL_GRID) return fail(ctx, RTX_ERR_INVALID, W_ + ": unknown accel");
     const bool tonemap = p.tonemap == RTX_TONEMAP_REINHARD && outs->rgba8;
     if (tonemap && (p.n_ranks != 1 || outs->frame_rgba8 || ray_mode))
         return fail(ctx, RTX_ERR_INVALID, W_ + ": the tone-map operator needs the whole frame on one GPU (n_ranks = 1, no frame_rgba8, no ray batch)");
@@ -676,6 +824,12 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
         }
     }
 
+    const bool use_grid = p.accel == RTX_ACCEL_GRID && ctx->scene.n_entries > kSmallSceneEntries;
+    if (use_grid) {
+        int rc = ensure_grid(ctx);
+        if (rc != RTX_OK) return rc;
+    }
+
     if (ray_mode) std::memcpy(sl.h_rays, rays, sizeof(rtx_ray) * n_rays);
     else std::memcpy(sl.h_cameras, cams, sizeof(rtx_camera) * n_frames);
 
@@ -720,6 +874,8 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
     a.frame_offset = p.frame_offset;
     a.frame_stride = p.frame_stride;
     a.counters = sl.d_counters;
+    a.use_grid = use_grid ? 1 : 0;
+    if (use_grid) a.grid = ctx->grid;
 
     // ---- enqueue ----------------------------------------------------------------------------------------------------------
     cudaStream_t cs = ctx->copy_stream;

@@ -87,10 +87,31 @@ struct SceneDev {
     const int32_t* slot;               // [n_objects] index into sph64 / walls (box: its first face)
 };
 
+// EXTENSION (rtx_params.accel = RTX_ACCEL_GRID; SURVEY §8(f)4, README.md:17 "acceleration structure"): a uniform grid over
+// the finite spheres. Cell (ix, iy, iz) lists the sphere slots whose inflated bounding box overlaps it; walls and
+// spheres the grid cannot hold (non-finite, or so large that they would fill it) stay on the "always" list and are
+// screened for every ray. The grid only PROPOSES candidates: every hit decision is still taken by the exact double
+// tests, with the reference's acceptance rule, so ids / distances / pixels equal the brute-force ones bit for bit.
+struct GridDev {
+    int32_t nx, ny, nz;                // 0, 0, 0: no grid (no finite sphere)
+    int32_t n_items;
+    double x0, y0, z0;                 // minimum corner
+    double x1, y1, z1;                 // maximum corner
+    double cell, inv_cell;             // cubic cells
+    double slack;                      // distance margin of the early exit (>> DDA rounding, << cell)
+    const uint32_t* cell_start;        // [nx*ny*nz + 1]
+    const void* items;                 // sphere slots, cell after cell: uint16_t if items16 else uint32_t
+    int32_t items16;
+    int32_t n_always;
+    const int32_t* always;             // [n_always] sphere slots screened for every ray
+};
+
 // Per-launch arguments of the trace kernel.
 struct TraceArgs {
     SceneDev scene;
     const rtx_camera* cameras;         // [n_frames] device copy
+    int32_t use_grid;                  // 1: trace_grid_kernel with `grid` (extension); 0: brute force
+    GridDev grid;
     const rtx_ray* rays;               // rtx_trace_rays: ray p replaces pixel p's primary ray (n_frames = local_rows = 1, width = n_rays)
     int32_t n_frames, width, height;   // global frame size
     int32_t local_rows;                // rows this rank renders per frame
@@ -178,10 +199,13 @@ constexpr int kSmallSceneEntries = 16;   // scenes of at most this many screen e
 struct TraceLaunchState {
     size_t smem_set[2] = {0, 0};       // largest dynamic shared-memory size requested so far: resident / streamed kernel
     int small_per_sm = 0;              // resident CTAs per SM of trace_small_kernel (occupancy query, once)
+    size_t smem_grid = 0;              // trace_grid_kernel (extension)
+    int grid_per_sm = 0;
 };
 
 // Launch wrappers implemented in the .cu files, called by api.cu.
 cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, int* launches, TraceLaunchState* state);
+cudaError_t launch_trace_grid(const TraceArgs& args, int n_sms, cudaStream_t stream, int* launches, TraceLaunchState* state);
 cudaError_t launch_quantise_f64(const double* rad, int64_t n_pixels, int mode, uint32_t* rgba8,
                                 unsigned long long* counters, int n_sms, cudaStream_t stream);
 cudaError_t launch_quantise_f32(const float* rad, int64_t n_pixels, int mode, uint32_t* rgba8,

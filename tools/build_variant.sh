@@ -9,6 +9,6 @@ defs=""
 for d in "$@"; do defs="$defs -D$d"; done
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off $defs \
     -I"$here/../include" -I"$here/csrc" -shared \
-    "$here/csrc/api.cu" "$here/csrc/trace.cu" "$here/csrc/aux_kernels.cu" "$here/csrc/tonemap.cu" \
+    "$here/csrc/api.cu" "$here/csrc/trace.cu" "$here/csrc/trace_grid.cu" "$here/csrc/aux_kernels.cu" "$here/csrc/tonemap.cu" \
     -o "$here/librtx_b200_$name.so"
 echo "built $here/librtx_b200_$name.so"
