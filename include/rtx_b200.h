@@ -339,6 +339,13 @@ int rtx_buffer_export(rtx_ctx* ctx, void* device_ptr, uint8_t handle[RTX_IPC_HAN
 int rtx_buffer_import(rtx_ctx* ctx, const uint8_t handle[RTX_IPC_HANDLE_BYTES], void** device_ptr);
 int rtx_buffer_release(rtx_ctx* ctx, void* imported_ptr);
 
+/* ONE process driving several GPUs (one context + one host thread per GPU, the C++ host's rtx::ShardedRenderer): the
+ * kernels of `ctx`'s device may then store into memory of `peer_device` (rank 0's frame from rtx_buffer_alloc, passed to
+ * the other contexts as rtx_outputs.frame_rgba8) over NVLink — the in-process counterpart of rtx_buffer_export / _import.
+ * Idempotent. rtx_device_count: number of visible CUDA devices (0 if none / no driver). */
+int rtx_enable_peer_access(rtx_ctx* ctx, int peer_device);
+int rtx_device_count(void);
+
 /* Pinned, mapped host memory for RTX_MEM_HOST_MAPPED outputs and for fast RTX_MEM_HOST read-back — the role of the
  * SDL surface the reference quantises into (SDL_CreateRGBSurface, main.cpp:193; written main.cpp:338-347).
  *   rtx_host_alloc / rtx_host_free         a new pinned + mapped buffer;

@@ -87,7 +87,7 @@ EXPORTS = (
     "rtx_abi_version", "rtx_status_string", "rtx_create", "rtx_destroy", "rtx_last_error", "rtx_set_stream",
     "rtx_set_scene", "rtx_camera_init", "rtx_default_params", "rtx_local_rows", "rtx_global_row",
     "rtx_render", "rtx_render_async", "rtx_wait", "rtx_trace_rays", "rtx_quantise", "rtx_tonemap", "rtx_tonemap_sums", "rtx_tonemap_apply", "rtx_unpermute_bands", "rtx_ffma_peak",
-    "rtx_host_alloc", "rtx_host_free", "rtx_host_register", "rtx_host_unregister", "rtx_host_device_pointer",
+    "rtx_enable_peer_access", "rtx_device_count", "rtx_host_alloc", "rtx_host_free", "rtx_host_register", "rtx_host_unregister", "rtx_host_device_pointer",
     "rtx_host_shared_open", "rtx_host_shared_close",
     "rtx_buffer_alloc", "rtx_buffer_free", "rtx_buffer_export", "rtx_buffer_import", "rtx_buffer_release",
 )

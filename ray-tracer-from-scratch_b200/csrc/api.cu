@@ -899,8 +899,10 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
     RTX_ENQ(cudaEventRecord(sl.ev[1], st));
     // A small scene rendered into HOST memory is bound by the PCIe read-back, not by the kernel (1080p: 0.08 ms of
     // tracing, 0.15 ms of copy): trace the frame as kRanges consecutive pixel ranges and copy each finished range on a
-    // second stream while the next one is traced. (Not for the big kernel: every launch of it has its own drain tail.)
-    const bool ranged = host_out && !unfused && !frame_copy && ctx->scene.n_entries <= kSmallSceneEntries && n_px >= kRangedMinPixels;
+    // second stream while the next one is traced. (Not for the big kernel: every launch of it has its own drain tail. Not for
+    // rtx_render_async either: there the whole read-back already overlaps the NEXT frame's kernel, and a stream of small
+    // frames is bound by the host's launch path — one launch and one copy per frame instead of four of each.)
+    const bool ranged = host_out && !async && !unfused && !frame_copy && ctx->scene.n_entries <= kSmallSceneEntries && n_px >= kRangedMinPixels;
     if (ranged) {
         for (int c = 0; c < kRanges; c++) {
             const size_t p0 = (n_px * c / kRanges) & ~static_cast<size_t>(3), p1 = c + 1 == kRanges ? n_px : (n_px * (c + 1) / kRanges) & ~static_cast<size_t>(3);
@@ -1271,6 +1273,33 @@ int rtx_buffer_release(rtx_ctx* ctx, void* imported_ptr)
     RTX_CUDA(ctx, cudaSetDevice(ctx->device));
     RTX_CUDA(ctx, cudaIpcCloseMemHandle(imported_ptr));
     return RTX_OK;
+}
+
+int rtx_enable_peer_access(rtx_ctx* ctx, int peer_device)
+{
+    if (!ctx) return RTX_ERR_INVALID;
+    if (peer_device == ctx->device) return RTX_OK;
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    int can = 0;
+    RTX_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) return fail(ctx, RTX_ERR_CUDA, "rtx_enable_peer_access: the devices are not peers");
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return RTX_OK;
+    }
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaDeviceEnablePeerAccess");
+    return RTX_OK;
+}
+
+int rtx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
 }
 
 int rtx_host_alloc(rtx_ctx* ctx, uint64_t bytes, void** host_ptr)

@@ -217,6 +217,16 @@ struct FrameTotals {
     double maxlum;
 };
 
+// acc += w * v, spelled as explicit fused multiply-adds: the front-to-back accumulation is this repo's own arithmetic (the
+// reference folds back to front, main.cpp:117), and written with plain * and + the compiler would be free to contract it
+// differently in each kernel that inlines it. Explicit operations make every kernel produce the same bits.
+__device__ __forceinline__ void accumulate(d3& acc, double w, d3 v)
+{
+    acc.x = __fma_rn(w, v.x, acc.x);
+    acc.y = __fma_rn(w, v.y, acc.y);
+    acc.z = __fma_rn(w, v.z, acc.z);
+}
+
 // Shade one finished segment of a chain (recursive_ray_tracing, main.cpp:89-119) and either set up the
 // reflected ray or write the pixel.
 __device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, const SceneDev& sc, FrameTotals& tot)
@@ -246,9 +256,7 @@ __device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, const S
             const double s = (a.sky_exponent == 0.25) ? sqrt(sqrt(vz)) : pow(vz, a.sky_exponent);
             col = lerp(a.sky_low, a.sky_high, s);
         }
-        c.acc.x += c.weight * col.x;
-        c.acc.y += c.weight * col.y;
-        c.acc.z += c.weight * col.z;
+        accumulate(c.acc, c.weight, col);
         done = true;
     } else {
         d3 normal;
@@ -288,17 +296,12 @@ __device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, const S
             local = add(local, scale(tint, ks));
         }
         if (c.remaining <= 0) {                                            // main.cpp:105-108
-            c.acc.x += c.weight * local.x;
-            c.acc.y += c.weight * local.y;
-            c.acc.z += c.weight * local.z;
+            accumulate(c.acc, c.weight, local);
             done = true;
         } else {
             // lerp(local, reflected, metallic) unrolled front to back (main.cpp:117)
-            const double wl = c.weight * (1.0 - m.metallic);
-            c.acc.x += wl * local.x;
-            c.acc.y += wl * local.y;
-            c.acc.z += wl * local.z;
-            c.weight *= m.metallic;
+            accumulate(c.acc, ex::mul(c.weight, ex::sub(1.0, m.metallic)), local);
+            c.weight = ex::mul(c.weight, m.metallic);
             const d3 start = add(pos, scale(normal, a.reflect_offset));    // main.cpp:111 (normal unnormalised)
             const double kk = mul(2.0, dot(dhat, nn));                     // vec.cpp:55
             c.d = sub(dhat, scale(nn, kk));                                // vec.cpp:56

@@ -8,7 +8,11 @@
 // CUDA-event times. The window/renderer/texture calls are replaced by a binary PPM (or raw RGBA8888) file.
 //
 //   rtx_headless [--width 640] [--aspect 1] [--depth 10] [--frames 3] [--keys wwad] [--out frame.ppm] [--raw frame.rgba]
-//                [--png frame.png] [--sun 1] [--tonemap 1] [--box 1]
+//                [--png frame.png] [--sun 1] [--tonemap 1] [--box 1] [--devices 0,1,...] [--band-rows 4] [--scene default|synthetic]
+//                [--accel 1]
+// --devices: more than one entry renders every frame on several GPUs from THIS process (rtx::ShardedRenderer: one context
+// and one host thread per GPU, cyclic row bands, every kernel storing its pixels straight into one pinned host surface);
+// a device may be repeated (0,0 = two contexts on one GPU). --scene synthetic = the 10 064-object scene of configs C3/C4.
 // --keys: one key event per frame — w s a d as in the reference (main.cpp:262-306); j l i k = the mouse look the reference
 // leaves commented out (rotate_left_right(+-0.05), rotate_up_down(+-0.05), main.cpp:319-323); anything else = no event.
 // --sun / --tonemap / --box switch on this repo's EXTENSIONS (default-off; include/rtx_b200.h): the sun of main.cpp:18-19
@@ -84,12 +88,54 @@ static void write_png(const std::string& path, const std::vector<uint32_t>& surf
     std::fclose(f);
 }
 
+static void write_outputs(const std::vector<uint32_t>& surface, int W, int H, const std::string& out_ppm, const std::string& out_raw,
+                          const std::string& out_png)
+{
+    if (!out_ppm.empty()) {
+        FILE* f = std::fopen(out_ppm.c_str(), "wb");
+        if (!f) throw std::runtime_error("cannot open " + out_ppm);
+        std::fprintf(f, "P6\n%d %d\n255\n", W, H);
+        for (uint32_t p : surface) {
+            const unsigned char rgb[3] = {static_cast<unsigned char>(p >> 24), static_cast<unsigned char>(p >> 16), static_cast<unsigned char>(p >> 8)};
+            std::fwrite(rgb, 1, 3, f);
+        }
+        std::fclose(f);
+    }
+    if (!out_raw.empty()) {
+        FILE* f = std::fopen(out_raw.c_str(), "wb");
+        if (!f) throw std::runtime_error("cannot open " + out_raw);
+        std::fwrite(surface.data(), 4, surface.size(), f);
+        std::fclose(f);
+    }
+    if (!out_png.empty()) write_png(out_png, surface, W, H);
+}
+
+// One key event (main.cpp:262-306); init() is NOT re-run after a move, exactly like the reference.
+static void apply_key(Camera& cam, char key)
+{
+    switch (key) {
+        case 'w': cam.forward(); break;
+        case 's': cam.backward(); break;
+        case 'a': cam.left(); break;
+        case 'd': cam.right(); break;
+        // the mouse look of main.cpp:319-323 (commented out there) at full deflection, x_input / y_input = -+1
+        case 'j': cam.rotate_left_right(0.05); break;
+        case 'l': cam.rotate_left_right(-0.05); break;
+        case 'i': cam.rotate_up_down(0.05); break;
+        case 'k': cam.rotate_up_down(-0.05); break;
+        default: break;
+    }
+}
+
 int main(int argc, char* argv[])
 {
     int width = 640, depth = 10, frames = 3;
     double aspect = 1.0;   // ASPECT_RATIO = 4/3 is integer division = 1 in the reference (main.cpp:25)
     std::string keys, out_ppm = "frame.ppm", out_raw, out_png;
-    bool ext_sun = false, ext_tonemap = false, ext_box = false;
+    bool ext_sun = false, ext_tonemap = false, ext_box = false, accel = false;
+    std::vector<int> devices = {0};
+    int band_rows = 4;
+    std::string scene_name = "default";
     for (int k = 1; k + 1 < argc; k += 2) {
         const std::string a = argv[k];
         if (a == "--width") width = std::atoi(argv[k + 1]);
@@ -103,6 +149,18 @@ int main(int argc, char* argv[])
         else if (a == "--sun") ext_sun = std::atoi(argv[k + 1]) != 0;
         else if (a == "--tonemap") ext_tonemap = std::atoi(argv[k + 1]) != 0;
         else if (a == "--box") ext_box = std::atoi(argv[k + 1]) != 0;
+        else if (a == "--accel") accel = std::atoi(argv[k + 1]) != 0;
+        else if (a == "--band-rows") band_rows = std::atoi(argv[k + 1]);
+        else if (a == "--scene") scene_name = argv[k + 1];
+        else if (a == "--devices") {
+            devices.clear();
+            const std::string list = argv[k + 1];
+            for (size_t pos = 0; pos <= list.size();) {
+                const size_t comma = std::min(list.find(',', pos), list.size());
+                devices.push_back(std::atoi(list.substr(pos, comma - pos).c_str()));
+                pos = comma + 1;
+            }
+        }
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     try {
@@ -117,9 +175,13 @@ int main(int argc, char* argv[])
         auto u = cam.init();
 
         Scene scene;                                  // main.cpp:156-163
-        scene.push_back(std::make_unique<Sphere>(Material(RGB(0, 1, 0), 0.5), point3(1.5, 0, 0), .5));
-        scene.push_back(std::make_unique<Wall>(Material(RGB(0, 0, 1)), point3(3.0, 2, 0), vec3(0, -1, 0), 1, 1));
-        scene.push_back(std::make_unique<Wall>(Material(RGB(0, 1, 0)), point3(3.0, -3, 0), vec3(0, 1, 0), 2, 2));
+        if (scene_name == "synthetic") {
+            scene = synthetic_scene();                // configs C3 / C4
+        } else {
+            scene.push_back(std::make_unique<Sphere>(Material(RGB(0, 1, 0), 0.5), point3(1.5, 0, 0), .5));
+            scene.push_back(std::make_unique<Wall>(Material(RGB(0, 0, 1)), point3(3.0, 2, 0), vec3(0, -1, 0), 1, 1));
+            scene.push_back(std::make_unique<Wall>(Material(RGB(0, 1, 0)), point3(3.0, -3, 0), vec3(0, 1, 0), 2, 2));
+        }
 
         const int H = static_cast<int>(cam.image_height), W = width;
         std::vector<uint32_t> surface(static_cast<size_t>(W) * H);
@@ -128,8 +190,36 @@ int main(int argc, char* argv[])
 
         if (ext_box) scene.push_back(std::make_unique<Box>(Material(RGB(0.9, 0.2, 0.2), 0.6), point3(2.5, -1.0, -0.8), vec3(1.0, 1.2, 0.9)));
 
-        Renderer renderer(0);
+        if (devices.size() > 1) {
+            // several GPUs: the two calls of the single-GPU loop below become ONE (trace + quantise fused, pixels stored by the
+            // kernels into the shared surface); the log keeps the reference's stage names
+            ShardedRenderer sharded(devices, band_rows);
+            sharded.params.max_depth = depth;
+            if (ext_sun) sharded.params.sun_enabled = 1;
+            if (accel) sharded.params.accel = RTX_ACCEL_GRID;
+            std::vector<int64_t> rt_times;
+            const uint32_t* pixels = nullptr;
+            for (int frame = 0; frame < frames; frame++) {
+                if (frame < static_cast<int>(keys.size())) apply_key(cam, keys[frame]);
+                auto t0 = std::chrono::high_resolution_clock::now();
+                pixels = sharded.render_surface(u, scene, cam);
+                auto t1 = std::chrono::high_resolution_clock::now();
+                rt_times.push_back(std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count());
+            }
+            std::copy(pixels, pixels + surface.size(), surface.begin());
+            write_outputs(surface, W, H, out_ppm, out_raw, out_png);
+            const rtx_stats st = sharded.stats();
+            const int64_t mean_us = rt_times.empty() ? 0 : std::accumulate(rt_times.begin(), rt_times.end(), int64_t{0}) / static_cast<int64_t>(rt_times.size());
+            std::cout << "Number of frames: " << frames << " : " << mean_us / 1000 << " ms average frame time\n";
+            std::cout << "   " << mean_us << " microseconds for average raytracing\n";
+            std::cout << "   0 milliseconds for surface average update\n";
+            std::cout << "   device (CUDA events): " << st.raytracing_ms << " ms raytracing on the slowest of " << devices.size() << " GPUs, "
+                      << st.total_rays << " rays, " << st.over_range_pixels << " over-range pixels in the last frame\n";
+            return 0;
+        }
+        Renderer renderer(devices[0]);
         renderer.params.max_depth = depth;
+        if (accel) renderer.params.accel = RTX_ACCEL_GRID;
         if (ext_sun) renderer.params.sun_enabled = 1;
         if (ext_tonemap) {
             renderer.params.tonemap = RTX_TONEMAP_REINHARD;
@@ -138,20 +228,7 @@ int main(int argc, char* argv[])
         std::vector<int64_t> total_times, rt_times, surface_update_times;
         std::vector<double> device_rt_ms, device_surface_ms;
         for (int frame = 0; frame < frames; frame++) {
-            if (frame < static_cast<int>(keys.size())) {   // one key event per frame (main.cpp:262-306)
-                switch (keys[frame]) {
-                    case 'w': cam.forward(); break;
-                    case 's': cam.backward(); break;
-                    case 'a': cam.left(); break;
-                    case 'd': cam.right(); break;
-                    // the mouse look of main.cpp:319-323 (commented out there) at full deflection, x_input / y_input = -+1
-                    case 'j': cam.rotate_left_right(0.05); break;
-                    case 'l': cam.rotate_left_right(-0.05); break;
-                    case 'i': cam.rotate_up_down(0.05); break;
-                    case 'k': cam.rotate_up_down(-0.05); break;
-                    default: break;
-                }
-            }
+            if (frame < static_cast<int>(keys.size())) apply_key(cam, keys[frame]);   // one key event per frame (main.cpp:262-306)
             auto rt_start = std::chrono::high_resolution_clock::now();
             renderer.rt_scene(u, scene, cam, frame_buffer);
             auto rt_end = std::chrono::high_resolution_clock::now();
@@ -164,24 +241,7 @@ int main(int argc, char* argv[])
             total_times.push_back(std::chrono::duration_cast<std::chrono::milliseconds>(surface_end - rt_start).count());
         }
 
-        if (!out_ppm.empty()) {
-            FILE* f = std::fopen(out_ppm.c_str(), "wb");
-            if (!f) throw std::runtime_error("cannot open " + out_ppm);
-            std::fprintf(f, "P6\n%d %d\n255\n", W, H);
-            for (uint32_t p : surface) {
-                const unsigned char rgb[3] = {static_cast<unsigned char>(p >> 24), static_cast<unsigned char>(p >> 16), static_cast<unsigned char>(p >> 8)};
-                std::fwrite(rgb, 1, 3, f);
-            }
-            std::fclose(f);
-        }
-        if (!out_raw.empty()) {
-            FILE* f = std::fopen(out_raw.c_str(), "wb");
-            if (!f) throw std::runtime_error("cannot open " + out_raw);
-            std::fwrite(surface.data(), 4, surface.size(), f);
-            std::fclose(f);
-        }
-
-        if (!out_png.empty()) write_png(out_png, surface, W, H);
+        write_outputs(surface, W, H, out_ppm, out_raw, out_png);
 
         auto mean = [](const std::vector<int64_t>& v) { return v.empty() ? 0 : std::accumulate(v.begin(), v.end(), int64_t{0}) / static_cast<int64_t>(v.size()); };
         auto meand = [](const std::vector<double>& v) { return v.empty() ? 0.0 : std::accumulate(v.begin(), v.end(), 0.0) / v.size(); };

@@ -17,7 +17,10 @@
 #include <cstdint>
 #include <memory>
 #include <stdexcept>
+#include <algorithm>
+#include <exception>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rtx_b200.h"
@@ -208,8 +211,37 @@ public:
     }
 };
 
+// The synthetic scene of configs C3 / C4: splitmix64 seeded 0xB200, U() = (next() >> 11) * 2^-53,
+// 10 000 spheres then 64 walls drawn in the survey's order. Same objects as scene.py::synthetic_scene.
+inline Scene synthetic_scene(int n_spheres = 10000, int n_walls = 64, uint64_t seed = 0xB200)
+{
+    uint64_t state = seed;
+    auto next = [&state]() {
+        state += 0x9E3779B97F4A7C15ull;
+        uint64_t z = state;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    auto U = [&next](double a, double b) { return a + (b - a) * (static_cast<double>(next() >> 11) * (1.0 / 9007199254740992.0)); };
+    Scene scene;
+    for (int k = 0; k < n_spheres; k++) {
+        const double cx = U(4, 64), cy = U(-32, 32), cz = U(-8, 24), r = U(.1, .6);
+        const double R = U(.1, 1), G = U(.1, 1), B = U(.1, 1), metallic = U(0, .8);
+        scene.push_back(std::make_unique<Sphere>(Material(RGB(R, G, B), metallic), point3(cx, cy, cz), r));
+    }
+    for (int k = 0; k < n_walls; k++) {
+        const double px = U(4, 64), py = U(-32, 32), pz = U(-8, 8), phi = U(0, 6.283185307179586), nz = U(-.5, .5);
+        const double length = U(1, 6), width = U(1, 6);
+        const double R = U(.1, 1), G = U(.1, 1), B = U(.1, 1), metallic = U(0, .8);
+        scene.push_back(std::make_unique<Wall>(Material(RGB(R, G, B), metallic), point3(px, py, pz), vec3(std::cos(phi), std::sin(phi), nz), length, width));
+    }
+    return scene;
+}
+
 // ---- the renderer: one rtx_ctx -------------------------------------------------------------------------------------------
 class Renderer {
+    friend class ShardedRenderer;
     rtx_ctx* ctx = nullptr;
     std::vector<rtx_object> uploaded;      // what the device holds: compared by content before every frame
     bool have_uploaded = false;
@@ -229,6 +261,14 @@ public:
     ~Renderer() { rtx_destroy(ctx); }
     Renderer(const Renderer&) = delete;
     Renderer& operator=(const Renderer&) = delete;
+
+    rtx_ctx* raw() const { return ctx; }
+    void enable_peer_access(int peer_device) { check(rtx_enable_peer_access(ctx, peer_device), "rtx_enable_peer_access"); }
+    // rtx_render with caller-built structures (the sharded host uses it); stats land in this->stats.
+    void render_raw(const rtx_camera* cams, int n, const rtx_params& p, const rtx_outputs& out)
+    {
+        check(rtx_render(ctx, cams, n, &p, &out, &stats), "rtx_render");
+    }
 
     void set_scene(const Scene& scene)
     {
@@ -326,6 +366,131 @@ private:
     }
     std::vector<double> radiance;
     std::vector<uint32_t> surface;
+};
+
+// ---- several GPUs, one process -----------------------------------------------------------------------------------
+// The reference's frame loop (main.cpp:250-375) is one thread calling rt_scene once per frame. Here the same call fans
+// out: one rtx_ctx and one host thread per GPU, the frame's rows dealt to the GPUs in cyclic bands (band b -> GPU
+// b mod N; rtx_params.band_rows / n_ranks / rank), and every trace kernel stores its finished pixels AT THEIR GLOBAL
+// POSITION in one shared surface — no gather step, no reassembly:
+//   * surface(): a pinned, mapped host surface, the stand-in for SDL's surface->pixels (main.cpp:193,344); each GPU
+//     writes its rows over its own PCIe link (zero copy);
+//   * render_to_device(): the frame in GPU 0's memory instead, peers storing over NVLink (rtx_enable_peer_access).
+// A device may be listed more than once ({0, 0}: two contexts on one GPU) — the same code path, useful for testing.
+class ShardedRenderer {
+    std::vector<std::unique_ptr<Renderer>> gpus;
+    std::vector<int> devices;
+    uint32_t* host_surface = nullptr;      // pinned + mapped, W * H words
+    uint32_t* host_alias = nullptr;        // what the kernels dereference
+    uint32_t* device_frame = nullptr;      // on devices[0]
+    size_t surface_words = 0, device_words = 0;
+    int band_rows;
+
+    template <class F>
+    void on_every_gpu(F&& body)
+    {
+        std::vector<std::thread> threads;
+        std::vector<std::exception_ptr> errors(gpus.size());
+        for (size_t g = 0; g < gpus.size(); g++)
+            threads.emplace_back([&, g] {
+                try { body(static_cast<int>(g), *gpus[g]); } catch (...) { errors[g] = std::current_exception(); }
+            });
+        for (auto& t : threads) t.join();
+        for (auto& e : errors)
+            if (e) std::rethrow_exception(e);
+    }
+    void render_into(const std::vector<vec3>& u, const Scene& scene, const Camera& cam, uint32_t* frame_alias)
+    {
+        const rtx_camera c = cam.pod(u);
+        on_every_gpu([&](int g, Renderer& r) {
+            r.sync_scene(scene);
+            rtx_params p = params;
+            p.band_rows = band_rows;
+            p.n_ranks = static_cast<int32_t>(gpus.size());
+            p.rank = g;
+            rtx_outputs out{};
+            out.memory = RTX_MEM_DEVICE;
+            out.frame_mode = RTX_FRAME_STORE;
+            out.frame_rgba8 = frame_alias;
+            r.render_raw(&c, 1, p, out);      // returns when this GPU's kernel is complete: its pixels are in place
+        });
+    }
+public:
+    rtx_params params;                     // applied to every GPU (band fields are set per GPU)
+    explicit ShardedRenderer(const std::vector<int>& device_list, int band_rows = 4) : devices(device_list), band_rows(band_rows)
+    {
+        if (devices.empty()) throw std::invalid_argument("ShardedRenderer: no devices");
+        rtx_default_params(&params);
+        for (int d : devices) gpus.push_back(std::make_unique<Renderer>(d));
+        for (size_t g = 1; g < gpus.size(); g++) gpus[g]->enable_peer_access(devices[0]);
+    }
+    ~ShardedRenderer()
+    {
+        if (host_surface) rtx_host_free(gpus[0]->raw(), host_surface);
+        if (device_frame) rtx_buffer_free(gpus[0]->raw(), device_frame);
+    }
+    size_t size() const { return gpus.size(); }
+    Renderer& gpu(size_t g) { return *gpus.at(g); }
+
+    // The shared host surface for a W x H frame (allocated on first use / size change), RGBA8888 words, pitch = W * 4.
+    uint32_t* surface(size_t W, size_t H)
+    {
+        if (surface_words != W * H) {
+            if (host_surface) rtx_host_free(gpus[0]->raw(), host_surface);
+            host_surface = host_alias = nullptr;
+            void* p = nullptr;
+            gpus[0]->check(rtx_host_alloc(gpus[0]->raw(), W * H * 4, &p), "rtx_host_alloc");
+            host_surface = static_cast<uint32_t*>(p);
+            void* d = nullptr;
+            gpus[0]->check(rtx_host_device_pointer(gpus[0]->raw(), p, &d), "rtx_host_device_pointer");
+            host_alias = static_cast<uint32_t*>(d);
+            surface_words = W * H;
+        }
+        return host_surface;
+    }
+
+    // rt_scene + quantise (main.cpp:329-347) over all GPUs into the shared host surface; returns it.
+    const uint32_t* render_surface(const std::vector<vec3>& u, const Scene& scene, const Camera& cam)
+    {
+        const rtx_camera c = cam.pod(u);
+        surface(static_cast<size_t>(c.width), static_cast<size_t>(c.height));
+        render_into(u, scene, cam, host_alias);
+        return host_surface;
+    }
+
+    // The same with the assembled frame left in the first GPU's memory (device pointer, W * H words).
+    const uint32_t* render_to_device(const std::vector<vec3>& u, const Scene& scene, const Camera& cam)
+    {
+        const rtx_camera c = cam.pod(u);
+        const size_t words = static_cast<size_t>(c.width) * c.height;
+        if (device_words != words) {
+            if (device_frame) rtx_buffer_free(gpus[0]->raw(), device_frame);
+            device_frame = nullptr;
+            void* p = nullptr;
+            gpus[0]->check(rtx_buffer_alloc(gpus[0]->raw(), words * 4, &p), "rtx_buffer_alloc");
+            device_frame = static_cast<uint32_t*>(p);
+            device_words = words;
+        }
+        render_into(u, scene, cam, device_frame);
+        return device_frame;
+    }
+
+    // Sum over the GPUs of the last frame's statistics; raytracing_ms is the slowest GPU's.
+    rtx_stats stats() const
+    {
+        rtx_stats s{};
+        for (const auto& g : gpus) {
+            s.total_rays += g->stats.total_rays;
+            s.sphere_tests += g->stats.sphere_tests;
+            s.wall_tests += g->stats.wall_tests;
+            s.over_range_pixels += g->stats.over_range_pixels;
+            s.launches += g->stats.launches;
+            s.raytracing_ms = std::max(s.raytracing_ms, g->stats.raytracing_ms);
+            s.total_ms = std::max(s.total_ms, g->stats.total_ms);
+            s.max_luminance = std::max(s.max_luminance, g->stats.max_luminance);
+        }
+        return s;
+    }
 };
 
 // Free-function form with the reference's exact signature shape (main.cpp:124-125); uses one process-wide renderer.

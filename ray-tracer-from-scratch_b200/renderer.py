@@ -76,6 +76,10 @@ def load_library(path=LIB_PATH):
     lib.rtx_trace_rays.restype = C.c_int
     lib.rtx_trace_rays.argtypes = [ctx, C.POINTER(abi.RayPOD), C.c_int64, C.POINTER(abi.Params), C.POINTER(abi.Outputs),
                                    C.POINTER(abi.Stats)]
+    lib.rtx_enable_peer_access.restype = C.c_int
+    lib.rtx_enable_peer_access.argtypes = [ctx, C.c_int]
+    lib.rtx_device_count.restype = C.c_int
+    lib.rtx_device_count.argtypes = []
     lib.rtx_host_alloc.restype = C.c_int
     lib.rtx_host_alloc.argtypes = [ctx, C.c_uint64, C.POINTER(C.c_void_p)]
     lib.rtx_host_free.restype = C.c_int

@@ -548,3 +548,123 @@ def test_grazing_spheres_never_lose_a_hit(gpu, renderer_mod, port, S):
     exp = port.render(scene, pod, 6)
     check_frame(got, exp, st)
     assert (exp["object_id"] >= 0).sum() > 50          # the construction does produce hits (and near-misses)
+
+
+def test_mapped_host_surface_equals_staged_path(gpu, renderer_mod, port, S):
+    """RTX_MEM_HOST_MAPPED: the kernels store straight into a pinned, mapped host surface (the SDL surface->pixels case,
+    main.cpp:193,344) — no staging buffer, no copy. Same words as the staged RTX_MEM_HOST path, for the small-scene and
+    the big kernel, all planes."""
+    import ctypes as C
+    from conftest import ROOT  # noqa: F401
+    abi = renderer_mod.abi
+    for scene, pod, depth in ((S.default_scene(), S.default_camera(200, 16.0 / 9.0).pod(), 8),
+                              (S.synthetic_scene(900, 12), S.default_camera(120, 16.0 / 9.0).pod(), 6)):
+        gpu.set_scene(scene)
+        staged, st = gpu.render([pod], renderer_mod.default_params(max_depth=depth), want=WANT)
+        n = pod.width * pod.height
+        sizes = {"rgba8": 4, "radiance_f64": 24, "radiance_f32": 12, "object_id": 4, "hit_mask": 1, "ray_count": 1}
+        ptrs = {k: gpu.host_alloc(n * b) for k, b in sizes.items()}
+        try:
+            o = abi.Outputs()
+            o.memory = abi.RTX_MEM_HOST_MAPPED
+            for k in sizes:
+                setattr(o, k, ptrs[k])
+            st2 = gpu.render_raw([pod], renderer_mod.default_params(max_depth=depth), o)
+            assert st2.total_rays == st.total_rays and st2.d2h_ms < 0.05          # nothing is copied after the kernel
+            for k, (field, dtype, tail) in renderer_mod._PLANES.items():
+                if k not in sizes:
+                    continue
+                got = np.ctypeslib.as_array(C.cast(ptrs[k], C.POINTER(C.c_uint8)), shape=(n * sizes[k],)).view(dtype).reshape(staged[k][0].shape)
+                assert np.array_equal(got, staged[k][0], equal_nan=True) if got.dtype.kind == "f" else np.array_equal(got, staged[k][0]), k
+        finally:
+            for p in ptrs.values():
+                gpu.host_free(p)
+    # pageable memory is refused in this mode (it cannot be mapped), with a message that says what to use
+    buf = np.zeros(16, np.uint32)
+    o = abi.Outputs()
+    o.memory, o.rgba8 = abi.RTX_MEM_HOST_MAPPED, buf.ctypes.data
+    with pytest.raises(renderer_mod.RtxError) as e:
+        gpu.render_raw([S.default_camera(4, 1.0).pod()], renderer_mod.default_params(), o)
+    assert e.value.status == abi.RTX_ERR_INVALID and "rtx_host_alloc" in str(e.value)
+
+
+def test_async_frames_in_flight_equal_synchronous_frames(gpu, renderer_mod, port, S):
+    """rtx_render_async / rtx_wait: two frames in flight, host and device outputs, stats returned in order; a third call
+    without a wait is refused; a synchronous call drains what is in flight."""
+    import torch
+    abi = renderer_mod.abi
+    scene = S.default_scene()
+    gpu.set_scene(scene)
+    cams = [c.pod() for c in S.flythrough_cameras(256, 160, 16.0 / 9.0)[::37]]
+    p = renderer_mod.default_params(max_depth=10)
+    exp = [port.render(scene, c, 10, want=("rgba8", "ray_count")) for c in cams]
+    host = [np.zeros((cams[0].height, cams[0].width), np.uint32) for _ in cams]
+    outs = []
+    for h in host:
+        o = abi.Outputs()
+        o.memory, o.rgba8 = abi.RTX_MEM_HOST, h.ctypes.data
+        outs.append(o)
+    stats = []
+    for k, c in enumerate(cams):
+        gpu.render_async([c], p, outs[k])
+        if k >= 1:
+            stats.append(gpu.wait())
+    stats.append(gpu.wait())
+    for k in range(len(cams)):
+        assert np.array_equal(host[k], exp[k]["rgba8"]), k
+        assert stats[k].total_rays == int(exp[k]["ray_count"].astype(np.int64).sum()), k
+    with pytest.raises(renderer_mod.RtxError):
+        gpu.wait()                                             # nothing in flight
+    gpu.render_async([cams[0]], p, outs[0])
+    gpu.render_async([cams[1]], p, outs[1])
+    with pytest.raises(renderer_mod.RtxError):
+        gpu.render_async([cams[2]], p, outs[2])                # a third call in flight is refused
+    dev = torch.zeros((cams[2].height, cams[2].width), dtype=torch.int32, device="cuda")
+    o = abi.Outputs()
+    o.memory, o.rgba8 = abi.RTX_MEM_DEVICE, dev.data_ptr()
+    st = gpu.render_raw([cams[2]], p, o)                       # synchronous: completes the two in flight first
+    assert np.array_equal(dev.cpu().numpy().view(np.uint32), exp[2]["rgba8"]) and st.total_rays == stats[2].total_rays
+    assert np.array_equal(host[0], exp[0]["rgba8"]) and np.array_equal(host[1], exp[1]["rgba8"])
+    with pytest.raises(renderer_mod.RtxError):
+        gpu.wait()
+
+
+def test_frame_copy_mode_places_bands_and_frames(gpu, renderer_mod, port, S):
+    """RTX_FRAME_COPY: staging + copy-engine transfers to the global position — cyclic bands of one frame (2-D copies,
+    ragged last band) and whole frames of a camera path with frame_offset / frame_stride, into pinned host memory."""
+    import ctypes as C
+    abi = renderer_mod.abi
+    scene = S.default_scene()
+    gpu.set_scene(scene)
+    pod = S.default_camera(100, 100.0 / 54).pod()                     # 54 rows: ragged for 4-row bands over 3 ranks
+    exp = port.render(scene, pod, 6, want=("rgba8",))["rgba8"]
+    H, W = pod.height, pod.width
+    ptr = gpu.host_alloc(H * W * 4)
+    try:
+        frame = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=(H, W))
+        frame[:] = 0
+        for rank in range(3):
+            o = abi.Outputs()
+            o.memory, o.frame_mode, o.frame_rgba8 = abi.RTX_MEM_DEVICE, abi.RTX_FRAME_COPY, ptr
+            gpu.render_raw([pod], renderer_mod.default_params(max_depth=6, band_rows=4, n_ranks=3, rank=rank), o)
+        assert np.array_equal(frame, exp)
+    finally:
+        gpu.host_free(ptr)
+    cams = [c.pod() for c in S.flythrough_cameras(256, 96, 16.0 / 9.0)[::32]]      # 8 frames
+    H, W = cams[0].height, cams[0].width
+    ptr = gpu.host_alloc(len(cams) * H * W * 4)
+    try:
+        frames = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=(len(cams), H, W))
+        frames[:] = 0
+        for rank in range(2):                                          # frame f -> rank f % 2, two chunks each, asynchronously
+            mine = list(range(rank, len(cams), 2))
+            for chunk in (mine[:2], mine[2:]):
+                o = abi.Outputs()
+                o.memory, o.frame_mode, o.frame_rgba8 = abi.RTX_MEM_DEVICE, abi.RTX_FRAME_COPY, ptr
+                gpu.render_async([cams[f] for f in chunk], renderer_mod.default_params(max_depth=10, frame_offset=chunk[0], frame_stride=2), o)
+            gpu.wait()
+            gpu.wait()
+        for f, c in enumerate(cams):
+            assert np.array_equal(frames[f], port.render(scene, c, 10, want=("rgba8",))["rgba8"]), f
+    finally:
+        gpu.host_free(ptr)
