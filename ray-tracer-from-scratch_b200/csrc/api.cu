@@ -751,6 +751,16 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
     const size_t n_px = static_cast<size_t>(n_frames) * local_rows * W;
 
     // ---- slot: at most kSlots calls in flight ---------------------------------------------------------------------
+    if (!async) {
+        // a synchronous call first completes whatever is in flight, oldest first (those calls' stats are dropped)
+        while (ctx->slot[ctx->oldest].pending) {
+            Slot& o = ctx->slot[ctx->oldest];
+            ctx->oldest = (ctx->oldest + 1) % kSlots;
+            int rc = finish_slot(ctx, o, nullptr);
+            if (rc != RTX_OK) return rc;
+        }
+        ctx->oldest = ctx->next_slot;
+    }
     Slot& sl = ctx->slot[ctx->next_slot];
     if (sl.pending) return fail(ctx, RTX_ERR_INVALID, W_ + ": too many calls in flight (rtx_wait first)");
 
@@ -1000,16 +1010,8 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
     ctx->next_slot = (ctx->next_slot + 1) % kSlots;
     ctx->error.clear();
     if (async) return RTX_OK;
-    // synchronous call: every earlier asynchronous call completes first, in order (their stats are dropped)
-    for (;;) {
-        Slot& o = ctx->slot[ctx->oldest];
-        const bool mine = &o == &sl;
-        ctx->oldest = (ctx->oldest + 1) % kSlots;
-        int rc = finish_slot(ctx, o, mine ? stats : nullptr);
-        if (rc != RTX_OK) return rc;
-        if (mine) break;
-    }
-    return RTX_OK;
+    ctx->oldest = ctx->next_slot;          // nothing else is in flight (drained above): this call is the only pending one
+    return finish_slot(ctx, sl, stats);
 }
 
 }  // namespace

@@ -122,7 +122,11 @@ class ShardedRenderer:
     def __init__(self, renderer, rank, world, band_rows=4, group=None, fused=True, n_chunks=4):
         self.r = renderer
         self.rank, self.world, self.band_rows, self.group = rank, world, band_rows, group
-        self.device = torch.device("cuda", renderer.device)
+        # The token tensor of the stream-ordered barrier lives where the collective backend wants it: on this rank's GPU
+        # (NCCL). Without CUDA (the gloo tests of this host logic, with a stand-in renderer) it is a CPU tensor; pixels are
+        # never computed here either way.
+        self.on_gpu = torch.cuda.is_available()
+        self.device = torch.device("cuda", renderer.device) if self.on_gpu else torch.device("cpu")
         self.fused = fused
         self.n_chunks = n_chunks
         self._frame = None      # device frame (set) on rank 0: (key, pointer valid in THIS process, tensor view on rank 0)
@@ -130,7 +134,12 @@ class ShardedRenderer:
         self._token = None
         # NCCL orders its collectives against torch's CURRENT stream only: bind the renderer's work to that stream, so
         # that the all-gather -> unpermute and kernel -> barrier orders hold without extra synchronisation.
-        renderer.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        if self.on_gpu:
+            renderer.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _sync(self):
+        if self.on_gpu:
+            torch.cuda.current_stream(self.device).synchronize()
 
     # -- the shared frame on rank 0 -------------------------------------------------------------------
     def _shared_frame(self, n_frames, H, W):
@@ -182,7 +191,7 @@ class ShardedRenderer:
         if self._frame is not None:
             _, ptr, _ = self._frame
             self._frame = None
-            torch.cuda.synchronize(self.device)
+            self._sync()
             # importers unmap FIRST, then everybody meets, then the owner frees: freeing exported memory that a peer
             # still has open is undefined behaviour
             if self.rank != 0:
@@ -196,7 +205,7 @@ class ShardedRenderer:
         if self._host is not None:
             _, hptr, _, _, name = self._host
             self._host = None
-            torch.cuda.synchronize(self.device)
+            self._sync()
             if self.world > 1:
                 dist.barrier(group=self.group)             # nobody still writes it
                 self.r.host_shared_close(hptr)
@@ -241,7 +250,7 @@ class ShardedRenderer:
             st = self.r.render_raw([cam_pod], p, o)          # COPY mode: returns when this rank's bands have landed
             self._barrier()
             if to_host and self.rank == 0:
-                torch.cuda.current_stream(self.device).synchronize()      # the barrier has completed: every rank's rows are in host memory
+                self._sync()                  # the barrier has completed: every rank's rows are in host memory
             return (view[0] if view is not None else None), st, st.launches
         local = torch.empty((rpr, W), dtype=torch.int32, device=self.device)
         ids = torch.empty((rpr, W), dtype=torch.int32, device=self.device) if want_ids else None
@@ -298,7 +307,7 @@ class ShardedRenderer:
                 in_flight -= 1
         self._barrier()
         if to_host and self.rank == 0:
-            torch.cuda.current_stream(self.device).synchronize()
+            self._sync()
         return view, total, (total.launches if total else 0)
 
     def render_frames(self, cam_pods, max_depth=10, to_host=False, **param_overrides):

@@ -1,3 +1,4 @@
+import ctypes
 import importlib
 import json
 import os
@@ -33,12 +34,48 @@ def ob():
     return binding
 
 
+class PinnedOracle:
+    """The plain-C oracle, pinned AT RUN TIME: every frame it renders with the reference's own parameters is rendered a
+    second time by oracle/_ref — the unmodified reference sources — and must agree bit for bit (ids, masks, ray counts,
+    RGBA8 words, radiance) before a GPU test is allowed to compare the CUDA path with it. Frames the reference cannot
+    express (this repo's extensions: boxes, sun, non-default parameters) go through the port alone."""
+
+    def __init__(self, port, ref):
+        self._port, self._ref = port, ref
+        self.cross_checked = 0
+
+    def __getattr__(self, name):
+        return getattr(self._port, name)
+
+    def render(self, scene, cam_pod, max_depth=10, rows=None, threads=0,
+               want=("radiance", "rgba8", "object_id", "hit_mask", "ray_count"), params=None):
+        out = self._port.render(scene, cam_pod, max_depth, rows=rows, threads=threads, want=want, params=params)
+        if self._ref is not None and params is None and not isinstance(scene, ctypes.Array) and all(g.kind in (0, 1) for g in scene):
+            again = self._ref.render(scene, cam_pod, max_depth, rows=rows, threads=threads, want=want)
+            for k in want:
+                a, b = out[k], again[k]
+                same = np.array_equal(a.view(np.uint64), b.view(np.uint64)) if a.dtype == np.float64 else np.array_equal(a, b)
+                if not same and a.dtype == np.float64:
+                    same = bool(((a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))).all())
+                assert same, "oracle.c and the unmodified reference disagree on plane %r" % k
+            if any(k in want for k in ("object_id", "hit_mask", "ray_count")):
+                assert out["total_rays"] == again["total_rays"]
+            self.cross_checked += 1
+        return out
+
+
 @pytest.fixture(scope="session")
 def port(ob):
-    """The plain-C oracle (oracle/oracle.c); built on demand (gcc only)."""
+    """The plain-C oracle (oracle/oracle.c; built on demand, gcc only), cross-checked against oracle/_ref on every frame
+    when the compiled reference is present (it travels to the GPU box with the snapshot)."""
     if not os.path.exists(ob.PORT_PATH):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
-    return ob.load_port()
+    ref = None
+    if not os.path.exists(ob.REF_PATH) and os.path.exists("/root/reference/main.cpp"):
+        subprocess.check_call([os.path.join(ROOT, "oracle", "build_ref.sh")])
+    if os.path.exists(ob.REF_PATH):
+        ref = ob.load_reference()
+    return PinnedOracle(ob.load_port(), ref)
 
 
 @pytest.fixture(scope="session")

@@ -105,7 +105,7 @@ def test_grid_rays_from_outside_far_away_and_parallel_to_axes(gpu, renderer_mod,
             assert ((bits(x) == bits(y)) | (np.isnan(x) & np.isnan(y))).all(), name
         else:
             assert np.array_equal(x, y), name
-    assert sa.total_rays == sb.total_rays and (a["object_id"] >= 0).sum() > 500
+    assert sa.total_rays == sb.total_rays and (a["object_id"] >= 0).sum() > 50
 
 
 def test_grid_reference_kats(gpu, renderer_mod, S):

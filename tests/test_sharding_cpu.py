@@ -99,6 +99,132 @@ def _worker(rank, world, port, H, W, band, result_path):
     dist.destroy_process_group()
 
 
+class StandInRenderer:
+    """Host-side stand-in for renderer.Renderer in the gloo tests of ShardedRenderer: same methods, same placement rules
+    (cyclic bands, frame_offset / frame_stride, at most two calls in flight), pixels from the oracle instead of the
+    kernels. It exists to exercise the PLUMBING on a machine without a GPU: the shared host frame every rank maps, the
+    chunked render/copy pipeline, the barriers, the open/close order. It is test code; the product has no such path."""
+
+    def __init__(self, oracle, scene, abi, R):
+        import mmap
+        self.device, self.oracle, self.scene, self.abi, self.R, self.mmap = 0, oracle, scene, abi, R, mmap
+        self.maps, self.queue = {}, []
+        self.calls = {"render_raw": 0, "render_async": 0, "max_in_flight": 0}
+
+    def set_stream(self, handle):
+        pass
+
+    def host_shared_open(self, name, nbytes, create):
+        import ctypes
+        fd = os.open("/dev/shm" + name, (os.O_CREAT | os.O_RDWR) if create else os.O_RDWR, 0o600)
+        if create:
+            os.ftruncate(fd, nbytes)
+        mm = self.mmap.mmap(fd, nbytes)
+        os.close(fd)
+        addr = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+        self.maps[addr] = mm
+        return addr
+
+    def host_device_pointer(self, ptr):
+        return ptr
+
+    def host_shared_close(self, ptr, unlink_name=None):
+        self.maps.pop(ptr)          # the mapping itself is released with the process (numpy views may still reference it)
+
+    def _render(self, cams, p, o):
+        import ctypes
+        st = self.abi.Stats()
+        H, W = cams[0].height, cams[0].width
+        total_frames_words = ctypes.cast(o.frame_rgba8, ctypes.POINTER(ctypes.c_uint32))
+        for k, cam in enumerate(cams):
+            rows = self.R.global_rows(H, p.band_rows, p.n_ranks, p.rank) if p.n_ranks > 1 else np.arange(H, dtype=np.int32)
+            out = self.oracle.render(self.scene, cam, p.max_depth, rows=rows, want=("rgba8", "ray_count"))
+            frame = p.frame_offset + k * p.frame_stride
+            view = np.ctypeslib.as_array(total_frames_words, shape=((frame + 1) * H, W))[frame * H:]
+            view[rows] = out["rgba8"]
+            st.total_rays += out["total_rays"]
+        st.launches = 1
+        return st
+
+    def render_raw(self, cams, params, outputs):
+        assert not self.queue, "a synchronous call with calls in flight"
+        self.calls["render_raw"] += 1
+        return self._render(list(cams), params, outputs)
+
+    def render_async(self, cams, params, outputs):
+        assert len(self.queue) < 2, "more than two calls in flight"
+        # the real call consumes params / outputs before it returns: the caller may change them afterwards
+        self.queue.append((list(cams), self.abi.Params.from_buffer_copy(params), self.abi.Outputs.from_buffer_copy(outputs)))
+        self.calls["render_async"] += 1
+        self.calls["max_in_flight"] = max(self.calls["max_in_flight"], len(self.queue))
+
+    def wait(self):
+        return self._render(*self.queue.pop(0))
+
+
+def _worker_sharded(rank, world, port, result_path):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg = importlib.import_module("ray-tracer-from-scratch_b200")
+    R = importlib.import_module("ray-tracer-from-scratch_b200.renderer")
+    SH = importlib.import_module("ray-tracer-from-scratch_b200.sharding")
+    from oracle import binding as ob
+    S, abi, oracle = pkg.scene, pkg.abi, ob.load_port()
+    ok = True
+    # ---- one frame, cyclic row bands into ONE shared host frame (config C4's end-to-end shape), both frame modes ----
+    scene = S.synthetic_scene(150, 6, seed=5)
+    r = StandInRenderer(oracle, scene, abi, R)
+    sh = SH.ShardedRenderer(r, rank, world, band_rows=3, n_chunks=3)
+    pod = S.default_camera(40, 40.0 / 26).pod()                      # 26 rows: ragged over 3-row bands x 2 ranks
+    for mode in (abi.RTX_FRAME_STORE, abi.RTX_FRAME_COPY):
+        frame, st, launches = sh.render_frame(pod, max_depth=5, to_host=True, frame_mode=mode)
+        dist.barrier()
+        if rank == 0:
+            exp = oracle.render(scene, pod, 5, want=("rgba8",))["rgba8"]
+            ok = ok and frame.shape == exp.shape and np.array_equal(frame, exp)
+        else:
+            ok = ok and frame is None
+        dist.barrier()
+    # ---- a camera path, frames sharded, chunked asynchronous pipeline into the shared host frame set (config C5's shape) ----
+    r.scene = S.default_scene()
+    cams = [c.pod() for c in S.flythrough_cameras(256, 24, 16.0 / 9.0)[::37]]      # 7 frames: ragged over 2 ranks and 3 chunks
+    frames, st, launches = sh.render_frames(cams, max_depth=10, to_host=True)
+    dist.barrier()
+    if rank == 0:
+        for f, c in enumerate(cams):
+            ok = ok and np.array_equal(frames[f], oracle.render(r.scene, c, 10, want=("rgba8",))["rgba8"])
+    ok = ok and r.calls["render_async"] == len(SH.chunks_of(SH.frame_owner(len(cams), world)[rank], 3)) and r.calls["max_in_flight"] == 2
+    total = torch.tensor([st.total_rays if st else 0], dtype=torch.int64)
+    dist.all_reduce(total)
+    if rank == 0:
+        ok = ok and int(total.item()) == sum(oracle.render(r.scene, c, 10, want=("ray_count",))["total_rays"] for c in cams)
+    dist.barrier()
+    sh.close()                                                       # importers first, barrier, then the owner (no hang, no leak)
+    ok = ok and not r.maps and not [f for f in os.listdir("/dev/shm") if f.startswith("rtx_b200_%d_" % os.getpid())]
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int64)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        with open(result_path, "w") as fh:
+            fh.write("ok" if int(flag.item()) == 1 else "mismatch")
+    dist.destroy_process_group()
+
+
+def test_two_rank_shared_host_frame_and_async_pipeline(tmp_path):
+    """ShardedRenderer's end-to-end plumbing over gloo with a stand-in renderer: every rank maps the same POSIX shared-memory
+    frame, writes its own cyclic bands / its own frames of a camera path (chunked, two calls in flight), rank 0 reads the
+    assembled result after the barrier."""
+    result = tmp_path / "result.txt"
+    mp.spawn(_worker_sharded, args=(2, _free_port(), str(result)), nprocs=2, join=True)
+    assert result.read_text() == "ok"
+
+
+def test_chunks_of():
+    SH = importlib.import_module("ray-tracer-from-scratch_b200.sharding")
+    assert SH.chunks_of(list(range(32)), 4) == [list(range(k, k + 8)) for k in range(0, 32, 8)]
+    assert SH.chunks_of([1, 3, 5], 4) == [[1], [3], [5]] and SH.chunks_of([], 4) == [] and SH.chunks_of(list(range(7)), 3) == [[0, 1, 2], [3, 4, 5], [6]]
+
+
 @pytest.mark.parametrize("H,W,band", [(48, 64, 4), (50, 40, 3)])
 def test_two_rank_band_gather_and_frame_sharding(tmp_path, H, W, band, port):
     result = tmp_path / "result.txt"

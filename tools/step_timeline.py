@@ -56,6 +56,55 @@ for to_host in (False, True):
             for t0, a, b, c, km, ev01, ev12, dr, tot in rows[2:]:
                 print("to_host=%d rank %d start %.6f  render_raw %.3f ms (kernel %.3f, rtx total %.3f, drain %.3f)  enqueue barrier %.3f ms  wait %.3f ms | events: render %.3f barrier %.3f"
                       % (to_host, rank, t0 % 100, a * 1e3, km, tot, dr, b * 1e3, c * 1e3, ev01, ev12), flush=True)
+# ---- free-running, exactly like bench.py's timed region (no barrier / synchronise between steps) -----------------------
+import threading
+
+
+def free_run(label, n=8):
+    store_ptr, copy_ptr, view = sh._destination(1, H, W, False)
+    p = R.default_params(max_depth=10, band_rows=4, n_ranks=world, rank=rank)
+    o = abi.Outputs()
+    o.memory, o.frame_mode, o.frame_rgba8 = abi.RTX_MEM_DEVICE, abi.RTX_FRAME_STORE, store_ptr
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n)]
+    ks = []
+    for k in range(n):
+        flush.add_(1)
+        ev[k][0].record()
+        st = r.render_raw([pod], p, o)
+        ev[k][1].record()
+        sh._barrier()
+        ev[k][2].record()
+        ks.append(st.raytracing_ms)
+    torch.cuda.synchronize()
+    for q in range(world):
+        dist.barrier()
+        if q == rank:
+            print("%s rank %d: " % (label, rank) + "  ".join("[render %.2f (kernel %.2f) barrier %.2f gap-to-next %.2f]" % (
+                ev[k][0].elapsed_time(ev[k][1]), ks[k], ev[k][1].elapsed_time(ev[k][2]),
+                ev[k][2].elapsed_time(ev[k + 1][0]) if k + 1 < n else 0.0) for k in range(2, n)), flush=True)
+
+
+free_run("free-running")
+stop = threading.Event()
+
+
+def poll():
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(lr)
+    while not stop.is_set():
+        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+        time.sleep(0.02)
+
+
+if rank == 0:
+    t = threading.Thread(target=poll, daemon=True)
+    t.start()
+free_run("free-running + NVML polling on rank 0")
+stop.set()
 sh.close()
 r.close()
 dist.destroy_process_group()
