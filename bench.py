@@ -432,7 +432,9 @@ class Arm:
             if world > 1:
                 dist.barrier()
             clocks = smp.stop() if smp else None
-            ms = sum(s.elapsed_time(e) for s, e in ev)
+            per_step = [s.elapsed_time(e) for s, e in ev]
+            ms = sum(per_step)
+            result["step_ms_rank0" + ("_e2e" if e2e else "")] = per_step
             t = torch.tensor([ms, float(rays), kernel_ms, float(launches)], dtype=torch.float64, device=dev)
             per_rank_kernel = [kernel_ms / n_steps]
             if world > 1:
@@ -478,6 +480,7 @@ class Arm:
         return dict(spec=spec, scene=scene, pods=pods, H=H, W=W, F=F, n_spheres=n_spheres, n_walls=len(scene) - n_spheres,
                     ms=ms, rays=rays, kernel_ms=kernel_ms, launches=launches, clocks=clocks, per_rank_kernel=per_rank_kernel,
                     ms_e=ms_e, rays_e=rays_e, launches_e=launches_e, steps=steps, e2e_steps=e2e_steps, drain=drain, parity=parity,
+                    step_ms=result.get("step_ms_rank0"), step_ms_e2e=result.get("step_ms_rank0_e2e"),
                     verified=verified, scene_bytes=len(scene) * ctypes.sizeof(abi.ObjectPOD), frame_bytes=H * W * 4 * F,
                     camera_bytes=ctypes.sizeof(abi.CameraPOD) * F,
                     e2e_path=("the trace kernel stores pixels straight into the pinned, mapped host frame (zero copy, RTX_FRAME_STORE / RTX_MEM_HOST_MAPPED)"
@@ -579,6 +582,7 @@ def main():
                     "h2d_bytes_per_step": world * m["scene_bytes"] + m["camera_bytes"] * (world if spec["name"] != "c5" else 1),
                     "d2h_bytes_per_step": m["frame_bytes"], "path": m["e2e_path"]},
             "parity": m["parity"],
+            "step_ms_rank0": m["step_ms"], "e2e_step_ms_rank0": m["step_ms_e2e"],
             "gpu_launches": launches,
             "clocks": m["clocks"],
         }
@@ -657,21 +661,27 @@ def main():
                     tot_ms += e0.elapsed_time(e1)
                     kern += st2.raytracing_ms
                 res[key] = {"ms_per_frame": tot_ms / 20, "mrays_s": st2.total_rays / (tot_ms / 20 * 1e-3) / 1e6, "kernel_ms": kern / 20}
-            # the same end-to-end work as a stream of frames: rtx_render_async keeps two frames in flight, so the read-back
-            # of frame k (copy stream) overlaps the scene upload + kernel of frame k+1 (each frame has its own host buffer)
-            host2b = torch.empty((pod2.height, pod2.width), dtype=torch.int32, pin_memory=True)
-            o_hostb = abi.Outputs()
-            o_hostb.memory, o_hostb.rgba8 = abi.RTX_MEM_HOST, host2b.data_ptr()
+            # the same end-to-end work as a stream of frames: rtx_render_async keeps three frames in flight, so the read-back
+            # of frame k (copy stream) overlaps the kernel of frame k+1 and the host's queueing of frame k+2
+            depth_q = abi.RTX_MAX_IN_FLIGHT
+            hosts = [host2] + [torch.empty((pod2.height, pod2.width), dtype=torch.int32, pin_memory=True) for _ in range(depth_q - 1)]
+            o_hosts = []
+            for h in hosts:
+                oh = abi.Outputs()
+                oh.memory, oh.rgba8 = abi.RTX_MEM_HOST, h.data_ptr()
+                o_hosts.append(oh)
+            host2b = hosts[1]
             n_stream = 64
             for rep in range(2):                                  # first pass warms up
                 flush.add_(1)
                 e0.record()
                 for k in range(n_stream):
                     r.set_scene(objs2)
-                    r.render_async([pod2], p2, o_host if k % 2 == 0 else o_hostb)
-                    if k >= 1:
+                    r.render_async([pod2], p2, o_hosts[k % depth_q])
+                    if k >= depth_q - 1:
                         st2 = r.wait()
-                st2 = r.wait()
+                for _ in range(depth_q - 1):
+                    st2 = r.wait()
                 e1.record()
                 e1.synchronize()
             ms_stream = e0.elapsed_time(e1) / n_stream
@@ -681,14 +691,15 @@ def main():
                 e0.record()
                 for k in range(n_stream):
                     r.render_async([pod2], p2, o_dev)
-                    if k >= 1:
+                    if k >= depth_q - 1:
                         st2 = r.wait()
-                st2 = r.wait()
+                for _ in range(depth_q - 1):
+                    st2 = r.wait()
                 e1.record()
                 e1.synchronize()
             ms_dstream = e0.elapsed_time(e1) / n_stream
             res["device_stream"] = {"ms_per_frame": ms_dstream, "mrays_s": st2.total_rays / (ms_dstream * 1e-3) / 1e6, "frames": n_stream,
-                                    "frames_in_flight": 2, "api": "rtx_render_async + rtx_wait"}
+                                    "frames_in_flight": depth_q, "api": "rtx_render_async + rtx_wait"}
             # the PCIe read-back of one frame alone (pinned memory): the floor of any host-facing 1080p frame on this box
             ts = []
             for _ in range(8):
@@ -700,7 +711,7 @@ def main():
             d2h_ms = sorted(ts)[len(ts) // 2]
             res["d2h_copy_alone"] = {"ms": d2h_ms, "gbs": dev2.numel() * 4 / (d2h_ms * 1e-3) / 1e9}
             res["e2e_stream"] = {"ms_per_frame": ms_stream, "mrays_s": st2.total_rays / (ms_stream * 1e-3) / 1e6, "frames": n_stream,
-                                 "frames_in_flight": 2, "api": "rtx_render_async + rtx_wait"}
+                                 "frames_in_flight": depth_q, "api": "rtx_render_async + rtx_wait"}
             import numpy as np
             par2 = parity_check(spec2, {"device frame": dev2.cpu().numpy().view(np.uint32), "host frame (e2e)": host2.numpy().view(np.uint32),
                                         "host frame (e2e_stream)": host2b.numpy().view(np.uint32)})

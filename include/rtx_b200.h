@@ -166,6 +166,8 @@ typedef struct rtx_params {
 
 #define RTX_MAX_DEPTH 254     /* ray_count is a uint8: depth+1 rays per pixel at most */
 
+#define RTX_MAX_IN_FLIGHT 3
+
 #define RTX_FRAME_STORE 0
 #define RTX_FRAME_COPY  1
 
@@ -280,9 +282,10 @@ int rtx_render(rtx_ctx* ctx, const rtx_camera* cameras, int32_t n_frames,
 
 /* The same call without the wait: everything (camera upload, kernels, read-back) is queued and the call returns.
  * rtx_wait blocks until the OLDEST call in flight on this context has completed and yields its stats; until then
- * the caller must not touch that call's outputs. At most two calls may be in flight per context (each owns its own
- * staging buffers): with host outputs, frame k crosses PCIe on the context's copy stream while the kernel of frame
- * k+1 runs — the per-call latency of small frames (host launch path + read-back) overlaps instead of adding up.
+ * the caller must not touch that call's outputs. At most RTX_MAX_IN_FLIGHT calls may be in flight per context (each
+ * owns its own staging buffers): with host outputs, frame k crosses PCIe on the context's copy stream while the kernel
+ * of frame k+1 runs and the host queues frame k+2 — the per-call latency of small frames (host launch path, kernel,
+ * read-back) overlaps instead of adding up; a further call before rtx_wait is refused with RTX_ERR_INVALID.
  * A synchronous rtx_render first completes the calls in flight (their stats are dropped). */
 int rtx_render_async(rtx_ctx* ctx, const rtx_camera* cameras, int32_t n_frames,
                      const rtx_params* params, const rtx_outputs* outputs);

@@ -15,6 +15,7 @@ RTX_TONEMAP_NONE, RTX_TONEMAP_REINHARD = 0, 1    # extension, see the header
 RTX_MEM_HOST, RTX_MEM_DEVICE, RTX_MEM_HOST_MAPPED = 0, 1, 2
 RTX_FRAME_STORE, RTX_FRAME_COPY = 0, 1
 RTX_MAX_DEPTH = 254
+RTX_MAX_IN_FLIGHT = 3
 
 
 class Vec3(C.Structure):

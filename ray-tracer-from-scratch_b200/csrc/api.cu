@@ -21,7 +21,7 @@ using namespace rtx;
 constexpr int kRanges = 4;                        // pixel ranges of a small-scene frame rendered into host memory
 constexpr size_t kRangedMinPixels = 1u << 17;     // below this a frame is one launch and one copy
 constexpr int kPlanes = 8;                        // rgba8, radiance f32, radiance f64, object id, hit mask, ray count, hit distance, hit normal
-constexpr int kSlots = 2;                         // calls in flight per context (rtx_render_async)
+constexpr int kSlots = RTX_MAX_IN_FLIGHT;         // calls in flight per context (rtx_render_async)
 
 // Everything ONE call in flight owns: pinned + device copies of its cameras / rays, its counters, its device staging
 // for host outputs and its events. Two slots let frame k's read-back overlap frame k+1's kernel (rtx_render_async).

@@ -230,7 +230,8 @@ class Renderer:
         return st
 
     def render_async(self, cams, params, outputs):
-        """rtx_render_async: queues the call and returns; wait() completes the oldest call in flight (at most two)."""
+        """rtx_render_async: queues the call and returns; wait() completes the oldest call in flight (at most
+        abi.RTX_MAX_IN_FLIGHT)."""
         arr = (abi.CameraPOD * len(cams))(*cams)
         self._check(self.lib.rtx_render_async(self._ctx, arr, len(cams), C.byref(params), C.byref(outputs)))
 

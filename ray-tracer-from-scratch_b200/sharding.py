@@ -296,7 +296,7 @@ class ShardedRenderer:
             o.frame_mode, o.frame_rgba8 = abi.RTX_FRAME_COPY, copy_ptr
             in_flight = 0
             for frames in chunks_of(mine, self.n_chunks):
-                if in_flight == 2:
+                if in_flight == abi.RTX_MAX_IN_FLIGHT:
                     total = _add_stats(total, self.r.wait())
                     in_flight -= 1
                 params.frame_offset = frames[0]              # frame k of this call is global frame frames[0] + k * world

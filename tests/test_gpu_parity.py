@@ -589,8 +589,8 @@ def test_mapped_host_surface_equals_staged_path(gpu, renderer_mod, port, S):
 
 
 def test_async_frames_in_flight_equal_synchronous_frames(gpu, renderer_mod, port, S):
-    """rtx_render_async / rtx_wait: two frames in flight, host and device outputs, stats returned in order; a third call
-    without a wait is refused; a synchronous call drains what is in flight."""
+    """rtx_render_async / rtx_wait: RTX_MAX_IN_FLIGHT frames in flight, host and device outputs, stats returned in order; one
+    call more without a wait is refused; a synchronous call drains what is in flight."""
     import torch
     abi = renderer_mod.abi
     scene = S.default_scene()
@@ -605,26 +605,32 @@ def test_async_frames_in_flight_equal_synchronous_frames(gpu, renderer_mod, port
         o.memory, o.rgba8 = abi.RTX_MEM_HOST, h.ctypes.data
         outs.append(o)
     stats = []
+    depth = abi.RTX_MAX_IN_FLIGHT
+    assert len(cams) > depth
     for k, c in enumerate(cams):
         gpu.render_async([c], p, outs[k])
-        if k >= 1:
+        if k >= depth - 1:
             stats.append(gpu.wait())
-    stats.append(gpu.wait())
+    for _ in range(depth - 1):
+        stats.append(gpu.wait())
     for k in range(len(cams)):
         assert np.array_equal(host[k], exp[k]["rgba8"]), k
         assert stats[k].total_rays == int(exp[k]["ray_count"].astype(np.int64).sum()), k
     with pytest.raises(renderer_mod.RtxError):
         gpu.wait()                                             # nothing in flight
-    gpu.render_async([cams[0]], p, outs[0])
-    gpu.render_async([cams[1]], p, outs[1])
+    for h in host:
+        h[:] = 0
+    for k in range(depth):
+        gpu.render_async([cams[k]], p, outs[k])
     with pytest.raises(renderer_mod.RtxError):
-        gpu.render_async([cams[2]], p, outs[2])                # a third call in flight is refused
-    dev = torch.zeros((cams[2].height, cams[2].width), dtype=torch.int32, device="cuda")
+        gpu.render_async([cams[depth]], p, outs[depth])        # one more call in flight is refused
+    dev = torch.zeros((cams[depth].height, cams[depth].width), dtype=torch.int32, device="cuda")
     o = abi.Outputs()
     o.memory, o.rgba8 = abi.RTX_MEM_DEVICE, dev.data_ptr()
-    st = gpu.render_raw([cams[2]], p, o)                       # synchronous: completes the two in flight first
-    assert np.array_equal(dev.cpu().numpy().view(np.uint32), exp[2]["rgba8"]) and st.total_rays == stats[2].total_rays
-    assert np.array_equal(host[0], exp[0]["rgba8"]) and np.array_equal(host[1], exp[1]["rgba8"])
+    st = gpu.render_raw([cams[depth]], p, o)                   # synchronous: completes the calls in flight first
+    assert np.array_equal(dev.cpu().numpy().view(np.uint32), exp[depth]["rgba8"]) and st.total_rays == stats[depth].total_rays
+    for k in range(depth):
+        assert np.array_equal(host[k], exp[k]["rgba8"]), k
     with pytest.raises(renderer_mod.RtxError):
         gpu.wait()
 

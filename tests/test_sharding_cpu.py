@@ -101,7 +101,7 @@ def _worker(rank, world, port, H, W, band, result_path):
 
 class StandInRenderer:
     """Host-side stand-in for renderer.Renderer in the gloo tests of ShardedRenderer: same methods, same placement rules
-    (cyclic bands, frame_offset / frame_stride, at most two calls in flight), pixels from the oracle instead of the
+    (cyclic bands, frame_offset / frame_stride, at most RTX_MAX_IN_FLIGHT calls in flight), pixels from the oracle instead of the
     kernels. It exists to exercise the PLUMBING on a machine without a GPU: the shared host frame every rank maps, the
     chunked render/copy pipeline, the barriers, the open/close order. It is test code; the product has no such path."""
 
@@ -152,7 +152,7 @@ class StandInRenderer:
         return self._render(list(cams), params, outputs)
 
     def render_async(self, cams, params, outputs):
-        assert len(self.queue) < 2, "more than two calls in flight"
+        assert len(self.queue) < self.abi.RTX_MAX_IN_FLIGHT, "too many calls in flight"
         # the real call consumes params / outputs before it returns: the caller may change them afterwards
         self.queue.append((list(cams), self.abi.Params.from_buffer_copy(params), self.abi.Outputs.from_buffer_copy(outputs)))
         self.calls["render_async"] += 1
@@ -194,7 +194,7 @@ def _worker_sharded(rank, world, port, result_path):
     if rank == 0:
         for f, c in enumerate(cams):
             ok = ok and np.array_equal(frames[f], oracle.render(r.scene, c, 10, want=("rgba8",))["rgba8"])
-    ok = ok and r.calls["render_async"] == len(SH.chunks_of(SH.frame_owner(len(cams), world)[rank], 3)) and r.calls["max_in_flight"] == 2
+    ok = ok and r.calls["render_async"] == len(SH.chunks_of(SH.frame_owner(len(cams), world)[rank], 3)) and r.calls["max_in_flight"] == min(abi.RTX_MAX_IN_FLIGHT, r.calls["render_async"])
     total = torch.tensor([st.total_rays if st else 0], dtype=torch.int64)
     dist.all_reduce(total)
     if rank == 0:
@@ -212,7 +212,7 @@ def _worker_sharded(rank, world, port, result_path):
 
 def test_two_rank_shared_host_frame_and_async_pipeline(tmp_path):
     """ShardedRenderer's end-to-end plumbing over gloo with a stand-in renderer: every rank maps the same POSIX shared-memory
-    frame, writes its own cyclic bands / its own frames of a camera path (chunked, two calls in flight), rank 0 reads the
+    frame, writes its own cyclic bands / its own frames of a camera path (chunked, several calls in flight), rank 0 reads the
     assembled result after the barrier."""
     result = tmp_path / "result.txt"
     mp.spawn(_worker_sharded, args=(2, _free_port(), str(result)), nprocs=2, join=True)
