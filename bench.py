@@ -675,16 +675,19 @@ def main():
             for rep in range(2):                                  # first pass warms up
                 flush.add_(1)
                 e0.record()
+                stage = [0.0, 0.0, 0.0, 0.0]
                 for k in range(n_stream):
                     r.set_scene(objs2)
                     r.render_async([pod2], p2, o_hosts[k % depth_q])
                     if k >= depth_q - 1:
                         st2 = r.wait()
+                        stage = [a + b for a, b in zip(stage, (st2.h2d_ms, st2.raytracing_ms, st2.d2h_ms, st2.total_ms))]
                 for _ in range(depth_q - 1):
                     st2 = r.wait()
                 e1.record()
                 e1.synchronize()
             ms_stream = e0.elapsed_time(e1) / n_stream
+            stage = [x / (n_stream - depth_q + 1) for x in stage]
             # ... and the device-resident frame as a stream (no host wait between frames: launch latency overlaps the kernel)
             for rep in range(2):
                 flush.add_(1)
@@ -699,7 +702,8 @@ def main():
                 e1.synchronize()
             ms_dstream = e0.elapsed_time(e1) / n_stream
             res["device_stream"] = {"ms_per_frame": ms_dstream, "mrays_s": st2.total_rays / (ms_dstream * 1e-3) / 1e6, "frames": n_stream,
-                                    "frames_in_flight": depth_q, "api": "rtx_render_async + rtx_wait"}
+                                    "frames_in_flight": depth_q, "api": "rtx_render_async + rtx_wait",
+                                 "per_frame_device_stages_ms": {"h2d": stage[0], "kernel": stage[1], "kernel_end_to_readback_end": stage[2], "first_to_last_event": stage[3]}}
             # the PCIe read-back of one frame alone (pinned memory): the floor of any host-facing 1080p frame on this box
             ts = []
             for _ in range(8):
@@ -711,7 +715,8 @@ def main():
             d2h_ms = sorted(ts)[len(ts) // 2]
             res["d2h_copy_alone"] = {"ms": d2h_ms, "gbs": dev2.numel() * 4 / (d2h_ms * 1e-3) / 1e9}
             res["e2e_stream"] = {"ms_per_frame": ms_stream, "mrays_s": st2.total_rays / (ms_stream * 1e-3) / 1e6, "frames": n_stream,
-                                 "frames_in_flight": depth_q, "api": "rtx_render_async + rtx_wait"}
+                                 "frames_in_flight": depth_q, "api": "rtx_render_async + rtx_wait",
+                                 "per_frame_device_stages_ms": {"h2d": stage[0], "kernel": stage[1], "kernel_end_to_readback_end": stage[2], "first_to_last_event": stage[3]}}
             import numpy as np
             par2 = parity_check(spec2, {"device frame": dev2.cpu().numpy().view(np.uint32), "host frame (e2e)": host2.numpy().view(np.uint32),
                                         "host frame (e2e_stream)": host2b.numpy().view(np.uint32)})

@@ -21,6 +21,7 @@ using namespace rtx;
 constexpr int kRanges = 4;                        // pixel ranges of a small-scene frame rendered into host memory
 constexpr size_t kRangedMinPixels = 1u << 17;     // below this a frame is one launch and one copy
 constexpr int kPlanes = 8;                        // rgba8, radiance f32, radiance f64, object id, hit mask, ray count, hit distance, hit normal
+constexpr size_t kSmallUploadBytes = 64 << 10;    // uploads up to this size go through a kernel, not a copy engine (aux_kernels.cu)
 constexpr int kSlots = RTX_MAX_IN_FLIGHT;         // calls in flight per context (rtx_render_async)
 
 // Everything ONE call in flight owns: pinned + device copies of its cameras / rays, its counters, its device staging
@@ -70,6 +71,8 @@ struct rtx_ctx {
     GridDev grid = {};
     void* d_grid_blob = nullptr;
     size_t grid_blob_cap = 0;
+    void* d_tail_scratch = nullptr;    // trace_kernel's tail rebalance: chain records of every CTA (allocated with the first big scene)
+    size_t tail_scratch_cap = 0;
 
     Slot slot[kSlots];
     int next_slot = 0;                 // slot the next call takes
@@ -252,6 +255,7 @@ void rtx_destroy(rtx_ctx* ctx)
     if (ctx->d_rad_scratch) cudaFree(ctx->d_rad_scratch);
     if (ctx->d_tm_sums) cudaFree(ctx->d_tm_sums);
     if (ctx->d_grid_blob) cudaFree(ctx->d_grid_blob);
+    if (ctx->d_tail_scratch) cudaFree(ctx->d_tail_scratch);
     for (auto& m : ctx->shared_host) {
         cudaHostUnregister(m.first);
         munmap(m.first, m.second);
@@ -389,7 +393,7 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
         ctx->h_scene_blob = nullptr;
         ctx->h_scene_blob_cap = 0;
         const size_t cap = std::max<size_t>(off, 1 << 16);
-        if (cudaHostAlloc(&ctx->h_scene_blob, cap, cudaHostAllocDefault) != cudaSuccess)
+        if (cudaHostAlloc(&ctx->h_scene_blob, cap, cudaHostAllocMapped) != cudaSuccess)
             return fail(ctx, RTX_ERR_NOMEM, "rtx_set_scene: pinned staging");
         ctx->h_scene_blob_cap = cap;
     } else {
@@ -417,7 +421,8 @@ int rtx_set_scene(rtx_ctx* ctx, const rtx_object* objects, int32_t n)
         if (e != cudaSuccess) return fail(ctx, RTX_ERR_NOMEM, std::string("cudaMalloc(scene): ") + cudaGetErrorString(e));
         ctx->scene_blob_cap = off;
     }
-    RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_scene_blob, blob, off, cudaMemcpyHostToDevice, ctx->stream));
+    if (off <= kSmallUploadBytes) RTX_CUDA(ctx, launch_small_upload(ctx->d_scene_blob, blob, off, ctx->stream));
+    else RTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_scene_blob, blob, off, cudaMemcpyHostToDevice, ctx->stream));
     RTX_CUDA(ctx, cudaEventRecord(ctx->ev_scene, ctx->stream));
     unsigned char* base = static_cast<unsigned char*>(ctx->d_scene_blob);
     SceneDev& s = ctx->scene;
@@ -772,8 +777,9 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
         sl.h_cameras = nullptr;
         sl.cameras_cap = 0;
         const int cap = std::max(n_frames, 16);
-        if (cudaMalloc(&sl.d_cameras, sizeof(rtx_camera) * cap) != cudaSuccess ||
-            cudaHostAlloc(&sl.h_cameras, sizeof(rtx_camera) * cap, cudaHostAllocDefault) != cudaSuccess)
+        // one spare element: the kernel-side upload moves whole 16-byte words (sizeof(rtx_camera) = 104)
+        if (cudaMalloc(&sl.d_cameras, sizeof(rtx_camera) * (cap + 1)) != cudaSuccess ||
+            cudaHostAlloc(&sl.h_cameras, sizeof(rtx_camera) * (cap + 1), cudaHostAllocMapped) != cudaSuccess)
             return fail(ctx, RTX_ERR_NOMEM, W_ + ": camera buffers");
         sl.cameras_cap = cap;
     }
@@ -785,7 +791,7 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
         sl.rays_cap = 0;
         const size_t cap = std::max<size_t>(n_rays, 256);
         if (cudaMalloc(&sl.d_rays, sizeof(rtx_ray) * cap) != cudaSuccess ||
-            cudaHostAlloc(&sl.h_rays, sizeof(rtx_ray) * cap, cudaHostAllocDefault) != cudaSuccess)
+            cudaHostAlloc(&sl.h_rays, sizeof(rtx_ray) * cap, cudaHostAllocMapped) != cudaSuccess)
             return fail(ctx, RTX_ERR_NOMEM, W_ + ": ray buffers");
         sl.rays_cap = cap;
     }
@@ -834,6 +840,10 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
         }
     }
 
+    if (ctx->scene.n_entries > kSmallSceneEntries) {
+        int rc = grow(ctx, &ctx->d_tail_scratch, &ctx->tail_scratch_cap, static_cast<size_t>(ctx->n_sms) * kTailScratchBytesPerCta);
+        if (rc != RTX_OK) return rc;
+    }
     const bool use_grid = p.accel == RTX_ACCEL_GRID && ctx->scene.n_entries > kSmallSceneEntries;
     if (use_grid) {
         int rc = ensure_grid(ctx);
@@ -884,6 +894,7 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
     a.frame_offset = p.frame_offset;
     a.frame_stride = p.frame_stride;
     a.counters = sl.d_counters;
+    a.tail_scratch = ctx->d_tail_scratch;
     a.use_grid = use_grid ? 1 : 0;
     if (use_grid) a.grid = ctx->grid;
 
@@ -902,10 +913,15 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
 
     int launches = 0;
     RTX_ENQ(cudaEventRecord(sl.ev[0], st));
-    if (ray_mode) RTX_ENQ(cudaMemcpyAsync(sl.d_rays, sl.h_rays, sizeof(rtx_ray) * n_rays, cudaMemcpyHostToDevice, st));
-    else RTX_ENQ(cudaMemcpyAsync(sl.d_cameras, sl.h_cameras, sizeof(rtx_camera) * n_frames, cudaMemcpyHostToDevice, st));
-    // counters: [0..3] = 0, [4..6] = ~0 (atomicMin slots), [7] = 0 — one copy from a pinned template
-    RTX_ENQ(cudaMemcpyAsync(sl.d_counters, sl.h_counters + 8, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    {
+        void* d_in = ray_mode ? static_cast<void*>(sl.d_rays) : static_cast<void*>(sl.d_cameras);
+        const void* h_in = ray_mode ? static_cast<const void*>(sl.h_rays) : static_cast<const void*>(sl.h_cameras);
+        const size_t in_bytes = ray_mode ? sizeof(rtx_ray) * static_cast<size_t>(n_rays) : sizeof(rtx_camera) * static_cast<size_t>(n_frames);
+        if (in_bytes <= kSmallUploadBytes) RTX_ENQ(launch_small_upload(d_in, h_in, in_bytes, st));      // no copy engine: see aux_kernels.cu
+        else RTX_ENQ(cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, st));
+    }
+    // counters: [0..3] = 0, [4..6] = ~0 (atomicMin slots), [7] = 0
+    RTX_ENQ(launch_reset_counters(sl.d_counters, 0ull, true, st));
     RTX_ENQ(cudaEventRecord(sl.ev[1], st));
     // A small scene rendered into HOST memory is bound by the PCIe read-back, not by the kernel (1080p: 0.08 ms of
     // tracing, 0.15 ms of copy): trace the frame as kRanges consecutive pixel ranges and copy each finished range on a
@@ -918,10 +934,7 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
             const size_t p0 = (n_px * c / kRanges) & ~static_cast<size_t>(3), p1 = c + 1 == kRanges ? n_px : (n_px * (c + 1) / kRanges) & ~static_cast<size_t>(3);
             a.pixel_begin = p0;
             a.pixel_end = p1;
-            if (c > 0) {   // the pixel pool of this launch starts at p0 (range 0 starts at the template's 0)
-                sl.h_counters[16 + c] = p0;
-                RTX_ENQ(cudaMemcpyAsync(sl.d_counters, sl.h_counters + 16 + c, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-            }
+            if (c > 0) RTX_ENQ(launch_reset_counters(sl.d_counters, p0, false, st));   // the pixel pool of this launch starts at p0
             RTX_ENQ(launch_trace(a, ctx->n_sms, st, &launches, &ctx->launch_state));
             RTX_ENQ(cudaEventRecord(sl.ev_range[c], st));
         }

@@ -145,6 +145,39 @@ cudaError_t launch_quantise_f32(const float* rad, int64_t n_pixels, int mode, ui
     return cudaGetLastError();
 }
 
+// ---- small uploads without the copy engine ---------------------------------------------------------------------------
+// Scene blob, cameras and the counter reset of a call are a few hundred bytes. As cudaMemcpyAsync they queue on a copy
+// engine — behind the 8 MB read-back of the PREVIOUS frame when frames are streamed (rtx_render_async): measured 96 us of
+// stall per 1080p frame in front of an 80 us kernel. A one-CTA kernel that reads the pinned, mapped staging buffer over
+// PCIe has no such queue.
+__global__ void __launch_bounds__(256) small_upload_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src_host, int n16)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src_host[i];
+}
+
+cudaError_t launch_small_upload(void* dst, const void* src_host_mapped, size_t bytes, cudaStream_t stream)
+{
+    const int n16 = static_cast<int>((bytes + 15) / 16);       // both buffers are allocated in multiples of 16 bytes
+    if (n16 <= 0) return cudaSuccess;
+    const int blocks = n16 > 256 * 8 ? 8 : (n16 + 255) / 256;
+    small_upload_kernel<<<blocks, 256, 0, stream>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src_host_mapped), n16);
+    return cudaGetLastError();
+}
+
+// counters of a call: [0] = first pixel of the launch, [1..3] = 0, [4..6] = ~0 (atomicMin slots), [7] = 0
+__global__ void reset_counters_kernel(unsigned long long* counters, unsigned long long first_pixel, int all)
+{
+    const int k = threadIdx.x;
+    if (k == 0) counters[0] = first_pixel;
+    else if (all && k < 8) counters[k] = (k >= 4 && k <= 6) ? ~0ull : 0ull;
+}
+
+cudaError_t launch_reset_counters(unsigned long long* counters, unsigned long long first_pixel, bool all, cudaStream_t stream)
+{
+    reset_counters_kernel<<<1, 8, 0, stream>>>(counters, first_pixel, all ? 1 : 0);
+    return cudaGetLastError();
+}
+
 // ---- multi-GPU epilogue ----------------------------------------------------------------------------------
 // dst row i lives in band b = i / band_rows, owned by rank b % n_ranks, at packed local row
 // (b / n_ranks) * band_rows + i % band_rows of that rank's block.

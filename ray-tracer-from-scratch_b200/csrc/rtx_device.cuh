@@ -141,7 +141,10 @@ struct TraceArgs {
     // counters: [0] next pixel, [1] total rays, [2] over-range pixels, [3] max luminance (double bits),
     // [4] kernel start, [5] pixel pool empty, [6] first warp exit, [7] last warp exit (globaltimer ns; [4..6] start at ~0)
     unsigned long long* counters;
+    void* tail_scratch;                // trace_kernel: n_sms * 1024 chain records of 104 B for the tail rebalance (may be null: off)
 };
+
+constexpr size_t kTailScratchBytesPerCta = 1024 * 104;
 
 // Reference quantise, main.cpp:345: implicit double -> Uint8. g++ emits cvttsd2si (32-bit) and keeps the
 // low byte: truncation toward zero, wrap mod 256; NaN or |v| >= 2^31 give 0x80000000 -> byte 0.
@@ -215,6 +218,8 @@ cudaError_t launch_tonemap_sums(const float* rad32, const double* rad64, int64_t
 cudaError_t launch_tonemap_apply(const float* rad32, const double* rad64, int64_t pixels_per_frame, int n_frames, const long long* sums,
                                  int64_t pixels_global, double key, double white, int mode, uint32_t* rgba8, unsigned long long* counters,
                                  int n_sms, cudaStream_t stream);
+cudaError_t launch_small_upload(void* dst, const void* src_host_mapped, size_t bytes, cudaStream_t stream);
+cudaError_t launch_reset_counters(unsigned long long* counters, unsigned long long first_pixel, bool all, cudaStream_t stream);
 cudaError_t launch_unpermute(const void* band_major, void* row_major, int height, int width, int elem_bytes,
                              int band_rows, int n_ranks, int rows_per_rank, int n_sms, cudaStream_t stream);
 cudaError_t run_ffma_peak(int variant, int n_sms, cudaStream_t stream, double* tflops, double* mhz);

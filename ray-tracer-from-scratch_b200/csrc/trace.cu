@@ -78,6 +78,12 @@ __device__ __forceinline__ unsigned screen_pairs(const float2 (&cx)[kPairsPerIte
     float2 pu[kPairsPerIter], pv[kPairsPerIter], q[kPairsPerIter];
     const float2 ux = dup(k.ux), uy = dup(k.uy), nuo = dup(k.nuo);
     const float2 vx = dup(k.vx), vy = dup(k.vy), vz = dup(k.vz), nvo = dup(k.nvo);
+#ifndef RTX_SCREEN_ORDER
+#define RTX_SCREEN_ORDER 1
+#endif
+    // The ORDER of these loops does not change any value (every pu / pv / q is the same chain of operations); it only nudges
+    // ptxas' schedule and with it how many FFMA2 read five fresh registers (tools/sass_ffma2.py counts them).
+#if RTX_SCREEN_ORDER == 0
 #pragma unroll
     for (int u = 0; u < kPairsPerIter; u++) pv[u] = __ffma2_rn(cz[u], vz, nvo);
 #pragma unroll
@@ -92,6 +98,66 @@ __device__ __forceinline__ unsigned screen_pairs(const float2 (&cx)[kPairsPerIte
     for (int u = 0; u < kPairsPerIter; u++) q[u] = __ffma2_rn(pv[u], pv[u], nw[u]);
 #pragma unroll
     for (int u = 0; u < kPairsPerIter; u++) q[u] = __ffma2_rn(pu[u], pu[u], q[u]);
+#elif RTX_SCREEN_ORDER == 1
+#pragma unroll
+    for (int u = 0; u < kPairsPerIter; u++) pu[u] = __ffma2_rn(cy[u], uy, nuo);
+#pragma unroll
+    for (int u = 0; u < kPairsPerIter; u++) pv[u] = __ffma2_rn(cz[u], vz, nvo);
+#pragma unroll
+    for (int u = 0; u < kPairsPerIter; u++) pu[u] = __ffma2_rn(cx[u], ux, pu[u]);
+#pragma unroll
+    for (int u = 0; u < kPairsPerIter; u++) pv[u] = __ffma2_rn(cy[u], vy, pv[u]);
+#pragma unroll
+    for (int u = 0; u < kPairsPerIter; u++) pv[u] = __ffma2_rn(cx[u], vx, pv[u]);
+#pragma unroll
+    for (int u = 0; u < kPairsPerIter; u++) q[u] = __ffma2_rn(pv[u], pv[u], nw[u]);
+#pragma unroll
+    for (int u = 0; u < kPairsPerIter; u++) q[u] = __ffma2_rn(pu[u], pu[u], q[u]);
+#elif RTX_SCREEN_ORDER == 2
+#pragma unroll
+    for (int u = 0; u < kPairsPerIter; u++) {       // entry-major
+        pv[u] = __ffma2_rn(cz[u], vz, nvo);
+        pu[u] = __ffma2_rn(cy[u], uy, nuo);
+        pv[u] = __ffma2_rn(cy[u], vy, pv[u]);
+        pu[u] = __ffma2_rn(cx[u], ux, pu[u]);
+        pv[u] = __ffma2_rn(cx[u], vx, pv[u]);
+        q[u] = __ffma2_rn(pv[u], pv[u], nw[u]);
+        q[u] = __ffma2_rn(pu[u], pu[u], q[u]);
+    }
+#elif RTX_SCREEN_ORDER >= 10 && RTX_SCREEN_ORDER < 20
+    // all ten interleavings of the two dependent chains  pv: A1 = cz*vz+nvo, A2 = cy*vy+pv, A3 = cx*vx+pv  and
+    // pu: B1 = cy*uy+nuo, B2 = cx*ux+pu  (schedule search: tools/schedule_search.py)
+#define RTX_A1 _Pragma("unroll") for (int u = 0; u < kPairsPerIter; u++) pv[u] = __ffma2_rn(cz[u], vz, nvo);
+#define RTX_A2 _Pragma("unroll") for (int u = 0; u < kPairsPerIter; u++) pv[u] = __ffma2_rn(cy[u], vy, pv[u]);
+#define RTX_A3 _Pragma("unroll") for (int u = 0; u < kPairsPerIter; u++) pv[u] = __ffma2_rn(cx[u], vx, pv[u]);
+#define RTX_B1 _Pragma("unroll") for (int u = 0; u < kPairsPerIter; u++) pu[u] = __ffma2_rn(cy[u], uy, nuo);
+#define RTX_B2 _Pragma("unroll") for (int u = 0; u < kPairsPerIter; u++) pu[u] = __ffma2_rn(cx[u], ux, pu[u]);
+#if RTX_SCREEN_ORDER == 10
+    RTX_A1 RTX_A2 RTX_A3 RTX_B1 RTX_B2
+#elif RTX_SCREEN_ORDER == 11
+    RTX_A1 RTX_A2 RTX_B1 RTX_A3 RTX_B2
+#elif RTX_SCREEN_ORDER == 12
+    RTX_A1 RTX_A2 RTX_B1 RTX_B2 RTX_A3
+#elif RTX_SCREEN_ORDER == 13
+    RTX_A1 RTX_B1 RTX_A2 RTX_A3 RTX_B2
+#elif RTX_SCREEN_ORDER == 14
+    RTX_A1 RTX_B1 RTX_A2 RTX_B2 RTX_A3
+#elif RTX_SCREEN_ORDER == 15
+    RTX_A1 RTX_B1 RTX_B2 RTX_A2 RTX_A3
+#elif RTX_SCREEN_ORDER == 16
+    RTX_B1 RTX_A1 RTX_A2 RTX_A3 RTX_B2
+#elif RTX_SCREEN_ORDER == 17
+    RTX_B1 RTX_A1 RTX_A2 RTX_B2 RTX_A3
+#elif RTX_SCREEN_ORDER == 18
+    RTX_B1 RTX_A1 RTX_B2 RTX_A2 RTX_A3
+#elif RTX_SCREEN_ORDER == 19
+    RTX_B1 RTX_B2 RTX_A1 RTX_A2 RTX_A3
+#endif
+#pragma unroll
+    for (int u = 0; u < kPairsPerIter; u++) q[u] = __ffma2_rn(pv[u], pv[u], nw[u]);
+#pragma unroll
+    for (int u = 0; u < kPairsPerIter; u++) q[u] = __ffma2_rn(pu[u], pu[u], q[u]);
+#endif
     unsigned h = 0u;
 #pragma unroll
     for (int u = 0; u < kPairsPerIter; u++) {
@@ -309,8 +375,91 @@ __global__ void __launch_bounds__(kSmallThreads, RTX_SMALL_MINBLOCKS) trace_smal
     }
 }
 
+// ---- rebalancing the tail --------------------------------------------------------------------------------------------
+// tools/tail_trace.py: after the pixel pool runs dry a 4K frame still holds 0.25 ms of work per SM, yet the
+// last warp finishes 1.6 ms later — the chains that are left sit in the warps they started in, and a warp with 40 live
+// chains needs ten cooperative passes while its neighbours idle. So ONCE, when every warp of the CTA has found the pool dry,
+// the CTA deals its live chains out again: every live chain is written to a per-CTA scratch area in global memory (104 B:
+// ray, accumulated colour, weight, pixel, depth budget — the rest is recomputed per segment), and chain i is picked up by
+// warp i mod 16. After that every warp holds the same number of chains (±1) and carries on exactly as before (cooperative
+// scan, queue, exact tests, shading). Which lane traces a chain has no influence on any result.
+#ifndef RTX_TAIL_REBALANCE
+#define RTX_TAIL_REBALANCE 1
+#endif
+constexpr bool kTailRebalance = RTX_TAIL_REBALANCE != 0;      // 0: developer switch (round 1's tail)
+struct TailShared {
+    int arrived;          // warps of this CTA that have found the pixel pool dry
+    int cnt[kWarps];      // live chains per warp at the rebalance
+    int pad[3];
+};
+struct ChainDump {        // what survives between two segments of a chain
+    d3 o, d, acc;
+    double weight;
+    unsigned long long pixel;
+    int remaining, first_id, rays, pad;
+};
+static_assert(sizeof(ChainDump) == 104, "ChainDump layout");
+
+__device__ __forceinline__ void dump_chain(ChainDump* dst, const Chain& c)
+{
+    dst->o = c.o; dst->d = c.d; dst->acc = c.acc;
+    dst->weight = c.weight;
+    dst->pixel = c.pixel;
+    dst->remaining = c.remaining; dst->first_id = c.first_id; dst->rays = c.rays; dst->pad = 0;
+}
+
+__device__ __forceinline__ void load_chain(Chain& c, const ChainDump* src)
+{
+    c.o = src->o; c.d = src->d; c.acc = src->acc;
+    c.weight = src->weight;
+    c.pixel = src->pixel;
+    c.remaining = src->remaining; c.first_id = src->first_id; c.rays = src->rays;
+    c.active = 1;
+    c.qn = 0;
+}
+
+// Every thread of the CTA must call this once (it synchronises the CTA twice).
+#ifndef RTX_REBALANCE_INLINE
+#define RTX_REBALANCE_INLINE 0
+#endif
+#if RTX_REBALANCE_INLINE
+__device__ __forceinline__ void rebalance_tail(
+#else
+__device__ __noinline__ void rebalance_tail(
+#endif
+Chain (&ch)[kChains], TailShared* ts, ChainDump* scratch)
+{
+    const unsigned lane_id = threadIdx.x & 31u;
+    const int warp = threadIdx.x >> 5;
+    const unsigned below = (1u << lane_id) - 1u;
+    const unsigned m0 = __ballot_sync(kFull, ch[0].active), m1 = __ballot_sync(kFull, ch[1].active);
+    if (lane_id == 0) ts->cnt[warp] = __popc(m0) + __popc(m1);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) {
+        const int n = ts->cnt[w];
+        if (w < warp) base += n;
+        total += n;
+    }
+    if (ch[0].active) dump_chain(scratch + base + __popc(m0 & below), ch[0]);
+    if (ch[1].active) dump_chain(scratch + base + __popc(m0) + __popc(m1 & below), ch[1]);
+    ch[0].active = ch[1].active = 0;
+    __syncthreads();                       // the dumps are visible to the whole CTA
+#pragma unroll
+    for (int i = 0; i < kChains; i++) {
+        const int idx = i * kThreads + static_cast<int>(lane_id) * kWarps + warp;      // chain idx -> warp idx mod 16
+        if (idx < total) load_chain(ch[i], scratch + idx);
+    }
+}
+
+#ifdef RTX_MAXNREG
+#define RTX_KERNEL_BOUNDS __maxnreg__(RTX_MAXNREG)
+#else
+#define RTX_KERNEL_BOUNDS __launch_bounds__(kThreads, 1)
+#endif
 template <bool STREAM>
-__global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, const int tile_pairs)
+__global__ void RTX_KERNEL_BOUNDS trace_kernel(const TraceArgs a, const int tile_pairs, ChainDump* const tail_scratch)
 {
     extern __shared__ float4 s_tile[];
     const SceneDev& sc = a.scene;
@@ -324,6 +473,9 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
     const unsigned plane_bytes = static_cast<unsigned>(plane_pairs) * 16u;
 
     if (!STREAM) {
+        // behind the tile: one mailbox per warp (cooperative drain), then the bookkeeping of the tail rebalance
+        if (tail_scratch != nullptr && threadIdx.x == 0)
+            reinterpret_cast<TailShared*>(reinterpret_cast<Mailbox*>(s_tile + 2 * plane_pairs) + kWarps)->arrived = 0;
         fill_tile(s_tile, plane_pairs, sc.ent32, total_pairs, a.filter_eps);
         __syncthreads();
     }
@@ -336,7 +488,10 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
         ch[i].rays = 0;
     }
     FrameTotals tot{0ull, 0ull, 0.0};
-    bool pool_dry = false;             // warp-uniform: a fetch of this warp found the pixel pool empty
+    // warp-uniform: 0 = pixels left; 1 = a fetch of this warp found the pixel pool empty; 2 = ... and the warp has told the CTA;
+    // 3 = ... and the CTA's chains have been rebalanced (ONE variable on purpose: anything else that lives across the scan
+    // changes ptxas' schedule of the hot loop, see tools/sass_ffma2.py)
+    int pool_dry = 0;
     Mailbox* const mbox = reinterpret_cast<Mailbox*>(s_tile + 2 * plane_pairs) + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicMin(&a.counters[4], globaltimer_ns());   // kernel start
 
@@ -355,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
             if (lane_id == 0) base = atomicAdd(&a.counters[0], static_cast<unsigned long long>(n0 + n1));
             base = __shfl_sync(kFull, base, 0);
             const unsigned below = (1u << lane_id) - 1u;
-            if (base + n0 + n1 > total_pixels) pool_dry = true;
+            if (base + n0 + n1 > total_pixels && pool_dry == 0) pool_dry = 1;
             if (lane_id == 0 && base + n0 + n1 > total_pixels && base <= total_pixels) {  // this fetch emptied the pool
                 atomicMin(&a.counters[5], globaltimer_ns());
 #ifdef RTX_TAIL_TRACE
@@ -371,11 +526,27 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
                 if (p < total_pixels) start_pixel(ch[1], p, a);
             }
         }
-        const int any_active = ch[0].active | ch[1].active;
+        int any_active = ch[0].active | ch[1].active;
         if (STREAM) {
             if (!__syncthreads_or(any_active)) break;
         } else {
-            if (__ballot_sync(kFull, any_active) == 0u) break;
+            bool warp_done = __ballot_sync(kFull, any_active) == 0u;
+            if (tail_scratch != nullptr && (pool_dry == 1 || pool_dry == 2)) {
+                TailShared* const tail = reinterpret_cast<TailShared*>(mbox - (threadIdx.x >> 5) + kWarps);
+                if (pool_dry == 1) {
+                    pool_dry = 2;
+                    if (lane_id == 0) atomicAdd(&tail->arrived, 1);
+                }
+                // once EVERY warp of the CTA has found the pool dry, the live chains are dealt out evenly (once); a warp
+                // that has run out of chains waits for that, a warp that still has some keeps working until then
+                if (warp_done || *reinterpret_cast<volatile int*>(&tail->arrived) == kWarps) {
+                    rebalance_tail(ch, tail, tail_scratch + static_cast<size_t>(blockIdx.x) * (kThreads * kChains));
+                    pool_dry = 3;
+                    any_active = ch[0].active | ch[1].active;
+                    warp_done = __ballot_sync(kFull, any_active) == 0u;
+                }
+            }
+            if (warp_done) break;
         }
 
 #ifdef RTX_TAIL_TRACE
@@ -397,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a, c
             }
         } else {
             const unsigned m0 = __ballot_sync(kFull, ch[0].active), m1 = __ballot_sync(kFull, ch[1].active);
-            bool coop = kCoopMax > 0 && pool_dry && (__popc(m0) + __popc(m1)) <= kCoopMax;
+            bool coop = kCoopMax > 0 && pool_dry != 0 && (__popc(m0) + __popc(m1)) <= kCoopMax;
             if (coop) coop = !__any_sync(kFull, (ch[0].active && ch[0].fallback) || (ch[1].active && ch[1].fallback));
             if (coop) {
                 unsigned r0 = m0, r1 = m1;
@@ -508,10 +679,10 @@ cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, 
     constexpr int iter_bytes = kPairsPerIter * 32;
     const size_t mbox_bytes = sizeof(Mailbox) * kWarps;
     const size_t need = static_cast<size_t>(args.scene.n_entries_padded) * sizeof(float4);
-    const bool stream_tiles = need + mbox_bytes > static_cast<size_t>(kMaxSmemBytes);
+    const bool stream_tiles = need + mbox_bytes + sizeof(TailShared) > static_cast<size_t>(kMaxSmemBytes);
     const size_t tile_bytes = stream_tiles ? (static_cast<size_t>(kMaxSmemBytes) - mbox_bytes) / iter_bytes * iter_bytes : (need ? need : iter_bytes);
     const int tile_pairs = static_cast<int>(tile_bytes / 32);
-    const size_t smem = tile_bytes + mbox_bytes;
+    const size_t smem = tile_bytes + mbox_bytes + (stream_tiles ? 0 : sizeof(TailShared));
     unsigned long long total =
         static_cast<unsigned long long>(args.n_frames) * static_cast<unsigned long long>(args.local_rows) * args.width;
     if (total == 0) return cudaSuccess;
@@ -540,14 +711,14 @@ cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, 
             if (err != cudaSuccess) return err;
             smem_set[1] = smem;
         }
-        trace_kernel<true><<<static_cast<unsigned>(blocks), kThreads, smem, stream>>>(args, tile_pairs);
+        trace_kernel<true><<<static_cast<unsigned>(blocks), kThreads, smem, stream>>>(args, tile_pairs, nullptr);
     } else {
         if (smem > smem_set[0]) {
             err = cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             if (err != cudaSuccess) return err;
             smem_set[0] = smem;
         }
-        trace_kernel<false><<<static_cast<unsigned>(blocks), kThreads, smem, stream>>>(args, tile_pairs);
+        trace_kernel<false><<<static_cast<unsigned>(blocks), kThreads, smem, stream>>>(args, tile_pairs, kTailRebalance ? static_cast<ChainDump*>(args.tail_scratch) : nullptr);
     }
     if (launches) (*launches)++;
     return cudaGetLastError();

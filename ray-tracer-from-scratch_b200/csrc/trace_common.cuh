@@ -313,7 +313,9 @@ __device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, const S
     if (done) {
         const unsigned long long p = c.pixel;
         const uint32_t word = (a.rgba8 || a.frame_rgba8) ? pack_rgba(c.acc.x, c.acc.y, c.acc.z, a.quantise_mode) : 0u;
-        if (a.rgba8) a.rgba8[p] = word;
+        // finished pixels are write-once: streaming stores (evict-first) keep them from pushing the chains' local-memory
+        // lines out of L2 (ncu: 1.2 GB of DRAM writes per 8K frame with plain stores, the frame itself is 0.13 GB)
+        if (a.rgba8) __stcs(&a.rgba8[p], word);
         if (a.frame_rgba8) {
             // fused gather: store at the pixel's global position (possibly another GPU's memory, over NVLink)
             const unsigned long long frame_pixels = static_cast<unsigned long long>(a.local_rows) * a.width;
@@ -327,17 +329,17 @@ __device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, const S
                 grow = (lb * a.n_ranks + a.rank) * a.band_rows + (lrow - lb * a.band_rows);
             }
             const unsigned long long gframe = static_cast<unsigned long long>(a.frame_offset) + static_cast<unsigned long long>(frame) * a.frame_stride;
-            a.frame_rgba8[(gframe * a.height + grow) * a.width + col] = word;
+            __stcs(&a.frame_rgba8[(gframe * a.height + grow) * a.width + col], word);
         }
         if (a.rad64) {
-            a.rad64[3 * p + 0] = c.acc.x;
-            a.rad64[3 * p + 1] = c.acc.y;
-            a.rad64[3 * p + 2] = c.acc.z;
+            __stcs(&a.rad64[3 * p + 0], c.acc.x);
+            __stcs(&a.rad64[3 * p + 1], c.acc.y);
+            __stcs(&a.rad64[3 * p + 2], c.acc.z);
         }
         if (a.rad32) {
-            a.rad32[3 * p + 0] = static_cast<float>(c.acc.x);
-            a.rad32[3 * p + 1] = static_cast<float>(c.acc.y);
-            a.rad32[3 * p + 2] = static_cast<float>(c.acc.z);
+            __stcs(&a.rad32[3 * p + 0], static_cast<float>(c.acc.x));
+            __stcs(&a.rad32[3 * p + 1], static_cast<float>(c.acc.y));
+            __stcs(&a.rad32[3 * p + 2], static_cast<float>(c.acc.z));
         }
         if (a.object_id) a.object_id[p] = c.first_id;
         if (a.hit_mask) a.hit_mask[p] = c.first_id >= 0 ? 1 : 0;

@@ -3,7 +3,9 @@
 oracle. Ids, hit masks, ray counts and RGBA8 must be identical, radiance within 1e-12 relative.
 
     python tools/fuzz_parity.py [seconds=120] [seed=1]          (FUZZ_BIG=1: larger scenes and frames;
-                                                                 FUZZ_EXT=1: also the extensions — boxes and the sun)
+                                                                 FUZZ_EXT=1: also the extensions — boxes and the sun;
+                                                                 FUZZ_ACCEL=1: half of the cases through the uniform grid,
+                                                                 rtx_params.accel = RTX_ACCEL_GRID — same oracle, same bar)
 """
 import importlib
 import os
@@ -34,7 +36,7 @@ def random_scene(rng):
                  rng.uniform(0, 1), rng.choice([1, 2, 8, 50, 200.5]))
     for _ in range(n_s):
         c = (rng.uniform(-6, 12) * scale, rng.uniform(-8, 8) * scale, rng.uniform(-6, 6) * scale)
-        scene.append(S.Sphere(mat(), c, rng.choice([0.05, 0.3, 1.0, 2.5]) * scale * rng.uniform(0.5, 1.5)))
+        scene.append(S.Sphere(mat(), c, rng.choice([0.05, 0.3, 1.0, 2.5, 2.5, 60.0 if rng.random() < 0.02 else 0.3]) * scale * rng.uniform(0.5, 1.5)))
     for _ in range(n_w):
         p = (rng.uniform(-6, 12) * scale, rng.uniform(-8, 8) * scale, rng.uniform(-6, 6) * scale)
         n = (rng.uniform(-1, 1), rng.uniform(-1, 1), rng.choice([0.0, 0.0, rng.uniform(-1, 1)]))
@@ -93,10 +95,11 @@ def main():
             for k, v in ext.items():
                 setattr(p, k, type(getattr(p, k))(*v) if isinstance(v, tuple) else v)
             kw.update(ext)
+        accel = 1 if os.environ.get("FUZZ_ACCEL") == "1" and rng.random() < 0.5 else 0
         r.set_scene(scene)
-        got, st = r.render([pod], R.default_params(max_depth=depth, **kw), want=want)
+        got, st = r.render([pod], R.default_params(max_depth=depth, accel=accel, **kw), want=want)
         exp = oracle.render(scene, pod, params=p)
-        tag = "case %d: %d objs, scale %g, %dx%d, depth %d, %s" % (n, len(scene), scale, pod.width, pod.height, depth, kw)
+        tag = "case %d: %d objs, scale %g, %dx%d, depth %d, accel %d, %s" % (n, len(scene), scale, pod.width, pod.height, depth, accel, kw)
         for k, e in (("object_id", "object_id"), ("hit_mask", "hit_mask"), ("ray_count", "ray_count"), ("rgba8", "rgba8")):
             if not np.array_equal(got[k][0], exp[e]):
                 bad = np.argwhere(got[k][0] != exp[e])

@@ -8,7 +8,7 @@ import sys
 lib = sys.argv[1] if len(sys.argv) > 1 else "ray-tracer-from-scratch_b200/librtx_b200.so"
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 m = re.search(r"Function : _ZN3rtx12trace_kernelILb0.*?(?=Function : |\Z)", sass, re.S)
-ins = [(int(a, 16), t.strip()) for a, t in re.findall(r"/\*([0-9a-f]{4})\*/\s+(.*?);", m.group(0))]
+ins = [(int(a, 16), t.strip()) for a, t in re.findall(r"/\*([0-9a-f]{4,6})\*/\s+(.*?);", m.group(0))]
 idx = [i for i, (_, t) in enumerate(ins) if t.startswith("FFMA2")]
 hist, forms, prev = {}, {}, [None] * 3
 for _, t in ins[idx[0]: idx[-1] + 1]:
@@ -33,3 +33,22 @@ cyc = sum(max(2.0, k / 2.0) * v for k, v in hist.items())
 print("FFMA2 in hot loop: %d; fresh registers per FFMA2: avg %.2f, histogram %s" % (n, tot / n, dict(sorted(hist.items()))))
 print("operand forms (P = register pair, s = one register broadcast): %s" % forms)
 print("register-file model: %.1f cycles for %d FFMA2 (%.0f%% of the 2-cycle pipe rate)" % (cyc, n, 100 * 2 * n / cyc))
+
+# The innermost loop that holds the 84 FFMA2 of one hot-loop iteration (12 entries x 2 chains): its instruction count is the
+# canary for code-generation accidents — an unrelated change to the kernel once made ptxas re-load kernel parameters inside
+# this loop (184 -> 220 instructions, +2 % frame time).
+best = None
+for a, t in ins:
+    if "BRA" in t:
+        m2 = re.search(r"0x([0-9a-f]+)", t)
+        if m2 and int(m2.group(1), 16) < a:
+            body = [x for x in ins if int(m2.group(1), 16) <= x[0] <= a]
+            if sum(1 for x in body if x[1].startswith("FFMA2")) == 84 and (best is None or len(body) < len(best)):
+                best = body
+if best:
+    ops = {}
+    for _, t in best:
+        parts = t.split()
+        op = (parts[1] if parts[0].startswith("@") else parts[0]).split(".")[0]
+        ops[op] = ops.get(op, 0) + 1
+    print("hot loop: %d instructions per iteration: %s" % (len(best), dict(sorted(ops.items(), key=lambda kv: -kv[1]))))
