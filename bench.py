@@ -434,7 +434,15 @@ class Arm:
             clocks = smp.stop() if smp else None
             per_step = [s.elapsed_time(e) for s, e in ev]
             ms = sum(per_step)
-            result["step_ms_rank0" + ("_e2e" if e2e else "")] = per_step
+            tag = "_e2e" if e2e else ""
+            result["step_ms_rank0" + tag] = per_step
+            if world > 1:      # every rank's per-step times, for the record (the headline uses the slowest rank's total)
+                gaps = [ev[k][1].elapsed_time(ev[k + 1][0]) for k in range(n_steps - 1)] + [0.0]    # untimed: the L2 flush between steps
+                mine = torch.tensor(per_step + gaps, dtype=torch.float64, device=dev)
+                everyone = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(everyone, mine)
+                result["step_ms_per_rank" + tag] = [[round(x, 3) for x in t.tolist()[:n_steps]] for t in everyone]
+                result["gap_ms_per_rank" + tag] = [[round(x, 3) for x in t.tolist()[n_steps:-1]] for t in everyone]
             t = torch.tensor([ms, float(rays), kernel_ms, float(launches)], dtype=torch.float64, device=dev)
             per_rank_kernel = [kernel_ms / n_steps]
             if world > 1:
@@ -481,6 +489,8 @@ class Arm:
                     ms=ms, rays=rays, kernel_ms=kernel_ms, launches=launches, clocks=clocks, per_rank_kernel=per_rank_kernel,
                     ms_e=ms_e, rays_e=rays_e, launches_e=launches_e, steps=steps, e2e_steps=e2e_steps, drain=drain, parity=parity,
                     step_ms=result.get("step_ms_rank0"), step_ms_e2e=result.get("step_ms_rank0_e2e"),
+                    step_ms_per_rank=result.get("step_ms_per_rank"), step_ms_per_rank_e2e=result.get("step_ms_per_rank_e2e"),
+                    gap_ms_per_rank=result.get("gap_ms_per_rank"),
                     verified=verified, scene_bytes=len(scene) * ctypes.sizeof(abi.ObjectPOD), frame_bytes=H * W * 4 * F,
                     camera_bytes=ctypes.sizeof(abi.CameraPOD) * F,
                     e2e_path=("the trace kernel stores pixels straight into the pinned, mapped host frame (zero copy, RTX_FRAME_STORE / RTX_MEM_HOST_MAPPED)"
@@ -583,6 +593,8 @@ def main():
                     "d2h_bytes_per_step": m["frame_bytes"], "path": m["e2e_path"]},
             "parity": m["parity"],
             "step_ms_rank0": m["step_ms"], "e2e_step_ms_rank0": m["step_ms_e2e"],
+            "step_ms_per_rank": m["step_ms_per_rank"], "e2e_step_ms_per_rank": m["step_ms_per_rank_e2e"],
+            "untimed_gap_ms_per_rank": m["gap_ms_per_rank"],
             "gpu_launches": launches,
             "clocks": m["clocks"],
         }

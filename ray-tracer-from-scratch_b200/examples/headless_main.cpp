@@ -213,6 +213,7 @@ int main(int argc, char* argv[])
             std::cout << "Number of frames: " << frames << " : " << mean_us / 1000 << " ms average frame time\n";
             std::cout << "   " << mean_us << " microseconds for average raytracing\n";
             std::cout << "   0 milliseconds for surface average update\n";
+            std::cout << "   fastest frame: " << *std::min_element(rt_times.begin(), rt_times.end()) << " microseconds (the first frame uploads the scene and allocates)\n";
             std::cout << "   device (CUDA events): " << st.raytracing_ms << " ms raytracing on the slowest of " << devices.size() << " GPUs, "
                       << st.total_rays << " rays, " << st.over_range_pixels << " over-range pixels in the last frame\n";
             return 0;

@@ -272,7 +272,18 @@ class ShardedRenderer:
                 frame_ids = torch.empty((H, W), dtype=torch.int32, device=self.device)
                 self.r.unpermute_bands(gathered_ids.data_ptr(), frame_ids.data_ptr(), H, W, 4, self.band_rows, self.world, rpr)
                 launches += 1
+        if to_host and self.rank == 0 and not want_ids:
+            frame = self._read_back(frame)          # the round-1 path: rank 0's PCIe link carries the whole frame
         return (frame, frame_ids) if want_ids else frame, st, launches
+
+    def _read_back(self, device_frames):
+        """All-gather comparison path: copies the assembled frame (set) on rank 0 into a pinned host buffer; numpy view."""
+        key = tuple(device_frames.shape)
+        if getattr(self, "_pinned", None) is None or self._pinned[0] != key:
+            self._pinned = (key, torch.empty(key, dtype=torch.int32, pin_memory=True))
+        self._pinned[1].copy_(device_frames, non_blocking=True)
+        self._sync()
+        return self._pinned[1].numpy().view(np.uint32)
 
     # -- a camera path, frames sharded ------------------------------------------------------------------------------
     def _pipelined_frames(self, cam_pods, mine, F, H, W, params, to_host):
@@ -333,4 +344,6 @@ class ShardedRenderer:
         if self.rank == 0:
             # frame f = r + world*k sits at gathered[r][k]: a pure reindexing
             frames = gathered.permute(1, 0, 2, 3).reshape(per_rank * self.world, H, W)[:F]
+            if to_host:
+                frames = self._read_back(frames.contiguous())
         return frames, st, launches
