@@ -413,11 +413,18 @@ class Arm:
         def timed_region(e2e, n_steps, n_warm, smp=None):
             for _ in range(n_warm):
                 step(e2e)
+            # The clock sampler (an NVML polling thread on rank 0) is started BEFORE the ranks line up: starting it after the
+            # barrier delayed rank 0's first timed step by ~10 ms, which every other rank then spent waiting in that step's
+            # barrier (measured: first step 111 ms on rank 1 against 101 ms for all later ones) — 1-2 ms on the mean of a
+            # 5-10 step run, the whole "multi-GPU step overhead" of round 1.
+            if smp:
+                smp.start()
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
-            if smp:
-                smp.start()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
             rays = kernel_ms = launches = 0
             for k in range(n_steps):
