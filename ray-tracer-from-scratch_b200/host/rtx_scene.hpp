@@ -18,7 +18,10 @@
 #include <memory>
 #include <stdexcept>
 #include <algorithm>
+#include <condition_variable>
 #include <exception>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -281,15 +284,22 @@ public:
     // The reference reads the scene vector afresh on every frame (main.cpp:329), so an element replaced or edited in
     // place must show in the next frame: the scene is re-described per call (O(N), nothing next to a frame) and
     // uploaded again whenever its CONTENT differs from what the device holds — not merely its address or size.
-    void sync_scene(const Scene& scene)
+    void sync_scene(const Scene& scene) { sync_described(describe_scene(scene)); }
+
+    static std::vector<rtx_object> describe_scene(const Scene& scene)
     {
         std::vector<rtx_object> objs;
         objs.reserve(scene.size());
         for (const auto& g : scene) objs.push_back(g->describe());
+        return objs;
+    }
+    // The same with a scene that has already been described (the multi-GPU host describes it once for all GPUs).
+    void sync_described(const std::vector<rtx_object>& objs)
+    {
         if (have_uploaded && objs.size() == uploaded.size() &&
             (objs.empty() || std::memcmp(objs.data(), uploaded.data(), objs.size() * sizeof(rtx_object)) == 0))
             return;
-        upload(std::move(objs));
+        upload(std::vector<rtx_object>(objs));
     }
 
     // rt_scene (main.cpp:124-139): fills frame_buffer[i][j] (row i, column j) with the radiance of every pixel.
@@ -370,7 +380,7 @@ private:
 
 // ---- several GPUs, one process -----------------------------------------------------------------------------------
 // The reference's frame loop (main.cpp:250-375) is one thread calling rt_scene once per frame. Here the same call fans
-// out: one rtx_ctx and one host thread per GPU, the frame's rows dealt to the GPUs in cyclic bands (band b -> GPU
+// out: one rtx_ctx and one persistent host thread per GPU, the frame's rows dealt to the GPUs in cyclic bands (band b -> GPU
 // b mod N; rtx_params.band_rows / n_ranks / rank), and every trace kernel stores its finished pixels AT THEIR GLOBAL
 // POSITION in one shared surface — no gather step, no reassembly:
 //   * surface(): a pinned, mapped host surface, the stand-in for SDL's surface->pixels (main.cpp:193,344); each GPU
@@ -386,24 +396,54 @@ class ShardedRenderer {
     size_t surface_words = 0, device_words = 0;
     int band_rows;
 
+    // One persistent host thread per GPU (the contexts are created here, driven there): a frame is one job handed to all of
+    // them; the caller's thread waits. Exceptions travel back to the caller.
+    std::vector<std::thread> workers;
+    std::mutex mtx;
+    std::condition_variable cv_job, cv_done;
+    std::function<void(int, Renderer&)> job;
+    std::vector<std::exception_ptr> errors;
+    int generation = 0, pending = 0;
+    bool stopping = false;
+
+    void worker_loop(int g)
+    {
+        int seen = 0;
+        for (;;) {
+            std::function<void(int, Renderer&)> mine;
+            {
+                std::unique_lock<std::mutex> lk(mtx);
+                cv_job.wait(lk, [&] { return stopping || generation != seen; });
+                if (stopping) return;
+                seen = generation;
+                mine = job;
+            }
+            try { mine(g, *gpus[g]); } catch (...) { errors[g] = std::current_exception(); }
+            std::lock_guard<std::mutex> lk(mtx);
+            if (--pending == 0) cv_done.notify_all();
+        }
+    }
     template <class F>
     void on_every_gpu(F&& body)
     {
-        std::vector<std::thread> threads;
-        std::vector<std::exception_ptr> errors(gpus.size());
-        for (size_t g = 0; g < gpus.size(); g++)
-            threads.emplace_back([&, g] {
-                try { body(static_cast<int>(g), *gpus[g]); } catch (...) { errors[g] = std::current_exception(); }
-            });
-        for (auto& t : threads) t.join();
+        {
+            std::unique_lock<std::mutex> lk(mtx);
+            job = std::forward<F>(body);
+            std::fill(errors.begin(), errors.end(), std::exception_ptr());
+            pending = static_cast<int>(gpus.size());
+            generation++;
+            cv_job.notify_all();
+            cv_done.wait(lk, [&] { return pending == 0; });
+        }
         for (auto& e : errors)
             if (e) std::rethrow_exception(e);
     }
     void render_into(const std::vector<vec3>& u, const Scene& scene, const Camera& cam, uint32_t* frame_alias)
     {
         const rtx_camera c = cam.pod(u);
+        const std::vector<rtx_object> described = Renderer::describe_scene(scene);     // once per frame, for all GPUs
         on_every_gpu([&](int g, Renderer& r) {
-            r.sync_scene(scene);
+            r.sync_described(described);
             rtx_params p = params;
             p.band_rows = band_rows;
             p.n_ranks = static_cast<int32_t>(gpus.size());
@@ -423,9 +463,17 @@ public:
         rtx_default_params(&params);
         for (int d : devices) gpus.push_back(std::make_unique<Renderer>(d));
         for (size_t g = 1; g < gpus.size(); g++) gpus[g]->enable_peer_access(devices[0]);
+        errors.resize(gpus.size());
+        for (size_t g = 0; g < gpus.size(); g++) workers.emplace_back([this, g] { worker_loop(static_cast<int>(g)); });
     }
     ~ShardedRenderer()
     {
+        {
+            std::lock_guard<std::mutex> lk(mtx);
+            stopping = true;
+        }
+        cv_job.notify_all();
+        for (auto& t : workers) t.join();
         if (host_surface) rtx_host_free(gpus[0]->raw(), host_surface);
         if (device_frame) rtx_buffer_free(gpus[0]->raw(), device_frame);
     }

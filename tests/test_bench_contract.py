@@ -31,3 +31,35 @@ def test_default_workload_is_the_8k_frame_at_every_n():
     for n in (1, 2, 4, 8):
         spec = bench.workload_spec("auto", n)
         assert spec["name"] == "c4" and spec["width"] == 7680 and spec["depth"] == 10
+
+
+def test_parity_block_flags_a_single_wrong_pixel(port, S):
+    """bench.py's `parity` block: per-row CRCs of the timed frame against the unmodified reference's (fullsize_c2.json).
+    The oracle's own 1080p frame passes; one flipped bit in one pixel is one bad row."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    spec = bench.workload_spec("c2", 1)
+    frame = port.render(S.default_scene(), S.default_camera(1920, 16.0 / 9.0).pod(), 8, want=("rgba8",))["rgba8"]
+    ok = bench.parity_check(spec, {"device frame": frame, "host frame": frame[None]})
+    assert ok["rows_checked"] == 2 * 1080 and ok["rows_bad"] == 0 and "fullsize_c2.json" in ok["source"]
+    bad = frame.copy()
+    bad[540, 960] ^= 0x100
+    out = bench.parity_check(spec, {"device frame": bad})
+    assert out["rows_bad"] == 1 and out["first_bad"] == [["device frame", 0, 540]]
+    small = bench.parity_check(spec, {"device frame": frame[:100]})
+    assert small["rows_bad"] is None and small["rows_checked"] == 0          # a scaled run is not compared, and says so
+
+
+def test_both_arms_print_the_same_structural_config():
+    sys.path.insert(0, ROOT)
+    import importlib
+    import bench
+    S = importlib.import_module("ray-tracer-from-scratch_b200").scene
+    spec = bench.workload_spec("auto", 8)
+    scene = bench.build_scene(S, spec["scene"])
+    pods = [S.default_camera(spec["width"], 16.0 / 9.0).pod()]
+    cfg = bench.structural_config(spec, S, pods, scene, 8, 4)
+    assert cfg == {"workload": spec["label"], "width": 7680, "height": 4320, "frames_per_step": 1, "depth": 10, "n_spheres": 10000,
+                   "n_walls": 64, "band_rows": 4}
+    assert bench.host_threads() >= 1
