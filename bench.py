@@ -120,6 +120,10 @@ class ClockSampler:
         if self.ok:
             self.t.start()
 
+    def reset(self):
+        """Forget what was sampled so far (the warm-up steps): the timed region starts now."""
+        self.samples, self.reasons = [], set()
+
     def stop(self):
         self._stop.set()
         if self.ok:
@@ -411,20 +415,20 @@ class Arm:
             return (st.total_rays if st else 0), (st.raytracing_ms if st else 0.0), launches
 
         def timed_region(e2e, n_steps, n_warm, smp=None):
-            for _ in range(n_warm):
-                step(e2e)
-            # The clock sampler (an NVML polling thread on rank 0) is started BEFORE the ranks line up: starting it after the
-            # barrier delayed rank 0's first timed step by ~10 ms, which every other rank then spent waiting in that step's
-            # barrier (measured: first step 111 ms on rank 1 against 101 ms for all later ones) — 1-2 ms on the mean of a
-            # 5-10 step run, the whole "multi-GPU step overhead" of round 1.
+            # The clock sampler (an NVML polling thread on rank 0) starts BEFORE the warm-up steps and is only reset when the
+            # timed region begins: started right before it, its first NVML queries (slow, and serialised with kernel launches
+            # inside the driver) delayed rank 0's first timed step by ~10 ms, which every other rank then spent waiting in
+            # that step's barrier (measured: first step 35.8 ms on ranks 1-7 against 26.1 ms for every later one) — 1-2 ms on
+            # the mean of a 5-10 step run, the whole "multi-GPU step overhead" of round 1.
             if smp:
                 smp.start()
+            for _ in range(n_warm):
+                step(e2e)
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-                torch.cuda.synchronize()
+            if smp:
+                smp.reset()
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
             rays = kernel_ms = launches = 0
             for k in range(n_steps):
