@@ -26,6 +26,7 @@ Metric (BASELINE.json): Mrays/s = rays traced (primary + reflections, equal to t
            oracle/build_ref.sh) row-parallel over all host threads on a bounded sample of the same frame.
 """
 import argparse
+import gc
 import importlib
 import json
 import os
@@ -415,15 +416,18 @@ class Arm:
             return (st.total_rays if st else 0), (st.raytracing_ms if st else 0.0), launches
 
         def timed_region(e2e, n_steps, n_warm, smp=None):
-            # The clock sampler (an NVML polling thread on rank 0) starts BEFORE the warm-up steps and is only reset when the
-            # timed region begins: started right before it, its first NVML queries (slow, and serialised with kernel launches
-            # inside the driver) delayed rank 0's first timed step by ~10 ms, which every other rank then spent waiting in
-            # that step's barrier (measured: first step 35.8 ms on ranks 1-7 against 26.1 ms for every later one) — 1-2 ms on
-            # the mean of a 5-10 step run, the whole "multi-GPU step overhead" of round 1.
+            # Warm-up steps are the timed steps without the clock: L2 flush included. (Until round 2 the flush kernel was
+            # first launched in the first TIMED step, where CUDA's lazy module loading made that one launch block the host
+            # for ~10 ms on rank 0; at N > 1 every other rank spent those 10 ms waiting in the first step's barrier — 1-2 ms
+            # on the mean of a 5-10 step run: the whole "multi-GPU step overhead" of round 1. Found with RTX_BENCH_TRACE=1
+            # and the per-rank step lists the line carries.)
             if smp:
                 smp.start()
             for _ in range(n_warm):
+                self.flush.add_(1)
                 step(e2e)
+            gc.collect()
+            gc.disable()                                           # no cyclic GC pass over ~100 000 scene objects mid-measurement
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
@@ -431,17 +435,26 @@ class Arm:
                 smp.reset()
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
             rays = kernel_ms = launches = 0
+            trace = os.environ.get("RTX_BENCH_TRACE") == "1"
+            t_sync = time.time()
             for k in range(n_steps):
+                h0 = time.time()
                 self.flush.add_(1)                                 # L2 flush, outside the step's events
                 ev[k][0].record()
+                h1 = time.time()
                 a, b, c = step(e2e)
+                h2 = time.time()
                 ev[k][1].record()
+                if trace and k < 2:
+                    print("[trace] rank %d e2e=%s step %d: starts +%.2f ms after the barrier, flush+record %.2f ms, step() %.2f ms (kernel %.2f)" % (
+                        rank, e2e, k, (h0 - t_sync) * 1e3, (h1 - h0) * 1e3, (h2 - h1) * 1e3, b), file=sys.stderr, flush=True)
                 rays += a
                 kernel_ms += b
                 launches += c
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
+            gc.enable()
             clocks = smp.stop() if smp else None
             per_step = [s.elapsed_time(e) for s, e in ev]
             ms = sum(per_step)
@@ -539,7 +552,7 @@ def main():
     r = arm.r
     flush = arm.flush
 
-    sampler = ClockSampler(visible_index(local_rank)) if rank == 0 else None
+    sampler = ClockSampler(visible_index(local_rank)) if rank == 0 and os.environ.get("RTX_BENCH_SAMPLER", "1") != "0" else None
     e2e_steps = max(2, min(args.steps, 5))
     m = arm.measure(spec, args.steps, args.warmup, e2e_steps, sampler)
     also = {}

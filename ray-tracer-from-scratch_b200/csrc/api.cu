@@ -7,7 +7,6 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
-#include <sys/syscall.h>
 #include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
@@ -147,32 +146,6 @@ int grow(rtx_ctx* ctx, void** p, size_t* cap, size_t need)
     if (e != cudaSuccess) return fail(ctx, RTX_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     *cap = need;
     return RTX_OK;
-}
-
-// mbind(MPOL_INTERLEAVE) over every online NUMA node, through the raw system call (no libnuma in the image).
-void interleave_pages(void* p, size_t bytes)
-{
-    unsigned long mask[16] = {};
-    int max_node = -1;
-    if (FILE* f = std::fopen("/sys/devices/system/node/online", "r")) {
-        char buf[256] = {};
-        if (std::fgets(buf, sizeof buf, f)) {
-            for (char* tok = std::strtok(buf, ",\n"); tok; tok = std::strtok(nullptr, ",\n")) {
-                int a = 0, b = 0;
-                const int n = std::sscanf(tok, "%d-%d", &a, &b);
-                if (n == 1) b = a;
-                if (n >= 1)
-                    for (int k = a; k <= b && k < 1024; k++) {
-                        mask[k / (8 * sizeof(unsigned long))] |= 1ul << (k % (8 * sizeof(unsigned long)));
-                        max_node = std::max(max_node, k);
-                    }
-            }
-        }
-        std::fclose(f);
-    }
-    if (max_node < 1) return;                    // one node (or unknown): nothing to interleave
-    constexpr int kMpolInterleave = 3;
-    syscall(SYS_mbind, p, bytes, kMpolInterleave, mask, static_cast<unsigned long>(max_node + 2), 0u);   // best effort
 }
 
 #ifndef RTX_PAIRS
@@ -1397,17 +1370,9 @@ int rtx_host_shared_open(rtx_ctx* ctx, const char* name, uint64_t bytes, int32_t
         close(fd);
         return fail(ctx, RTX_ERR_NOMEM, msg);
     }
-    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | (create ? 0 : MAP_POPULATE), fd, 0);
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_POPULATE, fd, 0);
     close(fd);
     if (p == MAP_FAILED) return fail(ctx, RTX_ERR_NOMEM, std::string("rtx_host_shared_open: mmap: ") + std::strerror(errno));
-    if (create) {
-        // The creator decides where the pages live. Eight GPUs writing one frame set that sits on ONE NUMA node share that
-        // node's memory controllers and the inter-socket link; interleaving the pages over all nodes spreads the load
-        // (best effort: a failing mbind leaves the default first-touch policy). RTX_SHM_INTERLEAVE=0 switches it off.
-        const char* env = std::getenv("RTX_SHM_INTERLEAVE");
-        if (!env || env[0] != '0') interleave_pages(p, bytes);
-        std::memset(p, 0, bytes);          // first touch under that policy
-    }
     cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
     if (e != cudaSuccess) {
         munmap(p, bytes);

@@ -293,6 +293,29 @@ __device__ __noinline__ void start_pixel(Chain& c, unsigned long long p, const T
 // This kernel is the same algorithm without the machinery: one chain per lane held in registers, every object tested
 // with the exact double routines, persistent lanes refilled from the same pixel counter. Results are identical by
 // construction (same sphere_exact / wall_exact / better / shade_body).
+// Wall::intersect (scene.cpp:4-35) for the small kernel, where every ray tests every wall exactly and half of those tests
+// end at "t > 0" being false: the quotient t = num / den can only be positive if num is neither zero nor NaN, den is not
+// NaN, and both carry the same sign bit (+-0 and +-inf included: num / +-0 = +-inf with the product of the signs) — a
+// necessary condition, checked on the bit patterns BEFORE the division (a ~25-instruction sequence in double). When it
+// holds, t is computed and tested exactly as in wall_exact; when it does not, the reference's own test would have failed
+// and -1 is returned as there. Same result for every input.
+__device__ __forceinline__ double wall_exact_lazy(d3 o, d3 d, const WallDev& w)
+{
+    using namespace ex;
+    const double denominator = dot(w.n, d);
+    const double numerator = dot(sub(w.p, o), w.n);
+    const bool same_sign = ((__double2hiint(numerator) ^ __double2hiint(denominator)) >= 0);
+    if (!(same_sign && numerator != 0.0 && numerator == numerator && denominator == denominator)) return -1.0;
+    const double t = div(numerator, denominator);
+    if (t > 0) {
+        const d3 rel = sub(add(o, scale(d, t)), w.p);
+        const double px = dot(rel, w.right);
+        const double py = dot(rel, w.up);
+        if (px >= 0 && px <= w.length && py >= 0 && py <= w.width) return t;
+    }
+    return -1.0;
+}
+
 constexpr int kSmallScene = kSmallSceneEntries;   // screen entries (spheres + walls + box faces)
 constexpr int kSmallThreads = 256;
 
@@ -355,7 +378,7 @@ __global__ void __launch_bounds__(kSmallThreads, RTX_SMALL_MINBLOCKS) trace_smal
             }
             for (int i = 0; i < sc.n_walls; i++) {
                 const WallDev& w = sc.walls[i];
-                const double t = wall_exact(c.o, c.d, w);
+                const double t = wall_exact_lazy(c.o, c.d, w);
                 if (better(t, w.key, c.best_dist, c.best_key)) { c.best_dist = t; c.best_key = w.key; }
             }
             shade_body(c, a, sc, tot);

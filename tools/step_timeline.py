@@ -60,30 +60,39 @@ for to_host in (False, True):
 import threading
 
 
-def free_run(label, n=8):
+def free_run(label, n=6):
     store_ptr, copy_ptr, view = sh._destination(1, H, W, False)
     p = R.default_params(max_depth=10, band_rows=4, n_ranks=world, rank=rank)
     o = abi.Outputs()
     o.memory, o.frame_mode, o.frame_rgba8 = abi.RTX_MEM_DEVICE, abi.RTX_FRAME_STORE, store_ptr
+    for _ in range(2):
+        r.render_raw([pod], p, o)
+        sh._barrier()
     dist.barrier()
     torch.cuda.synchronize()
+    t_sync = time.time()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n)]
-    ks = []
+    ks, host = [], []
     for k in range(n):
+        h0 = time.time()
         flush.add_(1)
         ev[k][0].record()
+        h1 = time.time()
         st = r.render_raw([pod], p, o)
+        h2 = time.time()
         ev[k][1].record()
         sh._barrier()
         ev[k][2].record()
+        h3 = time.time()
         ks.append(st.raytracing_ms)
+        host.append((h0 - t_sync, h1 - h0, h2 - h1, h3 - h2))
     torch.cuda.synchronize()
     for q in range(world):
         dist.barrier()
         if q == rank:
-            print("%s rank %d: " % (label, rank) + "  ".join("[render %.2f (kernel %.2f) barrier %.2f gap-to-next %.2f]" % (
+            print("%s rank %d: " % (label, rank) + "  ".join("[render %.2f (kernel %.2f) barrier %.2f | host: start +%.2f ms, flush+record %.2f, render_raw %.2f, barrier call %.2f]" % (
                 ev[k][0].elapsed_time(ev[k][1]), ks[k], ev[k][1].elapsed_time(ev[k][2]),
-                ev[k][2].elapsed_time(ev[k + 1][0]) if k + 1 < n else 0.0) for k in range(2, n)), flush=True)
+                host[k][0] * 1e3, host[k][1] * 1e3, host[k][2] * 1e3, host[k][3] * 1e3) for k in range(0, 3)), flush=True)
 
 
 free_run("free-running")
