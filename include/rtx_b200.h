@@ -341,6 +341,10 @@ int rtx_buffer_free(rtx_ctx* ctx, void* device_ptr);
 int rtx_buffer_export(rtx_ctx* ctx, void* device_ptr, uint8_t handle[RTX_IPC_HANDLE_BYTES]);
 int rtx_buffer_import(rtx_ctx* ctx, const uint8_t handle[RTX_IPC_HANDLE_BYTES], void** device_ptr);
 int rtx_buffer_release(rtx_ctx* ctx, void* imported_ptr);
+/* Copies `bytes` from device memory (rtx_buffer_alloc / _import, or any device pointer of this context's GPU or a peer)
+ * into host memory, ordered after the context's work; blocking. The host-side end of a frame assembled in rank 0's HBM
+ * (rtx::ShardedRenderer::render_to_device, the `value` path of bench.py), e.g. to hand it to a presenter or a file. */
+int rtx_buffer_read(rtx_ctx* ctx, const void* device_ptr, void* host_ptr, uint64_t bytes);
 
 /* ONE process driving several GPUs (one context + one host thread per GPU, the C++ host's rtx::ShardedRenderer): the
  * kernels of `ctx`'s device may then store into memory of `peer_device` (rank 0's frame from rtx_buffer_alloc, passed to

@@ -90,5 +90,5 @@ EXPORTS = (
     "rtx_render", "rtx_render_async", "rtx_wait", "rtx_trace_rays", "rtx_quantise", "rtx_tonemap", "rtx_tonemap_sums", "rtx_tonemap_apply", "rtx_unpermute_bands", "rtx_ffma_peak",
     "rtx_enable_peer_access", "rtx_device_count", "rtx_host_alloc", "rtx_host_free", "rtx_host_register", "rtx_host_unregister", "rtx_host_device_pointer",
     "rtx_host_shared_open", "rtx_host_shared_close",
-    "rtx_buffer_alloc", "rtx_buffer_free", "rtx_buffer_export", "rtx_buffer_import", "rtx_buffer_release",
+    "rtx_buffer_alloc", "rtx_buffer_free", "rtx_buffer_export", "rtx_buffer_import", "rtx_buffer_release", "rtx_buffer_read",
 )

@@ -1283,6 +1283,15 @@ int rtx_buffer_import(rtx_ctx* ctx, const uint8_t handle[RTX_IPC_HANDLE_BYTES], 
     return RTX_OK;
 }
 
+int rtx_buffer_read(rtx_ctx* ctx, const void* device_ptr, void* host_ptr, uint64_t bytes)
+{
+    if (!ctx || !device_ptr || !host_ptr) return fail(ctx, RTX_ERR_INVALID, "rtx_buffer_read: bad argument");
+    RTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    RTX_CUDA(ctx, cudaMemcpyAsync(host_ptr, device_ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RTX_OK;
+}
+
 int rtx_buffer_release(rtx_ctx* ctx, void* imported_ptr)
 {
     if (!ctx) return RTX_ERR_INVALID;

@@ -9,10 +9,12 @@
 //
 //   rtx_headless [--width 640] [--aspect 1] [--depth 10] [--frames 3] [--keys wwad] [--out frame.ppm] [--raw frame.rgba]
 //                [--png frame.png] [--sun 1] [--tonemap 1] [--box 1] [--devices 0,1,...] [--band-rows 4] [--scene default|synthetic]
-//                [--accel 1]
+//                [--accel 1] [--to-device 1]
 // --devices: more than one entry renders every frame on several GPUs from THIS process (rtx::ShardedRenderer: one context
 // and one host thread per GPU, cyclic row bands, every kernel storing its pixels straight into one pinned host surface);
 // a device may be repeated (0,0 = two contexts on one GPU). --scene synthetic = the 10 064-object scene of configs C3/C4.
+// --to-device 1 (with --devices): the frame is assembled in the FIRST GPU's memory instead (peers store over NVLink) and
+// read back once at the end.
 // --keys: one key event per frame — w s a d as in the reference (main.cpp:262-306); j l i k = the mouse look the reference
 // leaves commented out (rotate_left_right(+-0.05), rotate_up_down(+-0.05), main.cpp:319-323); anything else = no event.
 // --sun / --tonemap / --box switch on this repo's EXTENSIONS (default-off; include/rtx_b200.h): the sun of main.cpp:18-19
@@ -132,7 +134,7 @@ int main(int argc, char* argv[])
     int width = 640, depth = 10, frames = 3;
     double aspect = 1.0;   // ASPECT_RATIO = 4/3 is integer division = 1 in the reference (main.cpp:25)
     std::string keys, out_ppm = "frame.ppm", out_raw, out_png;
-    bool ext_sun = false, ext_tonemap = false, ext_box = false, accel = false;
+    bool ext_sun = false, ext_tonemap = false, ext_box = false, accel = false, to_device = false;
     std::vector<int> devices = {0};
     int band_rows = 4;
     std::string scene_name = "default";
@@ -150,6 +152,7 @@ int main(int argc, char* argv[])
         else if (a == "--tonemap") ext_tonemap = std::atoi(argv[k + 1]) != 0;
         else if (a == "--box") ext_box = std::atoi(argv[k + 1]) != 0;
         else if (a == "--accel") accel = std::atoi(argv[k + 1]) != 0;
+        else if (a == "--to-device") to_device = std::atoi(argv[k + 1]) != 0;
         else if (a == "--band-rows") band_rows = std::atoi(argv[k + 1]);
         else if (a == "--scene") scene_name = argv[k + 1];
         else if (a == "--devices") {
@@ -202,11 +205,12 @@ int main(int argc, char* argv[])
             for (int frame = 0; frame < frames; frame++) {
                 if (frame < static_cast<int>(keys.size())) apply_key(cam, keys[frame]);
                 auto t0 = std::chrono::high_resolution_clock::now();
-                pixels = sharded.render_surface(u, scene, cam);
+                pixels = to_device ? sharded.render_to_device(u, scene, cam) : sharded.render_surface(u, scene, cam);
                 auto t1 = std::chrono::high_resolution_clock::now();
                 rt_times.push_back(std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count());
             }
-            std::copy(pixels, pixels + surface.size(), surface.begin());
+            if (to_device) sharded.read_device_frame(pixels, surface.data(), surface.size());
+            else std::copy(pixels, pixels + surface.size(), surface.begin());
             write_outputs(surface, W, H, out_ppm, out_raw, out_png);
             const rtx_stats st = sharded.stats();
             const int64_t mean_us = rt_times.empty() ? 0 : std::accumulate(rt_times.begin(), rt_times.end(), int64_t{0}) / static_cast<int64_t>(rt_times.size());

@@ -523,6 +523,12 @@ public:
         return device_frame;
     }
 
+    // Copies a frame returned by render_to_device into host memory (blocking).
+    void read_device_frame(const uint32_t* device_frame_ptr, uint32_t* host, size_t words)
+    {
+        gpus[0]->check(rtx_buffer_read(gpus[0]->raw(), device_frame_ptr, host, words * 4), "rtx_buffer_read");
+    }
+
     // Sum over the GPUs of the last frame's statistics; raytracing_ms is the slowest GPU's.
     rtx_stats stats() const
     {

@@ -116,6 +116,8 @@ def load_library(path=LIB_PATH):
     lib.rtx_buffer_alloc.argtypes = [ctx, C.c_uint64, C.POINTER(C.c_void_p)]
     lib.rtx_buffer_export.restype = C.c_int
     lib.rtx_buffer_export.argtypes = [ctx, C.c_void_p, C.c_char_p]
+    lib.rtx_buffer_read.restype = C.c_int
+    lib.rtx_buffer_read.argtypes = [ctx, C.c_void_p, C.c_void_p, C.c_uint64]
     lib.rtx_buffer_import.restype = C.c_int
     lib.rtx_buffer_import.argtypes = [ctx, C.c_char_p, C.POINTER(C.c_void_p)]
     if lib.rtx_abi_version() != abi.ABI_VERSION:
@@ -395,6 +397,11 @@ class Renderer:
         p = C.c_void_p()
         self._check(self.lib.rtx_buffer_import(self._ctx, C.create_string_buffer(bytes(handle), 64), C.byref(p)))
         return p.value
+
+    def buffer_read(self, ptr, host_array):
+        """Blocking copy of host_array.nbytes bytes from a device pointer into a C-contiguous numpy array."""
+        self._check(self.lib.rtx_buffer_read(self._ctx, C.c_void_p(ptr), host_array.ctypes.data, host_array.nbytes))
+        return host_array
 
     def buffer_release(self, ptr):
         self._check(self.lib.rtx_buffer_release(self._ctx, C.c_void_p(ptr)))

@@ -46,6 +46,10 @@ def test_cpp_sharded_host_assembles_the_reference_frame(tmp_path, renderer_mod, 
     subprocess.run(common + ["--devices", devices, "--band-rows", str(band), "--raw", str(many)], check=True, capture_output=True)
     a, b = np.fromfile(one, dtype=np.uint32), np.fromfile(many, dtype=np.uint32)
     assert a.size == 192 * 108 and np.array_equal(a, b)
+    # the same frame assembled in the first GPU's memory (peer stores, rtx_enable_peer_access) and read back with rtx_buffer_read
+    dev = tmp_path / "dev.rgba"
+    subprocess.run(common + ["--devices", devices, "--band-rows", str(band), "--to-device", "1", "--raw", str(dev)], check=True, capture_output=True)
+    assert np.array_equal(np.fromfile(dev, dtype=np.uint32), a)
     exp = port.render(S.synthetic_scene(), S.default_camera(192, 16.0 / 9.0).pod(), 6, want=("rgba8",))["rgba8"]
     assert np.array_equal(a.reshape(108, 192), exp)                     # and the C++ scene generator draws the survey's scene
 
