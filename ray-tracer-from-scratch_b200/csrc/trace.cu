@@ -422,6 +422,8 @@ struct ChainDump {        // what survives between two segments of a chain
     int remaining, first_id, rays, pad;
 };
 static_assert(sizeof(ChainDump) == 104, "ChainDump layout");
+static_assert(static_cast<size_t>(kThreads) * kChains * sizeof(ChainDump) <= kTailScratchBytesPerCta,
+              "api.cu allocates kTailScratchBytesPerCta per CTA for the tail rebalance");
 
 __device__ __forceinline__ void dump_chain(ChainDump* dst, const Chain& c)
 {
