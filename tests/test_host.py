@@ -215,3 +215,18 @@ def test_camera_walk_reference_build_agrees_with_golden(ref, S):
     for w in _walks():
         states, _ = ref.camera_walk(_camera_of(S, w), [(op, arg) for op, arg in w["steps"]])
         assert _same(states, [[fh3(v) for v in st] for st in w["states"]])
+
+
+def test_hot_loop_canary(renderer_mod):
+    """The trace kernel's hot loop in the BUILT library: 84 FFMA2 (12 entries x 2 chains x 7) and nothing ptxas should not have
+    put there. An unrelated edit once made it re-load kernel parameters inside the loop (184 -> 220 instructions, +2 % frame
+    time); tools/sass_ffma2.py is the check, this test runs it."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_ffma2.py"), renderer_mod.LIB_PATH],
+                         capture_output=True, text=True, check=True).stdout
+    m = re.search(r"hot loop: (\d+) instructions per iteration: \{'FFMA2': (\d+)", out)
+    assert m, out
+    assert int(m.group(2)) == 84 and int(m.group(1)) <= 190, out
