@@ -674,3 +674,21 @@ def test_frame_copy_mode_places_bands_and_frames(gpu, renderer_mod, port, S):
             assert np.array_equal(frames[f], port.render(scene, c, 10, want=("rgba8",))["rgba8"]), f
     finally:
         gpu.host_free(ptr)
+
+
+def test_device_frame_buffer_alloc_store_read(gpu, renderer_mod, port, S):
+    """rtx_buffer_alloc + frame_rgba8 (RTX_FRAME_STORE, one rank) + rtx_buffer_read: the `value` path of bench.py without torch."""
+    abi = renderer_mod.abi
+    scene = S.default_scene()
+    gpu.set_scene(scene)
+    pod = S.default_camera(120, 1.5).pod()
+    n = pod.width * pod.height
+    ptr = gpu.buffer_alloc(n * 4)
+    try:
+        o = abi.Outputs()
+        o.memory, o.frame_rgba8 = abi.RTX_MEM_DEVICE, ptr
+        gpu.render_raw([pod], renderer_mod.default_params(max_depth=7), o)
+        got = gpu.buffer_read(ptr, np.zeros((pod.height, pod.width), np.uint32))
+        assert np.array_equal(got, port.render(scene, pod, 7, want=("rgba8",))["rgba8"])
+    finally:
+        gpu.buffer_free(ptr)
