@@ -60,6 +60,7 @@ def test_both_arms_print_the_same_structural_config():
     scene = bench.build_scene(S, spec["scene"])
     pods = [S.default_camera(spec["width"], 16.0 / 9.0).pod()]
     cfg = bench.structural_config(spec, S, pods, scene, 8, 4)
-    assert cfg == {"workload": spec["label"], "width": 7680, "height": 4320, "frames_per_step": 1, "depth": 10, "n_spheres": 10000,
-                   "n_walls": 64, "band_rows": 4}
+    assert {k: cfg[k] for k in ("workload", "width", "height", "frames_per_step", "depth", "n_spheres", "n_walls", "band_rows")} == {
+        "workload": spec["label"], "width": 7680, "height": 4320, "frames_per_step": 1, "depth": 10, "n_spheres": 10000, "n_walls": 64, "band_rows": 4}
+    assert "L2 flush" in cfg["l2"] and set(cfg) == {"workload", "width", "height", "frames_per_step", "depth", "n_spheres", "n_walls", "band_rows", "l2", "arms"}
     assert bench.host_threads() >= 1
