@@ -1021,10 +1021,14 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
     sl.launches = launches;
     sl.n_spheres = ctx->scene.n_spheres;
     sl.n_walls = ctx->scene.n_walls;
-    ctx->next_slot = (ctx->next_slot + 1) % kSlots;
     ctx->error.clear();
-    if (async) return RTX_OK;
-    ctx->oldest = ctx->next_slot;          // nothing else is in flight (drained above): this call is the only pending one
+    if (async) {
+        ctx->next_slot = (ctx->next_slot + 1) % kSlots;
+        return RTX_OK;
+    }
+    // Synchronous call: nothing else is in flight (drained above), and the slot is free again when this returns — so the next
+    // call takes the SAME slot and finds its staging buffers already allocated (rotating would allocate kSlots sets one call
+    // after the other, the later ones in the middle of somebody's timed region).
     return finish_slot(ctx, sl, stats);
 }
 
