@@ -437,6 +437,8 @@ class Arm:
             torch.cuda.synchronize()
             if smp:
                 smp.reset()
+            if not e2e:
+                drain.clear()                                      # drain_ms_per_step_rank0 is the mean over the timed steps
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
             rays = kernel_ms = launches = 0
             trace = os.environ.get("RTX_BENCH_TRACE") == "1"
@@ -487,6 +489,7 @@ class Arm:
             return ms, rays, kernel_max, int(launches), clocks, per_rank_kernel
 
         ms, rays, kernel_ms, launches, clocks, per_rank_kernel = timed_region(False, steps, warmup, sampler)
+        drain_timed = list(drain)
         ms_e, rays_e, _, launches_e, _, _ = timed_region(True, e2e_steps, max(1, min(warmup, 2)))
         verified = None
         if args.verify and world > 1:
@@ -503,19 +506,34 @@ class Arm:
                     ok = ok and bool(torch.equal(alone, got[f0:f0 + len(part)]))
                 verified = ok
             dist.barrier()
-        if rank != 0:
-            return None
         import numpy as np
         torch.cuda.synchronize()
-        planes = {"device frame (value)": result["device"].reshape(F, H, W).cpu().numpy().view(np.uint32),
-                  "host frame (e2e)": np.asarray(result["host"]).reshape(F, H, W).view(np.uint32)}
+        planes = None
+        if rank == 0:     # the frames of the timed regions, before anything else is rendered into the same buffers
+            planes = {"device frame (value)": result["device"].reshape(F, H, W).cpu().numpy().view(np.uint32),
+                      "host frame (e2e)": np.asarray(result["host"]).reshape(F, H, W).view(np.uint32)}
+        # The same frame in plain scan order (rtx_params.pixel_order = RTX_ORDER_SCAN), untimed: what the scheduling hint of the
+        # timed steps (tiles in the order of the previous frame's ray counts) is worth on this box.
+        scan_drain, scan_kernel = [], []
+        if spec["name"] != "c5":
+            for _ in range(2):
+                if world > 1:
+                    _, st, _ = sh.render_frame(pods[0], max_depth=spec["depth"], pixel_order=abi.RTX_ORDER_SCAN)
+                else:
+                    st = r.render_raw(pods, R.default_params(max_depth=spec["depth"], pixel_order=abi.RTX_ORDER_SCAN), outs[False])
+                if st:
+                    scan_drain.append(st.drain_ms)
+                    scan_kernel.append(st.raytracing_ms)
+        if rank != 0:
+            return None
         parity = parity_check(spec, planes)
         if planes["device frame (value)"].shape == planes["host frame (e2e)"].shape:
             parity["device_equals_host_frame"] = bool(np.array_equal(planes["device frame (value)"], planes["host frame (e2e)"]))
         n_spheres = sum(1 for g in scene if g.kind == abi.RTX_SPHERE)
         return dict(spec=spec, scene=scene, pods=pods, H=H, W=W, F=F, n_spheres=n_spheres, n_walls=len(scene) - n_spheres,
                     ms=ms, rays=rays, kernel_ms=kernel_ms, launches=launches, clocks=clocks, per_rank_kernel=per_rank_kernel,
-                    ms_e=ms_e, rays_e=rays_e, launches_e=launches_e, steps=steps, e2e_steps=e2e_steps, drain=drain, parity=parity,
+                    ms_e=ms_e, rays_e=rays_e, launches_e=launches_e, steps=steps, e2e_steps=e2e_steps, drain=drain_timed, parity=parity,
+                    scan_drain=scan_drain, scan_kernel=scan_kernel,
                     step_ms=result.get("step_ms_rank0"), step_ms_e2e=result.get("step_ms_rank0_e2e"),
                     step_ms_per_rank=result.get("step_ms_per_rank"), step_ms_per_rank_e2e=result.get("step_ms_per_rank_e2e"),
                     gap_ms_per_rank=result.get("gap_ms_per_rank"),
@@ -612,6 +630,10 @@ def main():
                          "algorithmic_flop_per_step": flops_per_step, "peak_source": peak_src,
                          "executed_flop_per_test": 14, "frac_executed": achieved / peak * 14.0 / 20.0 if n_walls * 33 < n_spheres else None,
                          "drain_ms_per_step_rank0": sum(m["drain"]) / max(1, len(m["drain"])),
+                         "pixel_order": "RTX_ORDER_AUTO: tiles of 256 pixels handed out in descending order of the previous frame's ray counts "
+                                        "(scheduling only, identical pixels; every step renders the same camera, so the hint is exact here)",
+                         "scan_order_rank0": {"drain_ms": m["scan_drain"], "kernel_ms": m["scan_kernel"],
+                                              "what": "the same frame with rtx_params.pixel_order = RTX_ORDER_SCAN, after the timed regions"},
                          "peak_measured_ffma2_tflops": ffma2, "peak_measured_ffma_scalar_tflops": ffma1,
                          "frac_of_measured_ffma2": achieved / ffma2 if ffma2 else None,
                          "hbm_write_gbs": m["frame_bytes"] / world / (kernel_ms / args.steps * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak_gbs()[0]},

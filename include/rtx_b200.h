@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RTX_ABI_VERSION 4
+#define RTX_ABI_VERSION 5
 
 /* ---- status codes ------------------------------------------------------- */
 #define RTX_OK              0
@@ -129,7 +129,7 @@ typedef struct rtx_params {
     int32_t  band_rows;
     int32_t  n_ranks;
     int32_t  rank;
-    int32_t  reserved2;
+    int32_t  pixel_order;      /* RTX_ORDER_*: WHEN a pixel is traced, never what it looks like; default RTX_ORDER_AUTO */
     /* Camera paths sharded by frame: camera k of this call is frame (frame_offset + k * frame_stride) of the whole
      * path. Only used to place pixels in rtx_outputs.frame_rgba8. Defaults 0, 1. */
     int32_t  frame_offset;
@@ -160,6 +160,17 @@ typedef struct rtx_params {
  * of the 10 064-object scene). The roofline / headline numbers are always quoted on RTX_ACCEL_NONE. */
 #define RTX_ACCEL_NONE 0
 #define RTX_ACCEL_GRID 1
+
+/* The order in which the trace kernel's persistent lanes pick up pixels. A frame ends with the ray chains that are still
+ * in flight when the last pixel has been handed out; if those last pixels are cheap ones (sky: one ray) that tail is short.
+ * RTX_ORDER_COST hands out tiles of 256 pixels most expensive first, judged by the ray counts the PREVIOUS call on this
+ * context collected for the same frame geometry (an interactive loop or a camera path: consecutive frames look alike; the
+ * first frame of a geometry runs in scan order). Every pixel is traced exactly as before — object ids, ray counts and
+ * pixels do not depend on the order. Only the brute-force kernel of scenes with more than 16 objects uses it.
+ * RTX_ORDER_AUTO = RTX_ORDER_COST for frames of at least 2^18 pixels, RTX_ORDER_SCAN below. */
+#define RTX_ORDER_AUTO 0
+#define RTX_ORDER_SCAN 1
+#define RTX_ORDER_COST 2
 
 #define RTX_TONEMAP_NONE     0  /* reference: radiance goes straight to the 8-bit pack (main.cpp:338-347) */
 #define RTX_TONEMAP_REINHARD 1  /* extension, see rtx_params */

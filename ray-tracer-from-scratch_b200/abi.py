@@ -5,12 +5,13 @@ the reference code (file:line) every field stands for.
 """
 import ctypes as C
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 RTX_OK, RTX_ERR_INVALID, RTX_ERR_CUDA, RTX_ERR_NO_SCENE, RTX_ERR_NOMEM = 0, 1, 2, 3, 4
 RTX_SPHERE, RTX_WALL, RTX_BOX = 0, 1, 2        # RTX_BOX: extension, see the header
 RTX_QUANT_WRAP, RTX_QUANT_SATURATE = 0, 1
 RTX_ACCEL_NONE, RTX_ACCEL_GRID = 0, 1               # extension, see the header
+RTX_ORDER_AUTO, RTX_ORDER_SCAN, RTX_ORDER_COST = 0, 1, 2   # scheduling hint of the big kernel, see the header
 RTX_TONEMAP_NONE, RTX_TONEMAP_REINHARD = 0, 1    # extension, see the header
 RTX_MEM_HOST, RTX_MEM_DEVICE, RTX_MEM_HOST_MAPPED = 0, 1, 2
 RTX_FRAME_STORE, RTX_FRAME_COPY = 0, 1
@@ -57,7 +58,7 @@ class Params(C.Structure):
                 ("accel", C.c_int32),
                 ("light_pos", Vec3), ("ground_color", Vec3), ("sky_low", Vec3), ("sky_high", Vec3),
                 ("reflect_offset", C.c_double), ("sky_exponent", C.c_double),
-                ("band_rows", C.c_int32), ("n_ranks", C.c_int32), ("rank", C.c_int32), ("reserved2", C.c_int32),
+                ("band_rows", C.c_int32), ("n_ranks", C.c_int32), ("rank", C.c_int32), ("pixel_order", C.c_int32),
                 ("frame_offset", C.c_int32), ("frame_stride", C.c_int32),
                 # extensions (off by default): sun and tone-map operator
                 ("sun_enabled", C.c_int32), ("tonemap", C.c_int32), ("sun_color", Vec3), ("sun_direction", Vec3),

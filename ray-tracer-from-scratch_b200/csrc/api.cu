@@ -20,6 +20,7 @@
 using namespace rtx;
 
 constexpr int kRanges = 4;                        // pixel ranges of a small-scene frame rendered into host memory
+constexpr size_t kOrderMinPixels = 1u << 18;      // RTX_ORDER_AUTO: frames below this keep the scan order (the sort is two more launches)
 constexpr size_t kRangedMinPixels = 1u << 17;     // below this a frame is one launch and one copy
 constexpr int kPlanes = 8;                        // rgba8, radiance f32, radiance f64, object id, hit mask, ray count, hit distance, hit normal
 constexpr size_t kSmallUploadBytes = 64 << 10;    // uploads up to this size go through a kernel, not a copy engine (aux_kernels.cu)
@@ -74,6 +75,13 @@ struct rtx_ctx {
     size_t grid_blob_cap = 0;
     void* d_tail_scratch = nullptr;    // trace_kernel's tail rebalance: chain records of every CTA (allocated with the first big scene)
     size_t tail_scratch_cap = 0;
+    // scheduling hint (rtx_params.pixel_order): [tiles] order | [tiles] cost | two histograms, fill counters | cells | [tiles] key; the order
+    // belongs to the pixel space of the call that produced the costs (order_key)
+    void* d_tile_mem = nullptr;
+    size_t tile_mem_cap = 0;
+    long long order_key[6] = {};
+    bool order_valid = false;
+    int order_parity = 0;
 
     Slot slot[kSlots];
     int next_slot = 0;                 // slot the next call takes
@@ -257,6 +265,7 @@ void rtx_destroy(rtx_ctx* ctx)
     if (ctx->d_tm_sums) cudaFree(ctx->d_tm_sums);
     if (ctx->d_grid_blob) cudaFree(ctx->d_grid_blob);
     if (ctx->d_tail_scratch) cudaFree(ctx->d_tail_scratch);
+    if (ctx->d_tile_mem) cudaFree(ctx->d_tile_mem);
     for (auto& m : ctx->shared_host) {
         cudaHostUnregister(m.first);
         munmap(m.first, m.second);
@@ -717,6 +726,7 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
         return fail(ctx, RTX_ERR_INVALID, W_ + ": outputs.memory must be RTX_MEM_HOST, RTX_MEM_DEVICE or RTX_MEM_HOST_MAPPED");
     if (p.tonemap != RTX_TONEMAP_NONE && p.tonemap != RTX_TONEMAP_REINHARD) return fail(ctx, RTX_ERR_INVALID, W_ + ": unknown tonemap");
     if (p.accel != RTX_ACCEL_NONE && p.accel != RTX_ACCEL_GRID) return fail(ctx, RTX_ERR_INVALID, W_ + ": unknown accel");
+    if (p.pixel_order < RTX_ORDER_AUTO || p.pixel_order > RTX_ORDER_COST) return fail(ctx, RTX_ERR_INVALID, W_ + ": unknown pixel_order");
     const bool tonemap = p.tonemap == RTX_TONEMAP_REINHARD && outs->rgba8;
     if (tonemap && (p.n_ranks != 1 || outs->frame_rgba8 || ray_mode))
         return fail(ctx, RTX_ERR_INVALID, W_ + ": the tone-map operator needs the whole frame on one GPU (n_ranks = 1, no frame_rgba8, no ray batch)");
@@ -851,6 +861,34 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
         if (rc != RTX_OK) return rc;
     }
 
+    // Scheduling hint for the big kernel: tiles of 256 pixels are handed out most expensive first, by the ray counts the
+    // previous call with the same pixel space collected (aux_kernels.cu). Only WHEN a pixel is traced changes, nothing else.
+    const size_t tiles_all = (n_px + ((size_t{1} << kOrderTileShift) - 1)) >> kOrderTileShift, tiles_full = n_px >> kOrderTileShift;
+    const bool hint = !ray_mode && !use_grid && ctx->scene.n_entries > kSmallSceneEntries && tiles_full >= 2 &&
+                      (p.pixel_order == RTX_ORDER_COST || (p.pixel_order == RTX_ORDER_AUTO && n_px >= kOrderMinPixels));
+    bool hint_reset = false;
+    uint32_t *tile_order = nullptr, *tile_cost = nullptr, *tile_hist = nullptr;
+    const long long packed_rows = static_cast<long long>(n_frames) * local_rows;
+    const size_t order_cells = hint ? tile_order_cells(W, packed_rows) : 0;
+    if (hint) {
+        const void* before = ctx->d_tile_mem;
+        int rc = grow(ctx, &ctx->d_tile_mem, &ctx->tile_mem_cap, (3 * tiles_all + 3 * kOrderKeys + order_cells) * sizeof(uint32_t));
+        if (rc != RTX_OK) {
+            ctx->order_valid = false;
+            return rc;
+        }
+        const long long key[6] = {n_frames, W, local_rows, band_rows, p.n_ranks, p.rank};
+        if (before != ctx->d_tile_mem || std::memcmp(key, ctx->order_key, sizeof key) != 0) {
+            hint_reset = true;
+            ctx->order_valid = false;
+            ctx->order_parity = 0;
+            std::memcpy(ctx->order_key, key, sizeof key);
+        }
+        tile_order = static_cast<uint32_t*>(ctx->d_tile_mem);
+        tile_cost = tile_order + tiles_all;
+        tile_hist = tile_cost + tiles_all;                 // two histograms, the fill counters, the cells, then 16 bits of key per tile
+    }
+
     if (ray_mode) std::memcpy(sl.h_rays, rays, sizeof(rtx_ray) * n_rays);
     else std::memcpy(sl.h_cameras, cams, sizeof(rtx_camera) * n_frames);
 
@@ -898,6 +936,8 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
     a.tail_scratch = ctx->d_tail_scratch;
     a.use_grid = use_grid ? 1 : 0;
     if (use_grid) a.grid = ctx->grid;
+    a.tile_cost = tile_cost;
+    a.tile_order = hint && ctx->order_valid ? tile_order : nullptr;
 
     // ---- enqueue ----------------------------------------------------------------------------------------------------------
     cudaStream_t cs = ctx->copy_stream;
@@ -923,6 +963,10 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
     }
     // counters: [0..3] = 0, [4..6] = ~0 (atomicMin slots), [7] = 0
     RTX_ENQ(launch_reset_counters(sl.d_counters, 0ull, true, st));
+    if (hint_reset) {
+        RTX_ENQ(launch_tile_reset(tile_order, tile_cost, static_cast<int>(tiles_all), tile_hist, static_cast<int>(3 * kOrderKeys + order_cells), st));
+        launches++;
+    }
     RTX_ENQ(cudaEventRecord(sl.ev[1], st));
     // A small scene rendered into HOST memory is bound by the PCIe read-back, not by the kernel (1080p: 0.08 ms of
     // tracing, 0.15 ms of copy): trace the frame as kRanges consecutive pixel ranges and copy each finished range on a
@@ -1015,6 +1059,21 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
         RTX_ENQ(cudaMemcpyAsync(sl.h_counters, sl.d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         RTX_ENQ(cudaEventRecord(sl.ev[4], st));
         RTX_ENQ(cudaEventRecord(sl.ev_done, st));
+    }
+    if (hint) {
+        // behind everything this call waits for: the next frame's order is built while this frame's pixels leave the GPU
+        uint32_t* const now = tile_hist + ctx->order_parity * kOrderKeys;
+        uint32_t* const next = tile_hist + (ctx->order_parity ^ 1) * kOrderKeys;
+        uint32_t* const cells = tile_hist + 3 * kOrderKeys;
+        cudaError_t e = launch_tile_order(tile_cost, static_cast<int>(tiles_full), W, packed_rows, cells, reinterpret_cast<uint16_t*>(cells + order_cells),
+                                          now, next, tile_hist + 2 * kOrderKeys, tile_order, st);
+        if (e != cudaSuccess) {
+            ctx->order_valid = false;
+            return bail(e, "launch_tile_order");
+        }
+        ctx->order_parity ^= 1;
+        ctx->order_valid = true;
+        launches += 3;
     }
 #undef RTX_ENQ
     sl.pending = true;

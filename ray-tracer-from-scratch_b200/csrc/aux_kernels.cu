@@ -178,6 +178,154 @@ cudaError_t launch_reset_counters(unsigned long long* counters, unsigned long lo
     return cudaGetLastError();
 }
 
+// ---- scheduling hint: the next frame's tile order ---------------------------------------------------------------------
+// trace_kernel hands out pixels through a pool; the frame ends when the chains still in flight at the moment the pool runs
+// dry are finished. If the LAST pixels handed out are cheap ones (sky: one ray) that tail is short, so the
+// pool serves tiles of 256 pixels in descending order of what they cost in the previous frame — longest processing time
+// first. No result depends on the order. The kernel adds every finished pixel's ray count to tile_cost; three small
+// launches turn the costs into a permutation and clear them for the next frame:
+//   1. cells: the largest tile cost in every cell of a coarse grid over the packed frame (256 pixels x 32 rows);
+//   2. key of a tile = its own cost class (1/8 ray per pixel) x 4 + how expensive its surroundings are (the cells up to 3
+//      above/below and 2 to either side: >= 96 rows, >= 512 pixels) — among equally cheap tiles the ones a moving or turning
+//      camera cannot have filled with objects go last; histogram of the keys;
+//   3. counting sort, highest key first (the order inside a key is whatever the atomics give); costs and cells cleared.
+// n = the number of COMPLETE tiles: a last partial tile keeps the last place, so that pool slots and pixels cover the same
+// range.
+__device__ __forceinline__ uint32_t cost_class(uint32_t cost)
+{
+    const uint32_t b = cost >> 5;                       // 256 pixels x (1 .. depth + 1) rays
+    return b < kOrderClasses ? b : kOrderClasses - 1;
+}
+
+struct TileGrid {
+    int width;       // pixels per packed row
+    int cells_x;     // ceil(width / 256)
+    int cells_y;     // ceil(packed rows / 32)
+};
+
+__device__ __forceinline__ void tile_cell(const TileGrid& g, int tile, int& cx, int& cy)
+{
+    const long long q = (static_cast<long long>(tile) << kOrderTileShift) + (1 << (kOrderTileShift - 1));   // the tile's middle pixel
+    const long long row = q / g.width;
+    cx = static_cast<int>(q - row * g.width) >> 8;
+    cy = static_cast<int>(row >> 5);
+    if (cy >= g.cells_y) cy = g.cells_y - 1;
+}
+
+__global__ void __launch_bounds__(1024) tile_cells_kernel(const uint32_t* __restrict__ cost, int n, TileGrid g, uint32_t* cells)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int cx, cy;
+    tile_cell(g, i, cx, cy);
+    atomicMax(&cells[cy * g.cells_x + cx], cost[i]);
+}
+
+__global__ void __launch_bounds__(1024) tile_key_kernel(const uint32_t* __restrict__ cost, int n, TileGrid g,
+                                                        const uint32_t* __restrict__ cells, uint16_t* __restrict__ key,
+                                                        uint32_t* hist, uint32_t* fill)
+{
+    __shared__ uint32_t sh[kOrderKeys];
+    for (int k = threadIdx.x; k < kOrderKeys; k += blockDim.x) sh[k] = 0u;
+    if (blockIdx.x == 0)
+        for (int k = threadIdx.x; k < kOrderKeys; k += blockDim.x) fill[k] = 0u;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int cx, cy;
+        tile_cell(g, i, cx, cy);
+        uint32_t around = 0u;
+        for (int y = max(cy - 3, 0); y <= min(cy + 3, g.cells_y - 1); y++)
+            for (int x = max(cx - 2, 0); x <= min(cx + 2, g.cells_x - 1); x++) around = max(around, cells[y * g.cells_x + x]);
+        // surroundings: 0 = nothing but single-ray pixels (up to 1/8 extra ray per pixel), 1 = up to 2 rays per pixel, 2 = up to 4, 3 = more
+        const uint32_t risk = around < 288u ? 0u : around < 512u ? 1u : around < 1024u ? 2u : 3u;
+        const uint32_t k = cost_class(cost[i]) * 4u + risk;
+        key[i] = static_cast<uint16_t>(k);
+        atomicAdd(&sh[k], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kOrderKeys; k += blockDim.x)
+        if (sh[k]) atomicAdd(&hist[k], sh[k]);
+}
+
+__global__ void __launch_bounds__(1024) tile_scatter_kernel(uint32_t* __restrict__ cost, int n, const uint16_t* __restrict__ key,
+                                                            const uint32_t* __restrict__ hist, uint32_t* hist_next, uint32_t* fill,
+                                                            uint32_t* __restrict__ order, uint32_t* cells, int n_cells)
+{
+    __shared__ uint32_t start[kOrderKeys], cnt[kOrderKeys], base[kOrderKeys];
+    const int t = threadIdx.x;
+    for (int k = t; k < kOrderKeys; k += blockDim.x) {
+        base[k] = hist[k];
+        cnt[k] = 0u;
+        if (blockIdx.x == 0) hist_next[k] = 0u;                        // the other histogram of the pair, for the next frame
+    }
+    for (int c = blockIdx.x * blockDim.x + t; c < n_cells; c += gridDim.x * blockDim.x) cells[c] = 0u;
+    __syncthreads();
+    for (int k = t; k < kOrderKeys; k += blockDim.x) {
+        uint32_t s = 0u;
+        for (int b = k + 1; b < kOrderKeys; b++) s += base[b];         // descending: the keys above this one come first
+        start[k] = s;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + t;
+    int b = 0;
+    uint32_t rank = 0u;
+    if (i < n) {
+        b = key[i];
+        rank = atomicAdd(&cnt[b], 1u);
+        cost[i] = 0u;
+    }
+    __syncthreads();
+    for (int k = t; k < kOrderKeys; k += blockDim.x) base[k] = cnt[k] ? atomicAdd(&fill[k], cnt[k]) : 0u;
+    __syncthreads();
+    if (i < n) order[start[b] + base[b] + rank] = static_cast<uint32_t>(i);
+}
+
+__global__ void __launch_bounds__(256) tile_identity_kernel(uint32_t* order, uint32_t* cost, int n_all, uint32_t* hist_fill_cells, int n_aux)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_all) {
+        order[i] = static_cast<uint32_t>(i);
+        cost[i] = 0u;
+    }
+    if (i < n_aux) hist_fill_cells[i] = 0u;              // both histograms, the fill counters and the cells
+}
+
+static TileGrid tile_grid(int width, long long packed_rows)
+{
+    TileGrid g;
+    g.width = width;
+    g.cells_x = (width + 255) / 256;
+    g.cells_y = static_cast<int>((packed_rows + 31) / 32);
+    if (g.cells_y < 1) g.cells_y = 1;
+    return g;
+}
+
+size_t tile_order_cells(int width, long long packed_rows)
+{
+    const TileGrid g = tile_grid(width, packed_rows);
+    return static_cast<size_t>(g.cells_x) * g.cells_y;
+}
+
+cudaError_t launch_tile_reset(uint32_t* tile_order, uint32_t* tile_cost, int n_tiles_all, uint32_t* hist_fill_cells, int n_aux, cudaStream_t stream)
+{
+    const int n = n_tiles_all > n_aux ? n_tiles_all : n_aux;
+    tile_identity_kernel<<<(n + 255) / 256, 256, 0, stream>>>(tile_order, tile_cost, n_tiles_all, hist_fill_cells, n_aux);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tile_order(uint32_t* tile_cost, int n_tiles, int width, long long packed_rows, uint32_t* cells, uint16_t* tile_key,
+                              uint32_t* hist_now, uint32_t* hist_next, uint32_t* fill, uint32_t* tile_order, cudaStream_t stream)
+{
+    if (n_tiles <= 0) return cudaSuccess;
+    const TileGrid g = tile_grid(width, packed_rows);
+    const int blocks = (n_tiles + 1023) / 1024;
+    tile_cells_kernel<<<blocks, 1024, 0, stream>>>(tile_cost, n_tiles, g, cells);
+    tile_key_kernel<<<blocks, 1024, 0, stream>>>(tile_cost, n_tiles, g, cells, tile_key, hist_now, fill);
+    tile_scatter_kernel<<<blocks, 1024, 0, stream>>>(tile_cost, n_tiles, tile_key, hist_now, hist_next, fill, tile_order, cells, g.cells_x * g.cells_y);
+    return cudaGetLastError();
+}
+
 // ---- multi-GPU epilogue ----------------------------------------------------------------------------------
 // dst row i lives in band b = i / band_rows, owned by rank b % n_ranks, at packed local row
 // (b / n_ranks) * band_rows + i % band_rows of that rank's block.

@@ -142,7 +142,16 @@ struct TraceArgs {
     // [4] kernel start, [5] pixel pool empty, [6] first warp exit, [7] last warp exit (globaltimer ns; [4..6] start at ~0)
     unsigned long long* counters;
     void* tail_scratch;                // trace_kernel: n_sms * 1024 chain records of 104 B for the tail rebalance (may be null: off)
+    // Scheduling hint, trace_kernel only — WHICH pixel a pool slot stands for; no result depends on it:
+    // slot s is pixel tile_order[s >> 8] * 256 + (s & 255) (tiles of kOrderTile consecutive packed pixels, most expensive
+    // first), and tile_cost[t] collects the rays traced for tile t's pixels — the next frame's order is built from it.
+    const uint32_t* tile_order;        // may be null: slot s = pixel s
+    uint32_t* tile_cost;               // may be null
 };
+
+constexpr int kOrderTileShift = 8;     // 256 pixels per tile
+constexpr int kOrderClasses = 128;     // cost classes of a tile: cost >> 5
+constexpr int kOrderKeys = 4 * kOrderClasses;   // counting sort of the tiles by (cost class, how expensive the surroundings are)
 
 constexpr size_t kTailScratchBytesPerCta = 1024 * 104;
 
@@ -200,9 +209,9 @@ constexpr int kSmallSceneEntries = 16;   // scenes of at most this many screen e
 // Per-context (= per-device) launch state of the trace kernels: cudaFuncAttributeMaxDynamicSharedMemorySize is a
 // per-device attribute, so what has been raised is remembered per context, not per thread or per process.
 struct TraceLaunchState {
-    size_t smem_set[2] = {0, 0};       // largest dynamic shared-memory size requested so far: resident / streamed kernel
+    bool smem_opt_in = false;          // trace_kernel<*>: the opt-in to > 48 KB of dynamic shared memory has been made by this context
     int small_per_sm = 0;              // resident CTAs per SM of trace_small_kernel (occupancy query, once)
-    size_t smem_grid = 0;              // trace_grid_kernel (extension)
+    bool smem_opt_in_grid = false;     // trace_grid_kernel (extension)
     int grid_per_sm = 0;
 };
 
@@ -219,6 +228,10 @@ cudaError_t launch_tonemap_apply(const float* rad32, const double* rad64, int64_
                                  int64_t pixels_global, double key, double white, int mode, uint32_t* rgba8, unsigned long long* counters,
                                  int n_sms, cudaStream_t stream);
 cudaError_t launch_small_upload(void* dst, const void* src_host_mapped, size_t bytes, cudaStream_t stream);
+size_t tile_order_cells(int width, long long packed_rows);
+cudaError_t launch_tile_reset(uint32_t* tile_order, uint32_t* tile_cost, int n_tiles_all, uint32_t* hist_fill_cells, int n_aux, cudaStream_t stream);
+cudaError_t launch_tile_order(uint32_t* tile_cost, int n_tiles, int width, long long packed_rows, uint32_t* cells, uint16_t* tile_key,
+                              uint32_t* hist_now, uint32_t* hist_next, uint32_t* fill, uint32_t* tile_order, cudaStream_t stream);
 cudaError_t launch_reset_counters(unsigned long long* counters, unsigned long long first_pixel, bool all, cudaStream_t stream);
 cudaError_t launch_unpermute(const void* band_major, void* row_major, int height, int width, int elem_bytes,
                              int band_rows, int n_ranks, int rows_per_rank, int n_sms, cudaStream_t stream);

@@ -283,8 +283,8 @@ __device__ __forceinline__ void fill_tile(float4* tile, int plane_pairs, const f
 }
 
 // Out-of-line wrappers for the big kernel (its chains live in local memory; the hot loop should stay small).
-__device__ __noinline__ void shade_chain(Chain& c, const TraceArgs& a, FrameTotals& tot) { shade_body(c, a, a.scene, tot); }
-__device__ __noinline__ void start_pixel(Chain& c, unsigned long long p, const TraceArgs& a) { start_pixel_body(c, p, a); }
+__device__ __noinline__ void shade_chain(Chain& c, const TraceArgs& a, FrameTotals& tot) { shade_body<true>(c, a, a.scene, tot); }
+__device__ __noinline__ void start_pixel(Chain& c, unsigned long long p, const TraceArgs& a) { start_pixel_body<true>(c, p, a); }
 
 // ---- small scenes ---------------------------------------------------------------------------------------------------
 // A handful of objects (the reference's own scene has three) needs no screen: the frame is bound by the double
@@ -728,23 +728,19 @@ cudaError_t launch_trace(const TraceArgs& args, int n_sms, cudaStream_t stream, 
     }
     unsigned long long blocks = (total + kThreads * kChains - 1) / (kThreads * kChains);
     if (blocks > static_cast<unsigned long long>(n_sms)) blocks = n_sms;
-    cudaError_t err;
-    size_t* const smem_set = state->smem_set;          // the attribute is sticky per function AND device: raise it only when needed
-    if (stream_tiles) {
-        if (smem > smem_set[1]) {
-            err = cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            if (err != cudaSuccess) return err;
-            smem_set[1] = smem;
-        }
-        trace_kernel<true><<<static_cast<unsigned>(blocks), kThreads, smem, stream>>>(args, tile_pairs, nullptr);
-    } else {
-        if (smem > smem_set[0]) {
-            err = cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            if (err != cudaSuccess) return err;
-            smem_set[0] = smem;
-        }
-        trace_kernel<false><<<static_cast<unsigned>(blocks), kThreads, smem, stream>>>(args, tile_pairs, kTailRebalance ? static_cast<ChainDump*>(args.tail_scratch) : nullptr);
+    // cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (function, device) pair of the PROCESS, not to a context. It is
+    // only an upper limit, so every context sets the same maximum once. (Raising it "when needed" per context let a second
+    // context with a small scene lower it under the first one's feet: cudaErrorInvalidValue at the big scene's next launch.)
+    if (!state->smem_opt_in) {
+        cudaError_t err = cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+        if (err != cudaSuccess) return err;
+        state->smem_opt_in = true;
     }
+    if (stream_tiles)
+        trace_kernel<true><<<static_cast<unsigned>(blocks), kThreads, smem, stream>>>(args, tile_pairs, nullptr);
+    else
+        trace_kernel<false><<<static_cast<unsigned>(blocks), kThreads, smem, stream>>>(args, tile_pairs, kTailRebalance ? static_cast<ChainDump*>(args.tail_scratch) : nullptr);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

@@ -190,10 +190,10 @@ cudaError_t launch_trace_grid(const TraceArgs& args, int n_sms, cudaStream_t str
     const size_t need = static_cast<size_t>(args.scene.n_entries_padded) * sizeof(float4) + (cs_words + item_words) * 4 + 16;
     const int in_smem = need <= static_cast<size_t>(227 * 1024) ? 1 : 0;
     const size_t smem = in_smem ? need : 0;
-    if (smem > state->smem_grid) {
-        cudaError_t e = cudaFuncSetAttribute(trace_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (!state->smem_opt_in_grid) {      // per (function, device) of the process: the same maximum from every context, once (see launch_trace)
+        cudaError_t e = cudaFuncSetAttribute(trace_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        state->smem_grid = smem;
+        state->smem_opt_in_grid = true;
     }
     int per_sm = 1;
     if (!in_smem) {

@@ -53,6 +53,13 @@ def test_c3_full_4k_frame_matches_reference(gpu, renderer_mod, S):
     check_against_fullsize(planes, st, g, np.array(g["rows"]))
     assert st.total_rays == g["total_rays"]
     assert st.over_range_pixels == sum(g["row_over_range"])
+    # the scheduling hint (rtx_params.pixel_order): scan order, then twice in the order of the previous frame's costs —
+    # the same frame against the same reference CRCs every time
+    for order in (renderer_mod.abi.RTX_ORDER_SCAN, renderer_mod.abi.RTX_ORDER_COST, renderer_mod.abi.RTX_ORDER_COST):
+        planes, st = gpu.render([S.default_camera(3840, 16.0 / 9.0).pod()], renderer_mod.default_params(max_depth=10, pixel_order=order),
+                                want=("rgba8", "ray_count", "object_id"))
+        check_against_fullsize(planes, st, g, np.array(g["rows"]))
+        assert st.total_rays == g["total_rays"] and st.over_range_pixels == sum(g["row_over_range"])
 
 
 def test_c4_8k_bands_and_properties(gpu, renderer_mod, S):
@@ -77,7 +84,7 @@ def test_c4_8k_bands_and_properties(gpu, renderer_mod, S):
         total += sr.total_rays
     assert total == st.total_rays
     # the separate quantise kernel on the double radiance gives the fused result
-    unf, su = gpu.render([pod], renderer_mod.default_params(max_depth=10, fuse_quantise=0), want=("rgba8",))
+    unf, su = gpu.render([pod], renderer_mod.default_params(max_depth=10, fuse_quantise=0, pixel_order=renderer_mod.abi.RTX_ORDER_SCAN), want=("rgba8",))
     assert np.array_equal(unf["rgba8"], full["rgba8"]) and su.launches == 2
 
 

@@ -692,3 +692,23 @@ def test_device_frame_buffer_alloc_store_read(gpu, renderer_mod, port, S):
         assert np.array_equal(got, port.render(scene, pod, 7, want=("rgba8",))["rgba8"])
     finally:
         gpu.buffer_free(ptr)
+
+
+def test_two_contexts_on_one_device_do_not_lower_each_others_shared_memory_limit(renderer_mod, S):
+    """The opt-in to > 48 KB of dynamic shared memory belongs to (kernel, device) of the process, not to a context: a second
+    context with a small scene once lowered it, and the first context's next big-scene launch failed (cudaErrorInvalidValue).
+    Brute force and grid kernels, big scene / small scene / big scene again."""
+    big, small = S.synthetic_scene(6000, 32, seed=3), S.synthetic_scene(40, 4, seed=3)
+    pod = S.default_camera(64, 16.0 / 9.0).pod()
+    a, b = renderer_mod.Renderer(0), renderer_mod.Renderer(0)
+    try:
+        a.set_scene(big)
+        b.set_scene(small)
+        for accel in (0, 1):
+            first, _ = a.render([pod], renderer_mod.default_params(max_depth=4, accel=accel), want=("rgba8",))
+            b.render([pod], renderer_mod.default_params(max_depth=4, accel=accel), want=("rgba8",))
+            again, _ = a.render([pod], renderer_mod.default_params(max_depth=4, accel=accel), want=("rgba8",))
+            assert np.array_equal(first["rgba8"], again["rgba8"])
+    finally:
+        a.close()
+        b.close()
