@@ -134,19 +134,27 @@ struct TraceArgs {
     double* hit_distance;              // primary ray: Collision.distance (DBL_MAX on a miss, main.cpp:70)
     double* hit_normal;                // primary ray: Collision.normal as returned, (0,0,0) on a miss
     int32_t frame_offset, frame_stride;
-    // Pixel range of this launch in the packed pixel space [n_frames][local_rows][width]; pixel_end = 0 means all.
-    // rtx_render launches a small scene as a few consecutive ranges so that the read-back of one range overlaps the
-    // tracing of the next (counters[0] is preset to pixel_begin by the host).
-    unsigned long long pixel_begin, pixel_end;
+    // One 16-byte slot, two readings (keeping sizeof(TraceArgs) where it was: the kernel copies the argument block to its
+    // stack, and 16 more bytes there reshuffled ptxas' choices in trace_kernel's hot loop, +0.3 % frame time):
+    union {
+        // trace_small_kernel — pixel range of this launch in the packed pixel space [n_frames][local_rows][width];
+        // pixel_end = 0 means all. rtx_render launches a small scene as a few consecutive ranges so that the read-back of one
+        // range overlaps the tracing of the next (counters[0] is preset to pixel_begin by the host).
+        struct {
+            unsigned long long pixel_begin, pixel_end;
+        };
+        // trace_kernel — scheduling hint; WHICH pixel a pool slot stands for, no result depends on it:
+        // slot s is pixel tile_order[s >> 8] * 256 + (s & 255) (tiles of 256 consecutive packed pixels, most expensive
+        // first), and tile_cost[t] collects the rays traced for tile t's pixels — the next frame's order is built from it.
+        struct {
+            const uint32_t* tile_order;    // may be null: slot s = pixel s
+            uint32_t* tile_cost;           // may be null
+        };
+    };
     // counters: [0] next pixel, [1] total rays, [2] over-range pixels, [3] max luminance (double bits),
     // [4] kernel start, [5] pixel pool empty, [6] first warp exit, [7] last warp exit (globaltimer ns; [4..6] start at ~0)
     unsigned long long* counters;
     void* tail_scratch;                // trace_kernel: n_sms * 1024 chain records of 104 B for the tail rebalance (may be null: off)
-    // Scheduling hint, trace_kernel only — WHICH pixel a pool slot stands for; no result depends on it:
-    // slot s is pixel tile_order[s >> 8] * 256 + (s & 255) (tiles of kOrderTile consecutive packed pixels, most expensive
-    // first), and tile_cost[t] collects the rays traced for tile t's pixels — the next frame's order is built from it.
-    const uint32_t* tile_order;        // may be null: slot s = pixel s
-    uint32_t* tile_cost;               // may be null
 };
 
 constexpr int kOrderTileShift = 8;     // 256 pixels per tile

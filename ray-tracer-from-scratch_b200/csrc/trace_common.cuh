@@ -25,7 +25,7 @@ constexpr int kQueue = RTX_QUEUE_CAP; // screen survivors buffered per chain bef
 #endif
 constexpr int kCoopMax = RTX_COOP_MAX;   // cooperative drain when a warp has at most this many live chains (0 = off)
 #ifndef RTX_TILE_ORDER
-#define RTX_TILE_ORDER 1      // 0: the tile-order scheduling hint compiled out (A/B builds)
+#define RTX_TILE_ORDER 3      // scheduling hint: bit 0 = slot -> pixel mapping, bit 1 = cost collection; 0 compiles it out (A/B builds)
 #endif
 #ifndef RTX_MBOX_CAP
 #define RTX_MBOX_CAP 96
@@ -348,7 +348,7 @@ __device__ __forceinline__ void shade_body(Chain& c, const TraceArgs& a, const S
         if (a.object_id) a.object_id[p] = c.first_id;
         if (a.hit_mask) a.hit_mask[p] = c.first_id >= 0 ? 1 : 0;
         if (a.ray_count) a.ray_count[p] = static_cast<uint8_t>(c.rays);
-        if (RTX_TILE_ORDER && ORDER && a.tile_cost) atomicAdd(&a.tile_cost[p >> kOrderTileShift], static_cast<uint32_t>(c.rays));
+        if ((RTX_TILE_ORDER & 2) && ORDER && a.tile_cost) atomicAdd(&a.tile_cost[p >> kOrderTileShift], static_cast<uint32_t>(c.rays));
         tot.rays += static_cast<unsigned long long>(c.rays);
         if (over_range(c.acc.x, c.acc.y, c.acc.z)) tot.over++;
         const double lum = (c.acc.x + c.acc.y + c.acc.z) * (1.0 / 3.0);
@@ -362,7 +362,7 @@ template <bool ORDER = false>
 __device__ __forceinline__ void start_pixel_body(Chain& c, unsigned long long p, const TraceArgs& a)
 {
     using namespace ex;
-    if (RTX_TILE_ORDER && ORDER && a.tile_order) {
+    if ((RTX_TILE_ORDER & 1) && ORDER && a.tile_order) {
         // scheduling hint: pool slot -> pixel, tiles in descending order of the previous frame's cost (a permutation of the
         // tiles in which a last, partial tile keeps its place, so slots and pixels cover the same range)
         p = (static_cast<unsigned long long>(a.tile_order[p >> kOrderTileShift]) << kOrderTileShift) | (p & ((1ull << kOrderTileShift) - 1ull));
