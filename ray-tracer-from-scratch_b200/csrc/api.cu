@@ -944,6 +944,8 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
     auto bail = [&](cudaError_t e, const char* what) {
         cudaStreamSynchronize(st);
         cudaStreamSynchronize(cs);
+        ctx->order_valid = false;      // the scheduling hint starts over: its counters may be half-way through a frame
+        ctx->order_key[0] = -1;
         return cuda_fail(ctx, e, what);
     };
 #define RTX_ENQ(call)                                        \
@@ -1067,10 +1069,7 @@ int render_impl(rtx_ctx* ctx, const rtx_camera* cams, int32_t n_frames, const rt
         uint32_t* const cells = tile_hist + 3 * kOrderKeys;
         cudaError_t e = launch_tile_order(tile_cost, static_cast<int>(tiles_full), W, packed_rows, cells, reinterpret_cast<uint16_t*>(cells + order_cells),
                                           now, next, tile_hist + 2 * kOrderKeys, tile_order, st);
-        if (e != cudaSuccess) {
-            ctx->order_valid = false;
-            return bail(e, "launch_tile_order");
-        }
+        if (e != cudaSuccess) return bail(e, "launch_tile_order");
         ctx->order_parity ^= 1;
         ctx->order_valid = true;
         launches += 3;

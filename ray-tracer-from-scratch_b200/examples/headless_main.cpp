@@ -9,7 +9,7 @@
 //
 //   rtx_headless [--width 640] [--aspect 1] [--depth 10] [--frames 3] [--keys wwad] [--out frame.ppm] [--raw frame.rgba]
 //                [--png frame.png] [--sun 1] [--tonemap 1] [--box 1] [--devices 0,1,...] [--band-rows 4] [--scene default|synthetic]
-//                [--accel 1] [--to-device 1]
+//                [--accel 1] [--to-device 1] [--pixel-order 0|1|2]   (RTX_ORDER_AUTO / _SCAN / _COST)
 // --devices: more than one entry renders every frame on several GPUs from THIS process (rtx::ShardedRenderer: one context
 // and one host thread per GPU, cyclic row bands, every kernel storing its pixels straight into one pinned host surface);
 // a device may be repeated (0,0 = two contexts on one GPU). --scene synthetic = the 10 064-object scene of configs C3/C4.
@@ -135,6 +135,7 @@ int main(int argc, char* argv[])
     double aspect = 1.0;   // ASPECT_RATIO = 4/3 is integer division = 1 in the reference (main.cpp:25)
     std::string keys, out_ppm = "frame.ppm", out_raw, out_png;
     bool ext_sun = false, ext_tonemap = false, ext_box = false, accel = false, to_device = false;
+    int pixel_order = RTX_ORDER_AUTO;
     std::vector<int> devices = {0};
     int band_rows = 4;
     std::string scene_name = "default";
@@ -152,6 +153,7 @@ int main(int argc, char* argv[])
         else if (a == "--tonemap") ext_tonemap = std::atoi(argv[k + 1]) != 0;
         else if (a == "--box") ext_box = std::atoi(argv[k + 1]) != 0;
         else if (a == "--accel") accel = std::atoi(argv[k + 1]) != 0;
+        else if (a == "--pixel-order") pixel_order = std::atoi(argv[k + 1]);
         else if (a == "--to-device") to_device = std::atoi(argv[k + 1]) != 0;
         else if (a == "--band-rows") band_rows = std::atoi(argv[k + 1]);
         else if (a == "--scene") scene_name = argv[k + 1];
@@ -200,6 +202,7 @@ int main(int argc, char* argv[])
             sharded.params.max_depth = depth;
             if (ext_sun) sharded.params.sun_enabled = 1;
             if (accel) sharded.params.accel = RTX_ACCEL_GRID;
+            sharded.params.pixel_order = pixel_order;
             std::vector<int64_t> rt_times;
             const uint32_t* pixels = nullptr;
             for (int frame = 0; frame < frames; frame++) {
@@ -225,6 +228,7 @@ int main(int argc, char* argv[])
         Renderer renderer(devices[0]);
         renderer.params.max_depth = depth;
         if (accel) renderer.params.accel = RTX_ACCEL_GRID;
+        renderer.params.pixel_order = pixel_order;
         if (ext_sun) renderer.params.sun_enabled = 1;
         if (ext_tonemap) {
             renderer.params.tonemap = RTX_TONEMAP_REINHARD;
