@@ -321,7 +321,8 @@ int rtx_quantise(rtx_ctx* ctx, const float* radiance_f32, const double* radiance
  * frames of pixels_per_frame RGB triples (exactly one of radiance_f32 / radiance_f64 non-NULL), memory = RTX_MEM_*.
  * params->tonemap must be RTX_TONEMAP_REINHARD. log_avg_luminance (HOST pointer, may be NULL) receives the n_frames
  * log-average luminances the operator used. The statistic is accumulated in fixed point with integer atomics, so the
- * output is identical from run to run. */
+ * output is identical from run to run. A float buffer is processed in single precision (luminance, logf, the map; the
+ * per-frame constants and the 8-bit pack stay double) — the specification's rgb32 branch — a double buffer in double. */
 int rtx_tonemap(rtx_ctx* ctx, const float* radiance_f32, const double* radiance_f64, int64_t pixels_per_frame, int32_t n_frames,
                 const rtx_params* params, uint32_t* rgba8, int32_t memory, double* log_avg_luminance, rtx_stats* stats);
 

@@ -488,11 +488,19 @@ void orc_quantise_f32(const float* rgb, int64_t n, int32_t mode, uint32_t* out)
  *   sum  = sum over the frame of llrint(log(1e-4 + L) * 2^32)      (32.32 fixed point: order independent)
  *   Lavg = exp(((double)sum / 2^32) / n);  Ls = key / Lavg * L;  Ld = Ls (1 + Ls / white^2) / (1 + Ls)  [white <= 0: no term]
  *   rgb *= Ld / L (0 where L <= 0)
- * Exactly one of rgb64 / rgb32 is non-NULL; log_avg (may be NULL) receives Lavg per frame. */
+ * Exactly one of rgb64 / rgb32 is non-NULL; log_avg (may be NULL) receives Lavg per frame.
+ * FLOAT radiance (rgb32) is processed in FLOAT — luminance, logf, Ls, Ld and the scale are single-precision operations, one
+ * rounding each (this file is compiled with -ffp-contract=off); the per-frame constants (Lavg, key / Lavg, 1 / white^2) are
+ * computed in double and rounded to float once; the scaled channels go to the 8-bit pack as doubles. */
 static double tm_lum(double r, double g, double b)
 {
     double l = 0.2126 * r + 0.7152 * g + 0.0722 * b;
     return l > 0.0 ? l : 0.0;
+}
+static float tm_lum_f(float r, float g, float b)
+{
+    float l = (0.2126f * r + 0.7152f * g) + 0.0722f * b;
+    return l > 0.0f ? l : 0.0f;
 }
 /* Step 1: ADDS the fixed-point sums of this buffer's frames to sums[n_frames]. */
 void orc_tonemap_sums(const double* rgb64, const float* rgb32, int64_t pixels, int32_t n_frames, int64_t* sums)
@@ -501,10 +509,12 @@ void orc_tonemap_sums(const double* rgb64, const float* rgb32, int64_t pixels, i
     for (int32_t f = 0; f < n_frames; f++) {
         const int64_t base = (int64_t)f * pixels;
         long long sum = 0;
-        for (int64_t k = base; k < base + pixels; k++) {
-            double r = rgb64 ? rgb64[3 * k] : (double)rgb32[3 * k], g = rgb64 ? rgb64[3 * k + 1] : (double)rgb32[3 * k + 1],
-                   b = rgb64 ? rgb64[3 * k + 2] : (double)rgb32[3 * k + 2];
-            sum += llrint(log(1e-4 + tm_lum(r, g, b)) * fix);
+        if (rgb32) {
+            for (int64_t k = base; k < base + pixels; k++)
+                sum += llrintf(logf(1e-4f + tm_lum_f(rgb32[3 * k], rgb32[3 * k + 1], rgb32[3 * k + 2])) * 4294967296.0f);
+        } else {
+            for (int64_t k = base; k < base + pixels; k++)
+                sum += llrint(log(1e-4 + tm_lum(rgb64[3 * k], rgb64[3 * k + 1], rgb64[3 * k + 2])) * fix);
         }
         sums[f] += sum;
     }
@@ -522,9 +532,21 @@ void orc_tonemap_apply(const double* rgb64, const float* rgb32, int64_t pixels, 
         const double key_over_avg = p->tonemap_key / lavg;
         const double inv_white2 = p->tonemap_white > 0.0 ? 1.0 / (p->tonemap_white * p->tonemap_white) : 0.0;
         if (log_avg) log_avg[f] = lavg;
+        if (rgb32) {
+            const float koa = (float)key_over_avg, iw2 = (float)inv_white2;
+            for (int64_t k = base; k < base + pixels; k++) {
+                float r = rgb32[3 * k], g = rgb32[3 * k + 1], b = rgb32[3 * k + 2];
+                float l = tm_lum_f(r, g, b);
+                float ls = koa * l;
+                float ld = (ls * (1.0f + ls * iw2)) / (1.0f + ls);
+                float s = l > 0.0f ? ld / l : 0.0f;
+                float R = r * s, G = g * s, B = b * s;
+                out[k] = pack_rgba(mk((double)R, (double)G, (double)B), p->quantise_mode);
+            }
+            continue;
+        }
         for (int64_t k = base; k < base + pixels; k++) {
-            double r = rgb64 ? rgb64[3 * k] : (double)rgb32[3 * k], g = rgb64 ? rgb64[3 * k + 1] : (double)rgb32[3 * k + 1],
-                   b = rgb64 ? rgb64[3 * k + 2] : (double)rgb32[3 * k + 2];
+            double r = rgb64[3 * k], g = rgb64[3 * k + 1], b = rgb64[3 * k + 2];
             double l = tm_lum(r, g, b);
             double ls = key_over_avg * l;
             double ld = (ls * (1.0 + ls * inv_white2)) / (1.0 + ls);

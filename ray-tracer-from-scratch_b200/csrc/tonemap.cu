@@ -11,6 +11,11 @@
 // atomic per warp for the global statistic. The statistic is accumulated in 32.32 FIXED POINT with integer atomics:
 // integer addition is associative, so the frame's log-average — and with it every pixel — is identical from run to
 // run whatever the order in which warps finish (a floating-point atomicAdd would not be).
+//
+// FLOAT radiance (rtx_tonemap / rtx_tonemap_sums / _apply on an f32 buffer) is processed in FLOAT: luminance, logf, the map
+// and the scale are single-precision operations with every rounding spelled out (the specification says so: oracle.c,
+// branch rgb32), only the per-frame constants (exp of the mean, key / Lavg) and the 8-bit pack stay double. With double
+// log / divide per pixel the f32 kernels were bound by the FP64 pipe at 46 % of the HBM roofline.
 #include <algorithm>
 
 #include "rtx_device.cuh"
@@ -32,6 +37,17 @@ __device__ __forceinline__ double luminance(double r, double g, double b)
 __device__ __forceinline__ long long log_fixed(double r, double g, double b)
 {
     return __double2ll_rn(ex::mul(log(ex::add(1e-4, luminance(r, g, b))), kFix));
+}
+
+__device__ __forceinline__ float luminance_f(float r, float g, float b)
+{
+    const float l = __fadd_rn(__fadd_rn(__fmul_rn(0.2126f, r), __fmul_rn(0.7152f, g)), __fmul_rn(0.0722f, b));
+    return l > 0.0f ? l : 0.0f;
+}
+
+__device__ __forceinline__ long long log_fixed(float r, float g, float b)
+{
+    return __float2ll_rn(__fmul_rn(logf(__fadd_rn(1e-4f, luminance_f(r, g, b))), 4294967296.0f));
 }
 
 struct MapConsts {
@@ -68,16 +84,37 @@ __device__ __forceinline__ uint32_t map_pixel(PackStats& s, const MapConsts& c, 
     return word;
 }
 
+// float radiance: the map in single precision (see the header comment); pack and statistics as for doubles
+__device__ __forceinline__ uint32_t map_pixel(PackStats& s, const MapConsts& c, float r, float g, float b, int mode)
+{
+    const float koa = static_cast<float>(c.key_over_avg), iw2 = static_cast<float>(c.inv_white2);
+    const float l = luminance_f(r, g, b);
+    const float ls = __fmul_rn(koa, l);
+    const float ld = __fdiv_rn(__fmul_rn(ls, __fadd_rn(1.0f, __fmul_rn(ls, iw2))), __fadd_rn(1.0f, ls));
+    const float k = l > 0.0f ? __fdiv_rn(ld, l) : 0.0f;
+    const double R = __fmul_rn(r, k), G = __fmul_rn(g, k), B = __fmul_rn(b, k);
+    bool over;
+    const uint32_t word = pack_rgba_flag(R, G, B, mode, over);
+    if (over) s.over++;
+    const double lum = (R + G + B) * (1.0 / 3.0);
+    if (lum > s.maxlum) s.maxlum = lum;
+    return word;
+}
+
+// Working type of a radiance type: float stays float, double stays double.
+template <typename T> struct Work { using type = double; };
+template <> struct Work<float> { using type = float; };
+
 // Four pixels (12 channels) of frame-relative quad q. VEC: 128-bit loads (the frame's base is 16-byte aligned).
 template <typename T, bool VEC>
-__device__ __forceinline__ void load_quad(const T* __restrict__ frame, long long q, double (&v)[12])
+__device__ __forceinline__ void load_quad(const T* __restrict__ frame, long long q, typename Work<T>::type (&v)[12])
 {
     if constexpr (VEC && sizeof(T) == 4) {
         const float4* in4 = reinterpret_cast<const float4*>(frame);
         const float4 a = __ldcs(&in4[3 * q]), b = __ldcs(&in4[3 * q + 1]), c = __ldcs(&in4[3 * q + 2]);
-        const float f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-#pragma unroll
-        for (int k = 0; k < 12; k++) v[k] = f[k];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
     } else if constexpr (VEC) {
         const double2* in2 = reinterpret_cast<const double2*>(frame);
 #pragma unroll
@@ -88,7 +125,7 @@ __device__ __forceinline__ void load_quad(const T* __restrict__ frame, long long
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < 12; k++) v[k] = static_cast<double>(frame[12 * q + k]);
+        for (int k = 0; k < 12; k++) v[k] = frame[12 * q + k];
     }
 }
 
@@ -100,7 +137,7 @@ __global__ void __launch_bounds__(256) tonemap_logsum_kernel(const T* __restrict
     long long acc = 0;
     for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < n_quads;
          q += static_cast<long long>(gridDim.x) * blockDim.x) {
-        double v[12];
+        typename Work<T>::type v[12];
         load_quad<T, VEC>(frame, q, v);
 #pragma unroll
         for (int k = 0; k < 4; k++) acc += log_fixed(v[3 * k], v[3 * k + 1], v[3 * k + 2]);
@@ -129,7 +166,7 @@ __global__ void __launch_bounds__(256) tonemap_pack_kernel(const T* __restrict__
     const long long n_quads = pixels >> 2;
     for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < n_quads;
          q += static_cast<long long>(gridDim.x) * blockDim.x) {
-        double v[12];
+        typename Work<T>::type v[12];
         load_quad<T, VEC>(frame, q, v);
         uint4 o;
         o.x = map_pixel(st, c, v[0], v[1], v[2], mode);

@@ -108,7 +108,8 @@ def test_standalone_tonemap(gpu, port, pkg, dtype, pixels, frames, white, mode):
     p.tonemap, p.tonemap_white, p.quantise_mode = pkg.abi.RTX_TONEMAP_REINHARD, white, mode
     got, lavg = gpu.tonemap(rgb, p)
     exp, lavg_exp = port.tonemap(rgb, p)
-    assert np.allclose(lavg, lavg_exp, rtol=1e-12)                        # same fixed-point sum up to a few ulps of log()
+    # the same fixed-point sum up to a few ulps of log() (double radiance) / logf() (float radiance: processed in float)
+    assert np.allclose(lavg, lavg_exp, rtol=1e-12 if rgb.dtype == np.float64 else 1e-6)
     d = _lsb(got, exp)
     assert d.max() <= 1 and (d > 0).mean() < 1e-3
     got2, lavg2 = gpu.tonemap(rgb, p)                                      # integer atomics: run-to-run identical
