@@ -54,6 +54,19 @@ def test_struct_sizes_match_header(pkg, tmp_path):
             assert int(got["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
 
 
+def test_constants_match_header(pkg):
+    """Every integer #define of the header that abi.py mirrors has the header's value (RTX_ORDER_*, RTX_ACCEL_*, RTX_MEM_*, ...)."""
+    header = open(os.path.join(ROOT, "include", "rtx_b200.h")).read()
+    defines = {k: int(v, 0) for k, v in re.findall(r"^#define\s+(RTX_[A-Z0-9_]+)\s+(-?(?:0x[0-9a-fA-F]+|\d+))\b", header, re.M)}
+    mirrored = [k for k in defines if hasattr(pkg.abi, k)]
+    assert len(mirrored) >= 20, mirrored
+    for k in mirrored:
+        assert getattr(pkg.abi, k) == defines[k], k
+    for k in ("RTX_ORDER_AUTO", "RTX_ORDER_SCAN", "RTX_ORDER_COST", "RTX_ACCEL_GRID", "RTX_MEM_HOST_MAPPED", "RTX_FRAME_COPY", "RTX_MAX_IN_FLIGHT"):
+        assert k in mirrored, k
+    assert defines["RTX_ABI_VERSION"] == pkg.abi.ABI_VERSION
+
+
 def test_no_cpu_fallback(lib, pkg):
     """Without a GPU the product path must fail loudly instead of computing anything on the host."""
     import torch
